@@ -1,0 +1,18 @@
+// agogo_b200 — tcgen05/TMEM/TMA residual tower (K5) interface.
+#pragma once
+#include "nn.cuh"
+
+struct TcTower {
+  bool ready = false;
+  void* impl = nullptr;
+};
+// shapes the tensor-core tower handles (K multiple of 64, board fits the padded tiling); smaller
+// nets (tic-tac-toe K=3, Connect-4 K=16) run on the fp32 CUDA-core kernels.
+bool tc_tower_supported(const NetDims& d);
+void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2);
+void tc_tower_free(TcTower& t);
+// split/scale/reorder the snapshot's filters and BN affines into the tensor-core operand layout
+void tc_tower_prepare(TcTower& t, const NetLayout& L, const Snapshot& s, cudaStream_t st, unsigned long long* launches);
+void tc_tower_forward(TcTower& t, const NetLayout& L, const Snapshot& s, Fp32Scratch& sc, const float* planes,
+                      const int* n_dev, int n_max, float* policy, int ldp, float* value, int* err_flag, cudaStream_t st,
+                      unsigned long long* launches);

@@ -148,7 +148,7 @@ struct Arena {
   // arena.go:80-179, split at the loop boundaries so the C API can run many games in lockstep;
   // Play() is exactly playBegin + playStep* + playFinish.  (The reference always returns None
   // as the winner, arena.go:178; the real winner is kept in the GameRecord.)
-  bool active = false, record = false;
+  bool active = false, record = false, lastEnded = false;  // lastEnded: the loop condition's last Ended()
   Player winner = None;
   int passCount = 0;
   GameRecord rec;
@@ -160,7 +160,8 @@ struct Arena {
     else { A.player = White; B.player = Black; currentPlayer = &B; }
     rec.a_player = A.player;
     game->SetToMove(currentPlayer->player);
-    active = !game->Ended(&winner);
+    lastEnded = game->Ended(&winner);
+    active = !lastEnded;
   }
   void searchBegin() { currentPlayer->mcts->SetGame(game); currentPlayer->mcts->SearchBegin(currentPlayer->player); }
   void searchRun(int n) { currentPlayer->mcts->SearchRun(n); }
@@ -177,9 +178,10 @@ struct Arena {
     game = apply_replace(game, PlayerMove{currentPlayer->player, best}, true);
     rec.moves.push_back(best);
     switchPlayer();
-    if (passCount >= 2) { active = false; return; }
-    if (max_moves > 0 && (int)rec.moves.size() >= max_moves) { active = false; return; }  // COMPLETION
-    active = !game->Ended(&winner);
+    if (passCount >= 2) { active = false; lastEnded = false; return; }
+    if (max_moves > 0 && (int)rec.moves.size() >= max_moves) { active = false; lastEnded = false; return; }  // COMPLETION
+    lastEnded = game->Ended(&winner);
+    active = !lastEnded;
   }
   bool playStep() { searchBegin(); searchRun(conf.Sims); searchEnd(); return active; }
   std::vector<Example> playFinish() {  // arena.go:139-178

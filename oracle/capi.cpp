@@ -268,11 +268,9 @@ int az_game_state(const az_engine* e, int32_t game, int32_t* board, int32_t cap,
   if (to_move) *to_move = s->ToMove();
   if (move_number) *move_number = s->MoveNumber();
   if (passes) *passes = s->Passes();
-  Player w = None;
-  bool en = false;
-  try { en = s->Ended(&w); } catch (...) {}
-  if (ended) *ended = en;
-  if (winner) *winner = w;
+  // ended/winner: what Arena.Play's loop condition last saw (arena.go:96)
+  if (ended) *ended = e->slots[game]->lastEnded;
+  if (winner) *winner = e->slots[game]->winner;
   return AZ_OK;
 }
 int az_examples_count(const az_engine* e, int64_t* n) { *n = (int64_t)e->examples.size(); return AZ_OK; }

@@ -137,3 +137,23 @@ def assert_same_run(a, b, what=""):
     assert a["stats"] == b["stats"], (what, a["stats"], b["stats"])
     for k in ("searches", "sims", "null_results", "evals", "select_children", "select_levels", "created", "backup_nodes"):
         assert a["counters"][k] == b["counters"][k], (what, k, a["counters"], b["counters"])
+
+
+def tame_gammas(engines, net, seed, target=0.9):
+    """Random-init `net` identically in all engines, then rescale every BatchNorm scale tensor so that
+    gamma/sqrt(eps) has std `target`.  With the reference's init (GlorotN over the full [B,C,H,W]
+    shape) and its test-mode BN (x/sqrt(eps)) the per-layer gain is
+    316*sqrt(2/((B+C)*H*W)), which only stays O(1) for the large configs; tiny test nets would
+    overflow to inf/NaN in oracle and engine alike, which pins nothing."""
+    e0 = engines[0]
+    e0.net_init(net, seed)
+    p = e0.net_get(net)
+    nt, _ = e0.param_count()
+    for i in range(nt):
+        name, shape, off, size = e0.param_desc(i)
+        if name.endswith("_γ"):
+            g = p[off:off + size]
+            g *= np.float32(target * np.sqrt(1e-5) / max(float(g.std()), 1e-12))
+    for e in engines:
+        e.net_set(net, p)
+    return p

@@ -1,0 +1,152 @@
+"""GPU parity tests: the CUDA engine through the C ABI against the reference's golden vectors and,
+call for call, against the CPU oracle on identical seeds.  Bit-exact for trees, moves, examples,
+labels, statistics and counters (integer / fp32-bit comparisons)."""
+import numpy as np
+import pytest
+
+from agogo_b200 import _capi as K
+from tests import helpers as H
+from tests.golden import rules_golden as G
+
+pytestmark = pytest.mark.gpu
+
+
+def test_engine_mnk_golden(engine_lib):
+    H.check_mnk_golden(engine_lib)
+
+
+def test_engine_c4_golden(engine_lib):
+    H.check_c4_golden(engine_lib)
+
+
+def test_engine_wq_golden(engine_lib):
+    H.check_wq_golden(engine_lib)
+
+
+@pytest.mark.parametrize("sims", [10, 50, 200])
+def test_engine_ttt_example_kat(engine_lib, sims):
+    H.check_ttt_kat(engine_lib, sims)
+
+
+def _pair(oracle, engine_lib, desc_fn):
+    return oracle.create(desc_fn()), engine_lib.create(desc_fn())
+
+
+def _setup_dummy(e):
+    # agogo.go:83-87: epoch-0 self-play, dummyInferer captured with Player == None -> value 0
+    e.set_inferer(0, K.INF_DUMMY, 0)
+    e.set_inferer(1, K.INF_DUMMY, 0)
+
+
+def test_parity_ttt_example_trees(oracle, engine_lib):
+    """Full tree state after every Search of the Example game, 4 lockstep copies."""
+    eo, eg = H.ttt_example_engine(oracle, 50, 4), H.ttt_example_engine(engine_lib, 50, 4)
+    a, b = H.play_and_collect(eo, 4, record=True), H.play_and_collect(eg, 4, record=True)
+    H.assert_same_run(a, b, "ttt-example")
+
+
+@pytest.mark.parametrize("sims", [5, 40])
+def test_parity_ttt_arena_dummy(oracle, engine_lib, sims):
+    """C1's epoch-0 self-play: tic-tac-toe, two agents, two trees with reuse, dummy inferer."""
+    def desc():
+        return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=sims, nn=H.tiny_nn(3, 3, 10), n_games=16, seed=11)
+    eo, eg = _pair(oracle, engine_lib, desc)
+    for e in (eo, eg):
+        _setup_dummy(e)
+    H.assert_same_run(H.play_and_collect(eo, 16), H.play_and_collect(eg, 16), "ttt-arena")
+    # a second batch continues the coin stream and the statistics
+    H.assert_same_run(H.play_and_collect(eo, 16), H.play_and_collect(eg, 16), "ttt-arena-2")
+
+
+def test_parity_gomoku_arena_dummy(oracle, engine_lib):
+    def desc():
+        return K.make_desc(K.GAME_MNK, 5, 5, 4, sims=12, nn=H.tiny_nn(5, 5, 26), n_games=6, seed=3)
+    eo, eg = _pair(oracle, engine_lib, desc)
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUMMY, 1)
+        e.set_inferer(1, K.INF_DUMMY, 2)
+    H.assert_same_run(H.play_and_collect(eo, 6), H.play_and_collect(eg, 6), "gomoku")
+
+
+def test_parity_c4_arena_dummy(oracle, engine_lib):
+    def desc():
+        return K.make_desc(K.GAME_C4, 6, 7, 4, sims=30, nn=H.tiny_nn(6, 7, 8), n_games=8, seed=5)
+    eo, eg = _pair(oracle, engine_lib, desc)
+    for e in (eo, eg):
+        _setup_dummy(e)
+    H.assert_same_run(H.play_and_collect(eo, 8), H.play_and_collect(eg, 8), "c4")
+
+
+@pytest.mark.parametrize("size,sims,plies", [(5, 24, 40), (9, 16, 30)])
+def test_parity_wq_arena_dummy(oracle, engine_lib, size, sims, plies):
+    def desc():
+        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=sims, n_games=4, seed=9, max_moves=plies,
+                           nn=H.tiny_nn(size, size, size * size + 1, features=18))
+    eo, eg = _pair(oracle, engine_lib, desc)
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUMMY, 1)
+        e.set_inferer(1, K.INF_DUMMY, 2)
+    H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "wq")
+
+
+def test_wq_random_rules_vs_oracle(oracle, engine_lib):
+    """Board.check / Board.Apply on random (also inconsistent) 7x7 positions, every point, both colours."""
+    rng = np.random.default_rng(1)
+    eo, eg = H.rules_engine(oracle, K.GAME_WQ, 7, 7), H.rules_engine(engine_lib, K.GAME_WQ, 7, 7)
+    boards, players, moves = [], [], []
+    for _ in range(60):
+        b = rng.choice([0, 1, 2], size=49, p=[0.4, 0.3, 0.3]).astype(np.int32)
+        for mv in range(49):
+            boards.append(b); players.append(1 + (mv + len(boards)) % 2); moves.append(mv)
+    boards = np.array(boards, np.int32)
+    ra, rb = eo.rules_apply(boards, players, moves), eg.rules_apply(boards, players, moves)
+    for x, y, name in zip(ra, rb, ("check", "applied", "boards", "taken")):
+        assert (x == y).all(), name
+    sa, sb = eo.rules_status(boards[::49]), eg.rules_status(boards[::49])
+    for x, y in zip(sa, sb):
+        assert (x == y).all()
+
+
+def _dual_pair(oracle, engine_lib, desc_fn, seeds=(21, 22)):
+    eo, eg = _pair(oracle, engine_lib, desc_fn)
+    for e in (eo, eg):
+        e.net_init(0, seeds[0]); e.net_init(1, seeds[1])
+    assert (eo.net_get(0).view(np.uint32) == eg.net_get(0).view(np.uint32)).all(), "net init differs"
+    H.tame_gammas([eo, eg], 0, seeds[0]); H.tame_gammas([eo, eg], 1, seeds[1])
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUAL); e.set_inferer(1, K.INF_DUAL)
+    return eo, eg
+
+
+def test_fp32_forward_vs_oracle(oracle, engine_lib):
+    """dualnet forward, fp32 CUDA-core path, tolerance 1e-4 (north star); typically ~1e-6."""
+    def desc():
+        return K.make_desc(K.GAME_WQ, 9, 9, 0, komi=7.5, sims=4, n_games=8, seed=2, max_moves=8, flags=K.FLAG_FP32_TOWER,
+                           nn=dict(k=8, shared_layers=2, fc=16, batch_size=4, features=18, action_space=82))
+    eo, eg = _dual_pair(oracle, engine_lib, desc)
+    rng = np.random.default_rng(0)
+    planes = rng.choice([0.0, 1.0, -1.0, 0.001], size=(8, 18 * 81)).astype(np.float32)
+    po, vo = eo.infer(0, planes)
+    pg, vg = eg.infer(0, planes)
+    assert np.isfinite(po).all() and np.isfinite(vo).all() and np.abs(vo).max() < 0.999
+    assert np.abs(po - pg).max() < 1e-4 and np.abs(vo - vg).max() < 1e-4
+    assert np.abs(pg.sum(axis=1) - 1).max() < 1e-5
+
+
+def test_parity_ttt_arena_dual_fp32(oracle, engine_lib):
+    """Two random dual nets (cmd/tictactoe shapes: K=3, 3 blocks, FC=8) driving the search."""
+    def desc():
+        return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=25, n_games=8, seed=4, flags=K.FLAG_FP32_TOWER,
+                           nn=dict(k=3, shared_layers=3, fc=8, batch_size=100, features=2, action_space=10))
+    eo, eg = _dual_pair(oracle, engine_lib, desc)
+    H.assert_same_run(H.play_and_collect(eo, 8), H.play_and_collect(eg, 8), "ttt-dual")
+
+
+def test_parity_wq_arena_dual_fp32(oracle, engine_lib):
+    """9x9 Go with two small random dual nets: varied priors, so captures / occupied-point no-ops /
+    the WQEncoder history planes all enter the trees; fp32 tower (op order identical to the oracle)."""
+    def desc():
+        return K.make_desc(K.GAME_WQ, 7, 7, 0, komi=7.5, sims=20, n_games=4, seed=13, max_moves=36, flags=K.FLAG_FP32_TOWER,
+                           nn=dict(k=4, shared_layers=1, fc=8, batch_size=4, features=18, action_space=50))
+    eo, eg = _dual_pair(oracle, engine_lib, desc)
+    H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "wq-dual")
