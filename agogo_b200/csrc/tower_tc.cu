@@ -1,7 +1,524 @@
+// agogo_b200 — K5: the residual tower as tcgen05 / TMEM / TMA implicit GEMMs (sm_100a only).
+//
+// One kernel launch per conv layer (the init 3x3 conv, then one launch per shared block computing
+// BOTH parallel branches as a single C->2C contraction, dualnet/dual.go:59-73):
+//   out[p, c] = relu(Aa[hw,c]*convA(x)[p,c] + Ba[hw,c]) + relu(Ab[hw,c]*convB(x)[p,c] + Bb[hw,c])
+// GEMM view: M = padded board positions of the whole batch, N = output channels, K = 9 taps x C_in.
+//   * activations live in HBM as NHWC fp16 hi/lo planes over a zero-bordered position grid
+//     ((H+1) x (W+1) per sample: one shared zero column / zero row), so that tap (dy,dx) of an
+//     M-tile is the SAME 2-D TMA box shifted by dy*(W+1)+dx rows — im2col by TMA coordinates,
+//     no gather, halo = zeros already in memory (or TMA out-of-bounds zero fill);
+//   * fp32 fidelity on fp16 tensor cores: x = hi + lo and w = hi + lo (both pre-scaled by powers of
+//     two), three tcgen05.mma passes per K-step (hi*hi + hi*lo + lo*hi) into one fp32 TMEM
+//     accumulator; the dropped lo*lo term is ~2^-22 relative;
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//     warps 2-5 = epilogue (tcgen05.ld -> BN-affine + ReLU + branch add -> fp16 hi/lo split ->
+//     global).  smem ring of K-blocks (full/empty mbarriers), double-buffered TMEM accumulator
+//     (tmem_full/tmem_empty mbarriers), persistent CTAs striding over (M-tile, N-tile).
+// Descriptor bit layouts follow the PTX ISA tcgen05 "shared memory descriptor" / "instruction
+// descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp in the image).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "mcts_dev.cuh"
 #include "tower_tc.cuh"
-bool tc_tower_supported(const NetDims&) { return false; }
-void tc_tower_alloc(TcTower&, const NetDims&, int, int) {}
-void tc_tower_free(TcTower&) {}
-void tc_tower_prepare(TcTower&, const NetLayout&, const Snapshot&, cudaStream_t, unsigned long long*) {}
-void tc_tower_forward(TcTower&, const NetLayout&, const Snapshot&, Fp32Scratch&, const float*, const int*, int, float*, int,
-                      float*, int*, cudaStream_t, unsigned long long*) {}
+
+namespace {
+
+constexpr int BM = 128;        // M tile (TMEM lanes)
+constexpr int BK = 64;         // K block: 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int NTHREADS = 192;  // 6 warps
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+__host__ __device__ constexpr int stage_bytes(int BN) { return 2 * A_TILE_BYTES + 2 * BN * BK * 2; }
+__host__ __device__ constexpr int num_stages(int BN) { return BN == 256 ? 2 : (BN == 128 ? 3 : 4); }
+__host__ __device__ constexpr int smem_bytes(int BN) { return num_stages(BN) * stage_bytes(BN) + 1024 + 256; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), cta_group::1
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_128B operand descriptor: start>>4 | LBO (ignored for swizzled K-major) |
+// SBO = 1024 B (8 rows x 128 B) | version 1 (bits 46-47) | layout type 2 (bits 61-63)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct ConvArgs {
+  const int* n_dev;   // batch size (device)
+  int n_max;
+  int S, Wp, H, W;    // positions per sample (H+1)*(W+1), row pitch W+1
+  int guard;          // zero rows in front of the activation buffers
+  int cin;            // padded input channels (multiple of 64)
+  int n_total;        // GEMM N of the layer (fused: 2*K)
+  int cout;           // output channels (K)
+  const float2* aff;  // [HW][n_total] {A', B} in weight-row order
+  __half* out_hi;     // [(guard + rows)][cout]
+  __half* out_lo;
+  float act_scale;    // 2^ea
+  int* err;
+};
+
+template <int BN, bool PAIR>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ConvArgs a) {
+  constexpr int STAGES = num_stages(BN);
+  constexpr int STAGE_BYTES = stage_bytes(BN);
+  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr int OUTC = PAIR ? BN / 2 : BN;  // output channels per N tile
+  constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : 128);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;  // full[S], empty[S], tfull[2], tempty[2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES * STAGE_BYTES + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n = min(*a.n_dev, a.n_max);
+  const int rows = n * a.S;
+  const int m_tiles = (rows + BM - 1) / BM;
+  const int n_tiles = a.n_total / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int kc_per_tap = a.cin / BK;
+  const int kblocks = 9 * kc_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const int arow = a.guard + m0 + dy * a.Wp + dx;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          tma_load_2d(sa, &tmA_hi, full_bar(s), kc * BK, arow);
+          tma_load_2d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, arow);
+          tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), tap * a.cin + kc * BK, n0);
+          tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), tap * a.cin + kc * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+        const int acc = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint64_t dAh = make_desc_sw128(sa), dAl = make_desc_sw128(sa + A_TILE_BYTES);
+          const uint64_t dBh = make_desc_sw128(sa + 2 * A_TILE_BYTES), dBl = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ks++) {
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 fp16 = 32 B along K inside the swizzle atom
+            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | ks) ? 1u : 0u);
+            umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above have read it
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      const int r = m0 + quad * 32 + lane;  // logical position row
+      const int p = r % a.S;
+      const int y = p / a.Wp, x = p - y * a.Wp;
+      const bool valid = r < rows && y < a.H && x < a.W;
+      const int hw = y * a.W + x;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const float2* aff = a.aff + (size_t)(valid ? hw : 0) * a.n_total + n0;
+      __half* ohi = a.out_hi + (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      __half* olo = a.out_lo + (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      bool overflow = false;
+#pragma unroll 1
+      for (int c0 = 0; c0 < OUTC; c0 += 32) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row + c0, ra);
+        if (PAIR) tmem_ld32(t_row + BN / 2 + c0, rb);
+        tmem_ld_wait();
+        if (valid) {
+          __align__(16) __half hi[32];
+          __align__(16) __half lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            float2 fa = __ldg(aff + c0 + i);
+            float v = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
+            if (PAIR) {
+              float2 fb = __ldg(aff + BN / 2 + c0 + i);
+              v += fmaxf(fmaf(fb.x, __uint_as_float(rb[i]), fb.y), 0.0f);
+            }
+            v *= a.act_scale;
+            __half h = __float2half_rn(v);
+            float hf = __half2float(h);
+            overflow |= !(fabsf(hf) <= 65504.0f);
+            hi[i] = h;
+            lo[i] = __float2half_rn(v - hf);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            *(uint4*)(ohi + c0 + q * 8) = *(const uint4*)(hi + q * 8);
+            *(uint4*)(olo + c0 + q * 8) = *(const uint4*)(lo + q * 8);
+          }
+        }
+      }
+      if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// fp32 NCHW planes -> zero-bordered NHWC fp16 hi/lo (channels padded to cpad)
+__global__ void k_pack_planes(const float* __restrict__ planes, const int* __restrict__ n_dev, int n_max, int F, int H,
+                              int W, int cpad, int guard, float scale, __half* hi, __half* lo) {
+  const int n = min(*n_dev, n_max);
+  const int HW = H * W, Wp = W + 1, S = (H + 1) * Wp;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * HW * cpad) return;
+  const int c = (int)(idx % cpad);
+  const int hw = (int)((idx / cpad) % HW);
+  const int b = (int)(idx / ((size_t)cpad * HW));
+  const int y = hw / W, x = hw - y * W;
+  float v = c < F ? planes[((size_t)b * F + c) * HW + hw] * scale : 0.0f;
+  __half h = __float2half_rn(v);
+  const size_t o = ((size_t)guard + (size_t)b * S + y * Wp + x) * cpad + c;
+  hi[o] = h;
+  lo[o] = __float2half_rn(v - __half2float(h));
+}
+// tower output (NHWC hi/lo, scaled) -> dense fp32 NCHW for the heads
+__global__ void k_unpack_tower(const __half* __restrict__ hi, const __half* __restrict__ lo, const int* __restrict__ n_dev,
+                               int n_max, int K, int H, int W, int guard, float inv_scale, float* out) {
+  const int n = min(*n_dev, n_max);
+  const int HW = H * W, Wp = W + 1, S = (H + 1) * Wp;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * HW * K) return;
+  const int c = (int)(idx % K);
+  const int hw = (int)((idx / K) % HW);
+  const int b = (int)(idx / ((size_t)K * HW));
+  const int y = hw / W, x = hw - y * W;
+  const size_t i = ((size_t)guard + (size_t)b * S + y * Wp + x) * K + c;
+  out[((size_t)b * K + c) * HW + hw] = (__half2float(hi[i]) + __half2float(lo[i])) * inv_scale;
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 2-D fp16 row-major [rows][cols] tensor, box {64 cols, box_rows}, 128B swizzle
+CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return m;
+}
+
+struct Layer {
+  int cin, n_total, bn;
+  bool pair;
+  __half *w_hi = nullptr, *w_lo = nullptr;  // [n_total][9*cin]
+  float2* aff = nullptr;                    // [HW][n_total]
+  CUtensorMap mB_hi, mB_lo;
+};
+struct Impl {
+  NetDims d;
+  int n_max, ea, guard, S, rows_alloc, num_sms;
+  __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
+  __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
+  CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
+  std::vector<Layer> layers;
+  float* tower_f32 = nullptr;  // [n_max][K][HW]
+};
+
+template <int BN, bool PAIR>
+void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
+                 const int* n_dev, int* err, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
+    attr_set = true;
+  }
+  ConvArgs a;
+  a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
+  a.cin = L.cin; a.n_total = L.n_total; a.cout = I.d.K; a.aff = L.aff; a.out_hi = ohi; a.out_lo = olo;
+  a.act_scale = ldexpf(1.0f, I.ea); a.err = err;
+  const int max_tiles = ((I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
+  const int grid = std::min(I.num_sms, max_tiles);
+  k_conv3x3_tc<BN, PAIR><<<grid, NTHREADS, smem_bytes(BN), st>>>(ah, al, L.mB_hi, L.mB_lo, a);
+}
+void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
+                   const int* n_dev, int* err, cudaStream_t st) {
+  if (L.pair && L.bn == 256) launch_conv<256, true>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (L.pair && L.bn == 128) launch_conv<128, true>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (!L.pair && L.bn == 256) launch_conv<256, false>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (!L.pair && L.bn == 128) launch_conv<128, false>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (!L.pair && L.bn == 64) launch_conv<64, false>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else throw std::runtime_error("tc tower: unsupported tile");
+}
+
+}  // namespace
+
+bool tc_tower_supported(const NetDims& d) {
+  return (d.K == 64 || d.K == 128 || d.K == 256) && d.F <= 64 && d.SharedLayers >= 0;
+}
+
+void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2) {
+  Impl* I = new Impl;
+  t.impl = I;
+  I->d = d; I->n_max = n_max; I->ea = act_scale_log2;
+  I->guard = ((d.W + 2 + 7) / 8) * 8;
+  I->S = (d.H + 1) * (d.W + 1);
+  I->rows_alloc = I->guard + n_max * I->S + I->guard + BM;
+  int dev;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&I->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  auto alloc_h = [&](size_t n) { __half* p; CUDA_CHECK(cudaMalloc(&p, n * 2)); CUDA_CHECK(cudaMemset(p, 0, n * 2)); return p; };
+  I->xin_hi = alloc_h((size_t)I->rows_alloc * 64); I->xin_lo = alloc_h((size_t)I->rows_alloc * 64);
+  for (int i = 0; i < 2; i++) { I->x_hi[i] = alloc_h((size_t)I->rows_alloc * d.K); I->x_lo[i] = alloc_h((size_t)I->rows_alloc * d.K); }
+  CUDA_CHECK(cudaMalloc(&I->tower_f32, (size_t)n_max * d.K * d.HW() * 4));
+  I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM);
+  for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM); }
+  // layers: init (single), then SharedLayers fused pairs
+  const int K = d.K, HW = d.HW();
+  for (int l = 0; l <= d.SharedLayers; l++) {
+    Layer L;
+    L.pair = l > 0;
+    L.cin = l == 0 ? 64 : K;
+    L.n_total = L.pair ? 2 * K : K;
+    L.bn = std::min(256, L.n_total);
+    const size_t ktot = (size_t)9 * L.cin;
+    L.w_hi = alloc_h((size_t)L.n_total * ktot); L.w_lo = alloc_h((size_t)L.n_total * ktot);
+    CUDA_CHECK(cudaMalloc(&L.aff, (size_t)HW * L.n_total * sizeof(float2)));
+    L.mB_hi = make_map(L.w_hi, L.n_total, ktot, L.bn); L.mB_lo = make_map(L.w_lo, L.n_total, ktot, L.bn);
+    I->layers.push_back(L);
+  }
+  CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+void tc_tower_free(TcTower& t) {
+  Impl* I = (Impl*)t.impl;
+  if (!I) return;
+  cudaFree(I->xin_hi); cudaFree(I->xin_lo);
+  for (int i = 0; i < 2; i++) { cudaFree(I->x_hi[i]); cudaFree(I->x_lo[i]); }
+  cudaFree(I->tower_f32);
+  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); }
+  delete I;
+  t.impl = nullptr;
+}
+
+// Host-side operand preparation (once per Agent.SwitchToInference): split the fp32 filters into
+// fp16 hi/lo at a per-layer power-of-two scale, reorder rows so that an N tile holds the same
+// output channels of both branches, fold BN-test (x/sqrt(eps)), gamma and the scales into A'.
+void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaStream_t st, unsigned long long*) {
+  Impl* I = (Impl*)t.impl;
+  const NetDims& d = I->d;
+  const int K = d.K, HW = d.HW();
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<float> h(s.total);
+  CUDA_CHECK(cudaMemcpy(h.data(), s.d, s.total * 4, cudaMemcpyDeviceToHost));
+  const float inv_sd = 1.0f / sqrtf(1e-5f);
+  for (size_t l = 0; l < I->layers.size(); l++) {
+    Layer& L = I->layers[l];
+    const size_t ktot = (size_t)9 * L.cin;
+    const int nb = L.pair ? 2 : 1;
+    const SnapUnit* u[2] = {&s.units[l == 0 ? 0 : 1 + 2 * (l - 1)], L.pair ? &s.units[2 + 2 * (l - 1)] : nullptr};
+    const int ci_real = u[0]->Ci;
+    float mx = 0;
+    for (int b = 0; b < nb; b++) {
+      const float* f = h.data() + u[b]->filter;
+      for (size_t i = 0; i < (size_t)K * ci_real * 9; i++) mx = std::max(mx, std::fabs(f[i]));
+    }
+    int ew = 0;
+    if (mx > 0 && std::isfinite(mx)) { int e2; frexpf(mx, &e2); ew = 7 - e2; }  // mx*2^ew in [64,128)
+    const float wscale = ldexpf(1.0f, ew);
+    std::vector<__half> whi((size_t)L.n_total * ktot, __float2half_rn(0.0f)), wlo((size_t)L.n_total * ktot, __float2half_rn(0.0f));
+    std::vector<float2> aff((size_t)HW * L.n_total);
+    const int half_bn = L.pair ? L.bn / 2 : L.bn;
+    const float fold = ldexpf(1.0f, -(I->ea + ew)) * inv_sd;
+    for (int row = 0; row < L.n_total; row++) {
+      const int tile = row / L.bn, q = row % L.bn;
+      const int br = L.pair ? (q >= half_bn ? 1 : 0) : 0;
+      const int ch = tile * half_bn + (q % half_bn);
+      const float* f = h.data() + u[br]->filter + (size_t)ch * ci_real * 9;
+      for (int tap = 0; tap < 9; tap++)
+        for (int ci = 0; ci < ci_real; ci++) {
+          float w = f[ci * 9 + tap] * wscale;  // filter[co][ci][ky][kx], tap = ky*3+kx
+          __half hh = __float2half_rn(w);
+          size_t o = (size_t)row * ktot + (size_t)tap * L.cin + ci;
+          whi[o] = hh;
+          wlo[o] = __float2half_rn(w - __half2float(hh));
+        }
+      const float* g = h.data() + u[br]->gamma + (size_t)ch * HW;
+      const float* be = h.data() + u[br]->beta + (size_t)ch * HW;
+      for (int hw = 0; hw < HW; hw++) aff[(size_t)hw * L.n_total + row] = make_float2(g[hw] * fold, be[hw]);
+    }
+    CUDA_CHECK(cudaMemcpy(L.w_hi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(L.w_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(L.aff, aff.data(), aff.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  (void)NL;
+  t.ready = true;
+}
+
+void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Scratch& sc, const float* planes,
+                      const int* n_dev, int n_max, float* policy, int ldp, float* value, int* err_flag, cudaStream_t st,
+                      unsigned long long* launches) {
+  Impl* I = (Impl*)t.impl;
+  if (!I || !t.ready) throw std::runtime_error("tc tower not prepared");
+  const NetDims& d = I->d;
+  const float scale = ldexpf(1.0f, I->ea);
+  {
+    size_t total = (size_t)n_max * d.HW() * 64;
+    k_pack_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planes, n_dev, n_max, d.F, d.H, d.W, 64, I->guard, scale,
+                                                                  I->xin_hi, I->xin_lo);
+    if (launches) (*launches)++;
+  }
+  int cur = 0;
+  dispatch_conv(*I, I->layers[0], I->mIn_hi, I->mIn_lo, I->x_hi[0], I->x_lo[0], n_dev, err_flag, st);
+  if (launches) (*launches)++;
+  for (size_t l = 1; l < I->layers.size(); l++) {
+    dispatch_conv(*I, I->layers[l], I->mX_hi[cur], I->mX_lo[cur], I->x_hi[cur ^ 1], I->x_lo[cur ^ 1], n_dev, err_flag, st);
+    if (launches) (*launches)++;
+    cur ^= 1;
+  }
+  {
+    size_t total = (size_t)n_max * d.HW() * d.K;
+    k_unpack_tower<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(I->x_hi[cur], I->x_lo[cur], n_dev, n_max, d.K, d.H, d.W,
+                                                                   I->guard, 1.0f / scale, I->tower_f32);
+    if (launches) (*launches)++;
+  }
+  heads_fp32(NL, s, sc, I->tower_f32, n_dev, n_max, policy, ldp, value, st, launches);
+}

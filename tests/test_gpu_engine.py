@@ -139,7 +139,7 @@ def test_parity_ttt_arena_dual_fp32(oracle, engine_lib):
         return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=25, n_games=8, seed=4, flags=K.FLAG_FP32_TOWER,
                            nn=dict(k=3, shared_layers=3, fc=8, batch_size=100, features=2, action_space=10))
     eo, eg = _dual_pair(oracle, engine_lib, desc)
-    H.assert_same_run(H.play_and_collect(eo, 8), H.play_and_collect(eg, 8), "ttt-dual")
+    H.assert_same_run(H.play_and_collect(eo, 8), H.play_and_collect(eg, 8), "ttt-dual", float_ulps=64)
 
 
 def test_parity_wq_arena_dual_fp32(oracle, engine_lib):
@@ -149,4 +149,58 @@ def test_parity_wq_arena_dual_fp32(oracle, engine_lib):
         return K.make_desc(K.GAME_WQ, 7, 7, 0, komi=7.5, sims=20, n_games=4, seed=13, max_moves=36, flags=K.FLAG_FP32_TOWER,
                            nn=dict(k=4, shared_layers=1, fc=8, batch_size=4, features=18, action_space=50))
     eo, eg = _dual_pair(oracle, engine_lib, desc)
-    H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "wq-dual")
+    H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "wq-dual", float_ulps=64)
+
+
+def _wq_planes(rng, n, size):
+    """Plausible WQEncoder planes: stones +-1 / 0 in history planes, one to-move plane set."""
+    x = np.zeros((n, 18, size * size), np.float32)
+    for b in range(n):
+        for q in range(0, 7):
+            board = rng.choice([0.0, 1.0, -1.0], size=size * size, p=[0.6, 0.2, 0.2]).astype(np.float32)
+            x[b, q] = board
+            x[b, 8 + q] = -board
+        x[b, 16 if b % 2 == 0 else 17] = 1.0 if b % 2 == 0 else -1.0
+    return x.reshape(n, -1)
+
+
+@pytest.mark.parametrize("k,layers,size,fc,n", [(64, 6, 9, 128, 6), (128, 2, 9, 64, 3), (256, 3, 19, 512, 3)])
+def test_tc_tower_vs_fp32_and_oracle(oracle, engine_lib, k, layers, size, fc, n):
+    """tcgen05 tower (fp16 hi/lo split, 3 passes) against the engine's fp32 CUDA-core tower and the
+    CPU oracle on the same weights: |dp|, |dv| < 1e-4 (north star tolerance)."""
+    A1 = size * size + 1
+    def desc(flags):
+        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=8, seed=2, max_moves=4, flags=flags,
+                           nn=dict(k=k, shared_layers=layers, fc=fc, batch_size=2, features=18, action_space=A1))
+    eo = oracle.create(desc(0))
+    e32 = engine_lib.create(desc(K.FLAG_FP32_TOWER))
+    etc = engine_lib.create(desc(0))
+    H.tame_gammas([eo, e32, etc], 0, 77)
+    for e in (eo, e32, etc):
+        e.set_inferer(0, K.INF_DUAL)
+    planes = _wq_planes(np.random.default_rng(5), n, size)
+    po, vo = eo.infer(0, planes)
+    p32, v32 = e32.infer(0, planes)
+    ptc, vtc = etc.infer(0, planes)
+    assert np.isfinite(po).all() and np.abs(vo).max() < 0.9999
+    assert np.abs(p32 - po).max() < 1e-4 and np.abs(v32 - vo).max() < 1e-4
+    err_p, err_v = np.abs(ptc - po).max(), np.abs(vtc - vo).max()
+    print("tc vs oracle: dp=%.3g dv=%.3g ; tc vs fp32: dp=%.3g dv=%.3g ; pmax=%.3g" %
+          (err_p, err_v, np.abs(ptc - p32).max(), np.abs(vtc - v32).max(), po.max()))
+    assert err_p < 1e-4 and err_v < 1e-4
+
+
+def test_tc_selfplay_runs(oracle, engine_lib):
+    """9x9 self-play with the tensor-core tower in the loop: moves legal-by-construction, finite
+    outputs, same move sequences as the oracle for the first plies (priors agree to ~1e-6)."""
+    def desc():
+        return K.make_desc(K.GAME_WQ, 9, 9, 0, komi=7.5, sims=16, n_games=4, seed=21, max_moves=6,
+                           nn=dict(k=64, shared_layers=2, fc=32, batch_size=2, features=18, action_space=82))
+    eo, eg = oracle.create(desc()), engine_lib.create(desc())
+    H.tame_gammas([eo, eg], 0, 31); H.tame_gammas([eo, eg], 1, 32)
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUAL); e.set_inferer(1, K.INF_DUAL)
+    a, b = H.play_and_collect(eo, 4, dump_trees=False), H.play_and_collect(eg, 4, dump_trees=False)
+    for ra, rb in zip(a["records"], b["records"]):
+        assert list(ra["moves"]) == list(rb["moves"])
+    assert a["counters"]["evals"] == b["counters"]["evals"]
