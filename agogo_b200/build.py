@@ -42,7 +42,7 @@ def build(verbose=False, ptxas_info=False):
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
     if _stale(OUT, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart", "-ldl", "-ccbin", "/usr/bin/g++"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart", "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -716,6 +716,18 @@ int az_comm_init(az_engine* e, int32_t, int32_t, const uint8_t*) {
   return AZ_ERR_UNSUPPORTED;
 }
 
+int az_profile(az_engine* e, int32_t enable, double out[8]) {
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  if (out) {
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile_collect(e->tc[a], e->stream, &out[0], &out[1], &out[2], &out[3]);
+  }
+  if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile(e->tc[a], enable != 0);
+  GUARD_END(e)
+  return AZ_OK;
+}
+
 int az_counters_get(const az_engine* ce, az_counters* out) {
   az_engine* e = const_cast<az_engine*>(ce);
   memset(out, 0, sizeof *out);

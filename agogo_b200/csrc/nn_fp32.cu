@@ -4,8 +4,11 @@
 // accumulated in ascending (ci, ky, kx) order with unfused multiply and add, i.e. the same
 // rounding sequence as the oracle's restatement (dualnet/ermahagerdmonards.go:33-73).
 // Compiled with -fmad=false.
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <thread>
 
 #include "nn.cuh"
 
@@ -61,33 +64,56 @@ static inline uint64_t derive_seed(uint64_t seed, uint64_t stream) {
   uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (stream + 1));
   return splitmix64(&s);
 }
+// splitmix64 is counter based (state_i = s0 + i*GOLDEN), so every tensor's stream can be generated
+// in independent chunks on many host threads and still be bit-identical to the sequential draw.
+static inline uint64_t splitmix_at(uint64_t s0, uint64_t i) {
+  uint64_t z = s0 + (i + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 void init_params_host(const NetLayout& L, uint64_t seed, std::vector<float>* out) {
   out->assign(L.total, 0.0f);
-  for (size_t t = 0; t < L.desc.size(); t++) {
-    const ParamDescH& d = L.desc[t];
-    float* p = out->data() + d.offset;
-    if (d.init == 0) continue;
-    double field = 1;
-    for (int i = 2; i < d.rank; i++) field *= d.shape[i];
-    double fan = (double)(d.shape[0] + d.shape[1]) * field;
-    double stdev = 1.0 * std::sqrt(2.0 / fan);
-    uint64_t s = derive_seed(seed, t);
-    if (d.init == 1) {
-      float lim = (float)(stdev * std::sqrt(3.0));
-      for (size_t i = 0; i < d.size; i++) {
-        float u = (float)(splitmix64(&s) >> 40) * (1.0f / 16777216.0f);
-        p[i] = (2.0f * u - 1.0f) * lim;
-      }
-    } else {
-      float sd = (float)stdev;
-      for (size_t i = 0; i < d.size; i++) {
-        double u1 = ((double)(splitmix64(&s) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
-        double u2 = ((double)(splitmix64(&s) >> 11)) * (1.0 / 9007199254740992.0);
-        float nrm = (float)(std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925 * u2));
-        p[i] = nrm * sd;
+  struct Job { size_t t, lo, hi; };
+  std::vector<Job> jobs;
+  const size_t CH = 1 << 20;
+  for (size_t t = 0; t < L.desc.size(); t++)
+    if (L.desc[t].init) for (size_t lo = 0; lo < L.desc[t].size; lo += CH) jobs.push_back({t, lo, std::min(L.desc[t].size, lo + CH)});
+  std::atomic<size_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      size_t j = next.fetch_add(1);
+      if (j >= jobs.size()) return;
+      const ParamDescH& d = L.desc[jobs[j].t];
+      float* p = out->data() + d.offset;
+      double field = 1;
+      for (int i = 2; i < d.rank; i++) field *= d.shape[i];
+      const double fan = (double)(d.shape[0] + d.shape[1]) * field;
+      const double stdev = 1.0 * std::sqrt(2.0 / fan);
+      const uint64_t s0 = derive_seed(seed, jobs[j].t);
+      if (d.init == 1) {
+        const float lim = (float)(stdev * std::sqrt(3.0));
+        for (size_t i = jobs[j].lo; i < jobs[j].hi; i++) {
+          float u = (float)(splitmix_at(s0, i) >> 40) * (1.0f / 16777216.0f);
+          p[i] = (2.0f * u - 1.0f) * lim;
+        }
+      } else {
+        const float sd = (float)stdev;
+        for (size_t i = jobs[j].lo; i < jobs[j].hi; i++) {
+          double u1 = ((double)(splitmix_at(s0, 2 * i) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+          double u2 = ((double)(splitmix_at(s0, 2 * i + 1) >> 11)) * (1.0 / 9007199254740992.0);
+          float nrm = (float)(std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586476925 * u2));
+          p[i] = nrm * sd;
+        }
       }
     }
-  }
+  };
+  unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  if (jobs.size() < 4) nt = 1;
+  std::vector<std::thread> th;
+  for (unsigned i = 1; i < nt; i++) th.emplace_back(work);
+  work();
+  for (auto& t : th) t.join();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -361,6 +361,16 @@ struct Impl {
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
   std::vector<Layer> layers;
   float* tower_f32 = nullptr;  // [n_max][K][HW]
+  // profiling
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<std::pair<size_t, size_t>> conv_spans, fwd_spans;  // (start event, stop event)
+  size_t ev_get(cudaStream_t st) {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); ev_pool.push_back(e); }
+    CUDA_CHECK(cudaEventRecord(ev_pool[ev_used], st));
+    return ev_used++;
+  }
 };
 
 template <int BN, bool PAIR>
@@ -435,6 +445,7 @@ void tc_tower_free(TcTower& t) {
   for (int i = 0; i < 2; i++) { cudaFree(I->x_hi[i]); cudaFree(I->x_lo[i]); }
   cudaFree(I->tower_f32);
   for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); }
+  for (cudaEvent_t e : I->ev_pool) cudaEventDestroy(e);
   delete I;
   t.impl = nullptr;
 }
@@ -500,6 +511,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   if (!I || !t.ready) throw std::runtime_error("tc tower not prepared");
   const NetDims& d = I->d;
   const float scale = ldexpf(1.0f, I->ea);
+  const size_t f0 = I->profile ? I->ev_get(st) : 0;
   {
     size_t total = (size_t)n_max * d.HW() * 64;
     k_pack_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planes, n_dev, n_max, d.F, d.H, d.W, 64, I->guard, scale,
@@ -510,7 +522,9 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   dispatch_conv(*I, I->layers[0], I->mIn_hi, I->mIn_lo, I->x_hi[0], I->x_lo[0], n_dev, err_flag, st);
   if (launches) (*launches)++;
   for (size_t l = 1; l < I->layers.size(); l++) {
+    size_t e0 = I->profile ? I->ev_get(st) : 0;
     dispatch_conv(*I, I->layers[l], I->mX_hi[cur], I->mX_lo[cur], I->x_hi[cur ^ 1], I->x_lo[cur ^ 1], n_dev, err_flag, st);
+    if (I->profile) I->conv_spans.push_back({e0, I->ev_get(st)});
     if (launches) (*launches)++;
     cur ^= 1;
   }
@@ -521,4 +535,21 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
     if (launches) (*launches)++;
   }
   heads_fp32(NL, s, sc, I->tower_f32, n_dev, n_max, policy, ldp, value, st, launches);
+  if (I->profile) I->fwd_spans.push_back({f0, I->ev_get(st)});
+}
+
+void tc_tower_profile(TcTower& t, bool enable) {
+  Impl* I = (Impl*)t.impl;
+  if (!I) return;
+  I->profile = enable;
+  if (enable) { I->ev_used = 0; I->conv_spans.clear(); I->fwd_spans.clear(); }
+}
+void tc_tower_profile_collect(TcTower& t, cudaStream_t st, double* conv_ms, double* conv_launches, double* fwd_ms,
+                              double* fwd_calls) {
+  Impl* I = (Impl*)t.impl;
+  if (!I) return;
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  for (auto& sp : I->conv_spans) { float ms; CUDA_CHECK(cudaEventElapsedTime(&ms, I->ev_pool[sp.first], I->ev_pool[sp.second])); *conv_ms += ms; *conv_launches += 1; }
+  for (auto& sp : I->fwd_spans) { float ms; CUDA_CHECK(cudaEventElapsedTime(&ms, I->ev_pool[sp.first], I->ev_pool[sp.second])); *fwd_ms += ms; *fwd_calls += 1; }
+  I->conv_spans.clear(); I->fwd_spans.clear(); I->ev_used = 0;
 }

@@ -13,6 +13,10 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
 void tc_tower_free(TcTower& t);
 // split/scale/reorder the snapshot's filters and BN affines into the tensor-core operand layout
 void tc_tower_prepare(TcTower& t, const NetLayout& L, const Snapshot& s, cudaStream_t st, unsigned long long* launches);
+// event timing of the fused-block conv launches (bench roofline); collect() synchronises the stream
+void tc_tower_profile(TcTower& t, bool enable);
+void tc_tower_profile_collect(TcTower& t, cudaStream_t st, double* conv_ms, double* conv_launches, double* fwd_ms,
+                              double* fwd_calls);
 void tc_tower_forward(TcTower& t, const NetLayout& L, const Snapshot& s, Fp32Scratch& sc, const float* planes,
                       const int* n_dev, int n_max, float* policy, int ldp, float* value, int* err_flag, cudaStream_t st,
                       unsigned long long* launches);

@@ -200,6 +200,12 @@ typedef struct az_counters {
 int az_counters_get(const az_engine* e, az_counters* out);
 int az_counters_reset(az_engine* e);
 
+/* Kernel timing for bench.py's roofline line: CUDA events on the engine's own stream around every
+ * launch of the dominant kernel (the fused 3x3 conv of a residual block).  enable=1 starts a fresh
+ * measurement, enable=0 stops; out (may be NULL) receives {conv_ms_total, conv_launches,
+ * forward_ms_total, forward_calls, 0...} accumulated since the last enable=1. */
+int az_profile(az_engine* e, int32_t enable, double out[8]);
+
 const char* az_build_info(void); /* "agogo_b200 <ver> sm_100a ..." or "oracle ..." */
 
 #ifdef __cplusplus

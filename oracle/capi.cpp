@@ -372,6 +372,8 @@ int az_train(az_engine* e, int32_t net, float* Xs, float* Pi, float* V, int32_t 
 int az_comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return AZ_ERR_UNSUPPORTED; }
 int az_comm_init(az_engine*, int32_t, int32_t, const uint8_t*) { return AZ_ERR_UNSUPPORTED; }
 
+int az_profile(az_engine*, int32_t, double out[8]) { if (out) for (int i = 0; i < 8; i++) out[i] = 0; return AZ_OK; }
+
 int az_counters_get(const az_engine* e, az_counters* out) {
   memset(out, 0, sizeof *out);
   Counters c = e->base;
