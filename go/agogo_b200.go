@@ -1,0 +1,138 @@
+// Package b200 is the cgo shim that puts the B200 engine (include/agogo_b200.h) under gorgonia/agogo's
+// Go API.  UNCOMPILED in this repository's image (no Go toolchain); kept as the binding a maintainer
+// would add next to agent.go / arena.go / agogo.go.  No Go pointer is retained by C after a call.
+package b200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../include
+#cgo LDFLAGS: -L${SRCDIR}/../agogo_b200 -lagogo_b200 -Wl,-rpath,${SRCDIR}/../agogo_b200
+#include <stdlib.h>
+#include "agogo_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"unsafe"
+
+	dual "github.com/gorgonia/agogo/dualnet"
+	"github.com/gorgonia/agogo/game"
+	"github.com/gorgonia/agogo/mcts"
+)
+
+// Engine owns the device state behind one agogo.AZ (two agents, two nets, n concurrent Arena games).
+type Engine struct{ h *C.az_engine }
+
+// Desc mirrors az_engine_desc; NN and MCTS are the reference's own config structs (source compatible).
+type Desc struct {
+	Kind, M, N, K int
+	Komi          float32
+	MaxMoves      int
+	NN            dual.Config
+	MCTS          mcts.Config
+	Sims          int
+	Encoder       int
+	Games, Device int
+	Seed          uint64
+}
+
+func check(e *Engine, rc C.int) error {
+	if rc == C.AZ_OK {
+		return nil
+	}
+	var h *C.az_engine
+	if e != nil {
+		h = e.h
+	}
+	msg := C.GoString(C.az_last_error(h))
+	if rc == C.AZ_ERR_PANIC { // conditions on which the reference itself panics (node.go:232, agent.go:70)
+		panic(msg)
+	}
+	return errors.New(msg)
+}
+
+// New replaces agogo.New (agogo.go:41-73): panics on invalid configs exactly like the reference.
+func New(d Desc) *Engine {
+	var cd C.az_engine_desc
+	cd.game.kind, cd.game.m, cd.game.n, cd.game.k = C.int32_t(d.Kind), C.int32_t(d.M), C.int32_t(d.N), C.int32_t(d.K)
+	cd.game.komi, cd.game.max_moves = C.float(d.Komi), C.int32_t(d.MaxMoves)
+	m := d.MCTS
+	cd.mcts.puct, cd.mcts.timeout_ns = C.float(m.PUCT), C.int64_t(m.Timeout)
+	cd.mcts.m, cd.mcts.n, cd.mcts.random_count, cd.mcts.budget = C.int32_t(m.M), C.int32_t(m.N), C.int32_t(m.RandomCount), C.int32_t(m.Budget)
+	cd.mcts.random_min_visits, cd.mcts.random_temperature = C.uint32_t(m.RandomMinVisits), C.float(m.RandomTemperature)
+	if m.DumbPass {
+		cd.mcts.dumb_pass = 1
+	}
+	cd.mcts.resign_percentage, cd.mcts.pass_preference, cd.mcts.sims = C.float(m.ResignPercentage), C.int32_t(m.PassPreference), C.int32_t(d.Sims)
+	n := d.NN
+	cd.nn.k, cd.nn.shared_layers, cd.nn.fc, cd.nn.l2 = C.int32_t(n.K), C.int32_t(n.SharedLayers), C.int32_t(n.FC), C.double(n.L2)
+	cd.nn.batch_size, cd.nn.width, cd.nn.height, cd.nn.features = C.int32_t(n.BatchSize), C.int32_t(n.Width), C.int32_t(n.Height), C.int32_t(n.Features)
+	cd.nn.action_space = C.int32_t(n.ActionSpace)
+	cd.encoder, cd.n_games, cd.device, cd.seed = C.int32_t(d.Encoder), C.int32_t(d.Games), C.int32_t(d.Device), C.uint64_t(d.Seed)
+	e := &Engine{}
+	if rc := C.az_engine_create(&cd, &e.h); rc != C.AZ_OK {
+		panic(C.GoString(C.az_last_error(nil))) // agogo.go:42-47
+	}
+	return e
+}
+
+func (e *Engine) Close() { C.az_engine_destroy(e.h); e.h = nil }
+
+// SetParams / Params move a dual.Dual's Model() tensors (dual.go:134-142 order) as one flat []float32;
+// the Go *dual.Dual stays the checkpoint container, so AZ.Save/Load (agogo.go:175-209) keep working.
+func (e *Engine) SetParams(net int, flat []float32) error {
+	return check(e, C.az_net_set_params(e.h, C.int32_t(net), (*C.float)(unsafe.Pointer(&flat[0])), C.uint64_t(len(flat))))
+}
+func (e *Engine) Params(net int, flat []float32) error {
+	return check(e, C.az_net_get_params(e.h, C.int32_t(net), (*C.float)(unsafe.Pointer(&flat[0])), C.uint64_t(len(flat))))
+}
+
+// SwitchToInference replaces Agent.SwitchToInference (agent.go:42-57); UseDummy replaces Agent.useDummy.
+func (e *Engine) SwitchToInference(agent int) error {
+	return check(e, C.az_agent_set_inferer(e.h, C.int32_t(agent), C.AZ_INF_DUAL, 0))
+}
+func (e *Engine) UseDummy(agent int, p game.Player) error {
+	return check(e, C.az_agent_set_inferer(e.h, C.int32_t(agent), C.AZ_INF_DUMMY, C.int32_t(p)))
+}
+
+// Infer replaces Inferer.Infer (datatypes.go:51-55, meta.go:168-190), batched.
+func (e *Engine) Infer(agent int, planes []float32, n int, policy, value []float32) error {
+	return check(e, C.az_infer(e.h, C.int32_t(agent), (*C.float)(unsafe.Pointer(&planes[0])), C.int32_t(n),
+		(*C.float)(unsafe.Pointer(&policy[0])), (*C.float)(unsafe.Pointer(&value[0]))))
+}
+
+// Play replaces a loop of Arena.Play(record, nil, nil) + game.Reset() (agogo.go:110-114, 144-148):
+// nGames games run concurrently on the device; examples come back in game order.
+func (e *Engine) Play(nGames int, record bool) error {
+	r := C.int32_t(0)
+	if record {
+		r = 1
+	}
+	return check(e, C.az_arena_play(e.h, C.int32_t(nGames), r))
+}
+
+// Examples drains the recorded examples into agogo.Example-shaped slices (datatypes.go:38-42).
+func (e *Engine) Examples(boardLen, policyLen int) (boards, policies, values []float32, err error) {
+	var n C.int64_t
+	if err = check(e, C.az_examples_count(e.h, &n)); err != nil || n == 0 {
+		return
+	}
+	boards, policies, values = make([]float32, int(n)*boardLen), make([]float32, int(n)*policyLen), make([]float32, int(n))
+	err = check(e, C.az_examples_read(e.h, 0, n, (*C.float)(unsafe.Pointer(&boards[0])), (*C.float)(unsafe.Pointer(&policies[0])),
+		(*C.float)(unsafe.Pointer(&values[0]))))
+	C.az_examples_clear(e.h)
+	return
+}
+
+// Stats replaces reading Agent.Wins/Loss/Draw (agent.go:21-24).
+func (e *Engine) Stats(agent int) (wins, loss, draw float32) {
+	var w, l, d C.float
+	C.az_agent_stats(e.h, C.int32_t(agent), &w, &l, &d)
+	return float32(w), float32(l), float32(d)
+}
+
+// Train replaces dual.Train (meta.go:16-54).
+func (e *Engine) Train(net int, Xs, Pi, V []float32, batches, iterations int, seed uint64) error {
+	return check(e, C.az_train(e.h, C.int32_t(net), (*C.float)(unsafe.Pointer(&Xs[0])), (*C.float)(unsafe.Pointer(&Pi[0])),
+		(*C.float)(unsafe.Pointer(&V[0])), C.int32_t(batches), C.int32_t(iterations), 0.1, C.uint64_t(seed), nil))
+}
