@@ -59,7 +59,7 @@ SYMBOLS = [
     "az_arena_step", "az_arena_finish", "az_search_begin", "az_search_run", "az_search_end", "az_game_record",
     "az_game_state", "az_examples_count", "az_examples_read", "az_examples_clear", "az_tree_dump", "az_rules_apply",
     "az_rules_status", "az_train", "az_comm_unique_id", "az_comm_init", "az_counters_get", "az_counters_reset",
-    "az_build_info", "az_profile",
+    "az_build_info", "az_profile", "az_train_grads", "az_train_apply",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -293,6 +293,20 @@ class Engine:
         self._ck(self.lib.dll.az_train(self.h, net, _p(Xs, C.c_float), _p(Pi, C.c_float), _p(V, C.c_float), batches,
                                        iterations, C.c_float(lr), C.c_uint64(shuffle_seed), _p(costs, C.c_float)))
         return costs
+
+    def train_grads(self, net, X, Pi, V):
+        X = np.ascontiguousarray(X, np.float32)
+        Pi = np.ascontiguousarray(Pi, np.float32)
+        V = np.ascontiguousarray(V, np.float32)
+        g = np.empty(self.param_count()[1], np.float32)
+        c = C.c_float()
+        self._ck(self.lib.dll.az_train_grads(self.h, net, _p(X, C.c_float), _p(Pi, C.c_float), _p(V, C.c_float),
+                                             _p(g, C.c_float), C.byref(c)))
+        return g, c.value
+
+    def train_apply(self, net, grads, lr=0.1):
+        grads = np.ascontiguousarray(grads, np.float32)
+        self._ck(self.lib.dll.az_train_apply(self.h, net, _p(grads, C.c_float), C.c_float(lr)))
 
     def comm_init(self, rank, world, uid):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid))

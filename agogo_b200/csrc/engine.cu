@@ -12,6 +12,10 @@
 #include "mcts_dev.cuh"
 #include "nn.cuh"
 #include "tower_tc.cuh"
+#include "train.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 // kernels (mcts.cu)
 size_t mcts_ws_bytes(const GameP& P, int cellsP);
@@ -76,6 +80,9 @@ struct az_engine {
   float *h_ex_board = nullptr, *h_ex_policy = nullptr, *h_ex_value = nullptr;
   int32_t* h_ex_valid = nullptr;
   int32_t* h_small = nullptr;  // [n_active, err]
+  TrainWS train;
+  void* comm = nullptr;  // ncclComm_t
+  int rank = 0, world = 1;
   mutable std::string err;
 
   template <class T>
@@ -87,6 +94,37 @@ struct az_engine {
     return (T*)p;
   }
 };
+
+// NCCL is bound lazily with dlopen so that single-GPU use has no libnccl dependency at load time
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  const char* (*GetErrorString)(ncclResult_t);
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool ok = false;
+  if (!ok) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw std::runtime_error(std::string("libnccl.so.2 not found: ") + dlerror());
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString)
+      throw std::runtime_error("libnccl.so.2: missing symbols");
+    ok = true;
+  }
+  return api;
+}
+static void nccl_allreduce_sum(az_engine* e, float* buf, size_t n) {
+  NcclApi& a = nccl_api();
+  ncclResult_t r = a.AllReduce(buf, buf, n, ncclFloat32, ncclSum, (ncclComm_t)e->comm, e->stream);
+  if (r != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce: ") + a.GetErrorString(r));
+}
 
 #define GUARD_BEGIN try {
 #define GUARD_END(e)                                                   \
@@ -118,6 +156,8 @@ void az_engine_destroy(az_engine* e) {
   cudaDeviceSynchronize();
   for (void* p : e->allocs) cudaFree(p);
   for (int a = 0; a < 2; a++) { tc_tower_free(e->tc[a]); }
+  train_ws_free(e->train);
+  if (e->comm) { try { nccl_api().CommDestroy((ncclComm_t)e->comm); } catch (...) {} }
   fp32_scratch_free(e->fp32);
   if (e->h_ex_board) cudaFreeHost(e->h_ex_board);
   if (e->h_ex_policy) cudaFreeHost(e->h_ex_policy);
@@ -705,15 +745,118 @@ int az_rules_status(az_engine* e, int32_t n, const int32_t* boards, const int32_
   return AZ_OK;
 }
 
-// ---- train / comm (row D2/D4/K7/K8: next milestone) ------------------------------------------
-int az_train(az_engine* e, int32_t, float*, float*, float*, int32_t, int32_t, float, uint64_t, float*) {
-  e->err = "az_train: the CUDA backward pass is not built yet (DESIGN.md: next row)";
-  return AZ_ERR_UNSUPPORTED;
+// ---- dual.Train (meta.go:16-54) and the gradient all-reduce (K7/K8) ---------------------------
+static void ensure_train(az_engine* e) { train_ws_alloc(e->train, e->L); }
+
+static void shuffle_rows(std::vector<float>& Xs, std::vector<float>& Pi, std::vector<float>& V, int rows, uint64_t* s) {
+  // shuffleBatch (meta.go:57-102): Fisher-Yates over rows, j = r.Intn(i+1), injected splitmix64 stream
+  const size_t xr = Xs.size() / rows, pr = Pi.size() / rows;
+  for (int i = 0; i < rows; i++) {
+    int j = (int)(splitmix64(s) % (uint64_t)(i + 1));
+    if (i == j) continue;
+    std::swap_ranges(Xs.begin() + i * xr, Xs.begin() + (i + 1) * xr, Xs.begin() + j * xr);
+    std::swap_ranges(Pi.begin() + i * pr, Pi.begin() + (i + 1) * pr, Pi.begin() + j * pr);
+    std::swap(V[i], V[j]);
+  }
 }
-int az_comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return AZ_ERR_UNSUPPORTED; }
-int az_comm_init(az_engine* e, int32_t, int32_t, const uint8_t*) {
-  e->err = "az_comm_init: gradient all-reduce arrives with az_train";
-  return AZ_ERR_UNSUPPORTED;
+
+// one step on the batch already staged in the workspace: grads, [all-reduce], SGD
+static void train_one(az_engine* e, int net, float lr) {
+  train_step_grads(e->train, e->L, e->net_params[net], e->stream, &e->launches);
+  float gscale = 1.0f;
+  if (e->comm) {
+    nccl_allreduce_sum(e, train_ws_grads(e->train), e->L.total);
+    gscale = 1.0f / (float)e->world;
+  }
+  train_sgd(e->train, e->L, e->net_params[net], lr, gscale, e->stream, &e->launches);
+}
+
+int az_train(az_engine* e, int32_t net, float* Xs, float* Pi, float* V, int32_t batches, int32_t iterations, float lr,
+             uint64_t shuffle_seed, float* costs_out) {
+  if (net < 0 || net > 1 || batches < 1 || iterations < 0) return AZ_ERR_INVALID;
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  ensure_train(e);
+  const NetDims& d = e->L.d;
+  const size_t xr = (size_t)d.F * d.HW(), pr = d.A1;
+  const int rows = batches * d.B;
+  std::vector<float> x(Xs, Xs + rows * xr), p(Pi, Pi + rows * pr), v(V, V + rows);
+  float *dX, *dPi, *dV;
+  train_ws_inputs(e->train, &dX, &dPi, &dV);
+  std::vector<float> costs((size_t)batches * iterations);
+  uint64_t rs = shuffle_seed;
+  for (int it = 0; it < iterations; it++) {
+    for (int bat = 0; bat < batches; bat++) {
+      const size_t s0 = (size_t)bat * d.B;
+      CUDA_CHECK(cudaMemcpyAsync(dX, x.data() + s0 * xr, d.B * xr * 4, cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaMemcpyAsync(dPi, p.data() + s0 * pr, d.B * pr * 4, cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaMemcpyAsync(dV, v.data() + s0, d.B * 4, cudaMemcpyHostToDevice, e->stream));
+      train_one(e, net, lr);
+      CUDA_CHECK(cudaMemcpyAsync(&costs[(size_t)it * batches + bat], train_ws_cost(e->train), 4, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));  // pageable staging buffers are reused next batch
+    }
+    shuffle_rows(x, p, v, rows, &rs);
+  }
+  memcpy(Xs, x.data(), x.size() * 4); memcpy(Pi, p.data(), p.size() * 4); memcpy(V, v.data(), v.size() * 4);
+  if (costs_out) memcpy(costs_out, costs.data(), costs.size() * 4);
+  GUARD_END(e)
+  return AZ_OK;
+}
+
+int az_train_grads(az_engine* e, int32_t net, const float* X, const float* Pi, const float* V, float* grads_out,
+                   float* cost_out) {
+  if (net < 0 || net > 1) return AZ_ERR_INVALID;
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  ensure_train(e);
+  const NetDims& d = e->L.d;
+  float *dX, *dPi, *dV;
+  train_ws_inputs(e->train, &dX, &dPi, &dV);
+  CUDA_CHECK(cudaMemcpyAsync(dX, X, (size_t)d.B * d.F * d.HW() * 4, cudaMemcpyHostToDevice, e->stream));
+  CUDA_CHECK(cudaMemcpyAsync(dPi, Pi, (size_t)d.B * d.A1 * 4, cudaMemcpyHostToDevice, e->stream));
+  CUDA_CHECK(cudaMemcpyAsync(dV, V, (size_t)d.B * 4, cudaMemcpyHostToDevice, e->stream));
+  train_step_grads(e->train, e->L, e->net_params[net], e->stream, &e->launches);
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (grads_out) CUDA_CHECK(cudaMemcpy(grads_out, train_ws_grads(e->train), e->L.total * 4, cudaMemcpyDeviceToHost));
+  if (cost_out) CUDA_CHECK(cudaMemcpy(cost_out, train_ws_cost(e->train), 4, cudaMemcpyDeviceToHost));
+  GUARD_END(e)
+  return AZ_OK;
+}
+int az_train_apply(az_engine* e, int32_t net, const float* grads, float lr) {
+  if (net < 0 || net > 1) return AZ_ERR_INVALID;
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  ensure_train(e);
+  CUDA_CHECK(cudaMemcpyAsync(train_ws_grads(e->train), grads, e->L.total * 4, cudaMemcpyHostToDevice, e->stream));
+  train_sgd(e->train, e->L, e->net_params[net], lr, 1.0f, e->stream, &e->launches);
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  GUARD_END(e)
+  return AZ_OK;
+}
+
+int az_comm_unique_id(uint8_t id[128]) {
+  try {
+    NcclApi& n = nccl_api();
+    ncclUniqueId u;
+    if (n.GetUniqueId(&u) != ncclSuccess) return AZ_ERR_CUDA;
+    static_assert(sizeof(u) == 128, "ncclUniqueId size");
+    memcpy(id, &u, 128);
+    return AZ_OK;
+  } catch (const std::exception& ex) { g_create_error = ex.what(); return AZ_ERR_UNSUPPORTED; }
+}
+int az_comm_init(az_engine* e, int32_t rank, int32_t world, const uint8_t id[128]) {
+  if (world < 1 || rank < 0 || rank >= world) return AZ_ERR_INVALID;
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  NcclApi& n = nccl_api();
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t c;
+  ncclResult_t r = n.CommInitRank(&c, world, u, rank);
+  if (r != ncclSuccess) throw std::runtime_error(std::string("ncclCommInitRank: ") + n.GetErrorString(r));
+  e->comm = c; e->rank = rank; e->world = world;
+  GUARD_END(e)
+  return AZ_OK;
 }
 
 int az_profile(az_engine* e, int32_t enable, double out[8]) {

@@ -1,0 +1,362 @@
+// agogo_b200 — K7: dual.Train (dualnet/meta.go:16-54) on the device, fp32 CUDA cores.
+// One step = forward in BatchNorm train mode on a batch of exactly BatchSize samples, the
+// reference's loss (dual.go:105-126: "xent" on raw logits, ermahagerdmonards.go:106-147, + MSE on
+// the pre-tanh value), reverse-mode gradients for every Model() tensor (batch-shaped BN affines
+// and biases included), vanilla SGD (meta.go:20,39).  Correctness-first kernels (one thread per
+// output, block reductions, no atomics => deterministic); the tensor-core version of the conv
+// passes is the next optimisation row.  Semantics are pinned against oracle/dual.hpp
+// (dual_train_step), whose backward is itself pinned by a finite-difference check.
+#include <stdexcept>
+#include <vector>
+
+#include "nn.cuh"
+#include "train.cuh"
+
+namespace {
+
+__global__ void k_conv_fwd(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z, int B, int Ci,
+                           int Co, int H, int W, int k) {
+  const int HW = H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Co * HW) return;
+  const int hw = (int)(idx % HW), co = (int)((idx / HW) % Co), b = (int)(idx / ((size_t)HW * Co));
+  const int y = hw / W, xx = hw - y * W, pad = (k - 1) / 2;
+  const float* xb = x + (size_t)b * Ci * HW;
+  const float* wk = w + (size_t)co * Ci * k * k;
+  float acc = 0.0f;
+  for (int ci = 0; ci < Ci; ci++)
+    for (int ky = 0; ky < k; ky++) {
+      int yy = y + ky - pad;
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < k; kx++) {
+        int xc = xx + kx - pad;
+        if (xc < 0 || xc >= W) continue;
+        acc += wk[(ci * k + ky) * k + kx] * xb[(size_t)ci * HW + yy * W + xc];
+      }
+    }
+  z[idx] = acc;
+}
+
+__device__ inline float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = 0.0f;
+  if (threadIdx.x < 32) {
+    r = threadIdx.x < nw ? sh[threadIdx.x] : 0.0f;
+#pragma unroll
+    for (int off = 16; off; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    if (threadIdx.x == 0) sh[0] = r;
+  }
+  __syncthreads();
+  r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// per channel: mean and biased variance over (B, HW)
+__global__ void k_bn_stats(const float* __restrict__ z, float* mean, float* var, int B, int Co, int HW) {
+  __shared__ float sh[32];
+  const int co = blockIdx.x;
+  const int m = B * HW;
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) { int b = i / HW, hw = i - b * HW; s += z[((size_t)b * Co + co) * HW + hw]; }
+  const float mu = block_sum(s, sh) / (float)m;
+  float v = 0.0f;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) { int b = i / HW, hw = i - b * HW; float d = z[((size_t)b * Co + co) * HW + hw] - mu; v += d * d; }
+  const float vv = block_sum(v, sh) / (float)m;
+  if (threadIdx.x == 0) { mean[co] = mu; var[co] = vv; }
+}
+__global__ void k_bn_apply(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ var,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, float* xn, float* y, size_t total,
+                           int Co, int HW) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int co = (int)((idx / HW) % Co);
+  const float sd = sqrtf(var[co] + 1e-5f);
+  const float n = (z[idx] - mean[co]) / sd;
+  xn[idx] = n;
+  const float v = gamma[idx] * n + beta[idx];
+  y[idx] = v > 0.0f ? v : 0.0f;
+}
+__global__ void k_add_relu(const float* __restrict__ a, const float* __restrict__ b, float* out, size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float s = a[idx] + b[idx];
+  out[idx] = s > 0.0f ? s : 0.0f;
+}
+// out[b,o] = sum_j in[b,j] W[j,o] + bias[b,o]  (batch-shaped bias, ermahagerdmonards.go:80-83)
+__global__ void k_linear_fwd(const float* __restrict__ in, const float* __restrict__ Wm, const float* __restrict__ bias,
+                             float* out, int B, int J, int O, int relu) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * O) return;
+  const int b = idx / O, o = idx - b * O;
+  float acc = 0.0f;
+  for (int j = 0; j < J; j++) acc += in[(size_t)b * J + j] * Wm[(size_t)j * O + o];
+  acc += bias[idx];
+  out[idx] = relu ? (acc > 0.0f ? acc : 0.0f) : acc;
+}
+// cost + d cost/d logits + d cost/d vraw (dual.go:105-126)
+__global__ void k_loss(const float* __restrict__ logits, const float* __restrict__ Pi, const float* __restrict__ vraw,
+                       const float* __restrict__ V, float* dlog, float* dv, float* cost, int B, int A) {
+  __shared__ float sh[32];
+  const int n = B * A;
+  float ps = 0.0f;
+  const float invBA = 1.0f / (float)n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    ps += -(Pi[i] * logits[i] + (1.0f - Pi[i]) * (1.0f - logits[i]));
+    dlog[i] = (1.0f - 2.0f * Pi[i]) * invBA;
+  }
+  const float psum = block_sum(ps, sh);
+  float vs = 0.0f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float d = vraw[b] - V[b];
+    vs += d * d;
+    dv[b] = 2.0f * d / (float)B;
+  }
+  const float vsum = block_sum(vs, sh);
+  if (threadIdx.x == 0) *cost = psum / (float)n + vsum / (float)B;
+}
+// dW[j,o] = sum_b in[b,j] dout[b,o]
+__global__ void k_linear_bwd_w(const float* __restrict__ in, const float* __restrict__ dout, float* dW, int B, int J, int O) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= J * O) return;
+  const int j = idx / O, o = idx - j * O;
+  float acc = 0.0f;
+  for (int b = 0; b < B; b++) acc += in[(size_t)b * J + j] * dout[(size_t)b * O + o];
+  dW[idx] = acc;
+}
+// din[b,j] = sum_o W[j,o] dout[b,o]
+__global__ void k_linear_bwd_in(const float* __restrict__ Wm, const float* __restrict__ dout, float* din, int B, int J, int O) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * J) return;
+  const int b = idx / J, j = idx - b * J;
+  float acc = 0.0f;
+  for (int o = 0; o < O; o++) acc += Wm[(size_t)j * O + o] * dout[(size_t)b * O + o];
+  din[idx] = acc;
+}
+__global__ void k_relu_mask(const float* __restrict__ act, float* d, size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n && !(act[idx] > 0.0f)) d[idx] = 0.0f;
+}
+// BN backward, part 1: ReLU gate, dgamma/dbeta (batch-shaped: one contribution each), dxn
+__global__ void k_bn_bwd_pre(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ xn,
+                             const float* __restrict__ gamma, float* dgamma, float* dbeta, float* dxn, size_t total) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float d = y[idx] > 0.0f ? dy[idx] : 0.0f;
+  dgamma[idx] = d * xn[idx];
+  dbeta[idx] = d;
+  dxn[idx] = d * gamma[idx];
+}
+// part 2: dz = (dxn - mean(dxn) - xn * mean(dxn*xn)) / sqrt(var + eps), per channel, in place
+__global__ void k_bn_bwd_apply(float* dxn, const float* __restrict__ xn, const float* __restrict__ var, int B, int Co, int HW) {
+  __shared__ float sh[32];
+  const int co = blockIdx.x;
+  const int m = B * HW;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    int b = i / HW, hw = i - b * HW;
+    size_t idx = ((size_t)b * Co + co) * HW + hw;
+    s1 += dxn[idx];
+    s2 += dxn[idx] * xn[idx];
+  }
+  const float m1 = block_sum(s1, sh) / (float)m;
+  const float m2 = block_sum(s2, sh) / (float)m;
+  const float sd = sqrtf(var[co] + 1e-5f);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    int b = i / HW, hw = i - b * HW;
+    size_t idx = ((size_t)b * Co + co) * HW + hw;
+    dxn[idx] = (dxn[idx] - m1 - xn[idx] * m2) / sd;
+  }
+}
+// dW[co,ci,ky,kx] = sum_{b,y,x} x[b,ci,y+dy,x+dx] dz[b,co,y,x]; one block per (co,ci)
+__global__ void k_conv_bwd_w(const float* __restrict__ x, const float* __restrict__ dz, float* dW, int B, int Ci, int Co,
+                             int H, int W, int k) {
+  __shared__ float sh[32];
+  const int co = blockIdx.x / Ci, ci = blockIdx.x - co * Ci;
+  const int HW = H * W, pad = (k - 1) / 2, m = B * HW;
+  for (int t = 0; t < k * k; t++) {
+    const int ddy = t / k - pad, ddx = t % k - pad;
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      int b = i / HW, hw = i - b * HW;
+      int y = hw / W, xx = hw - y * W;
+      int yy = y + ddy, xc = xx + ddx;
+      if (yy < 0 || yy >= H || xc < 0 || xc >= W) continue;
+      acc += x[((size_t)b * Ci + ci) * HW + yy * W + xc] * dz[((size_t)b * Co + co) * HW + hw];
+    }
+    const float r = block_sum(acc, sh);
+    if (threadIdx.x == 0) dW[((size_t)co * Ci + ci) * k * k + t] = r;
+  }
+}
+// dx[b,ci,y,x] += sum_{co,ky,kx} w[co,ci,ky,kx] dz[b,co,y-dy,x-dx]
+__global__ void k_conv_bwd_in(const float* __restrict__ w, const float* __restrict__ dz, float* dx, int B, int Ci, int Co,
+                              int H, int W, int k) {
+  const int HW = H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * Ci * HW) return;
+  const int hw = (int)(idx % HW), ci = (int)((idx / HW) % Ci), b = (int)(idx / ((size_t)HW * Ci));
+  const int y = hw / W, xx = hw - y * W, pad = (k - 1) / 2;
+  float acc = 0.0f;
+  for (int co = 0; co < Co; co++) {
+    const float* wk = w + ((size_t)co * Ci + ci) * k * k;
+    const float* dzb = dz + ((size_t)b * Co + co) * HW;
+    for (int ky = 0; ky < k; ky++) {
+      int yy = y - (ky - pad);
+      if (yy < 0 || yy >= H) continue;
+      for (int kx = 0; kx < k; kx++) {
+        int xc = xx - (kx - pad);
+        if (xc < 0 || xc >= W) continue;
+        acc += wk[ky * k + kx] * dzb[yy * W + xc];
+      }
+    }
+  }
+  dx[idx] += acc;
+}
+__global__ void k_sgd(float* p, const float* __restrict__ g, float lr, float gscale, size_t n) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) p[idx] = p[idx] - lr * (g[idx] * gscale);
+}
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+struct TrainImpl {
+  NetDims d;
+  std::vector<float*> z, xn, y;   // per unit
+  std::vector<float*> mean, var;  // per unit
+  std::vector<float*> cur;        // block inputs/outputs: cur[0] = init output, cur[i+1] = block i output
+  float *X = nullptr, *Pi = nullptr, *V = nullptr;
+  float *logits = nullptr, *h1 = nullptr, *vraw = nullptr, *dlog = nullptr, *dv = nullptr, *dh1 = nullptr;
+  float *dph = nullptr, *dvh = nullptr, *dcur = nullptr, *dprev = nullptr, *tmp = nullptr, *dl = nullptr;
+  float* cost = nullptr;
+  float* grads = nullptr;
+  std::vector<void*> allocs;
+  float* alloc(size_t n) {
+    float* p;
+    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * 4));
+    allocs.push_back(p);
+    return p;
+  }
+};
+
+void train_ws_alloc(TrainWS& ws, const NetLayout& L) {
+  if (ws.impl) return;
+  TrainImpl* T = new TrainImpl;
+  ws.impl = T;
+  const NetDims& d = L.d;
+  T->d = d;
+  const size_t B = d.B, HW = d.HW();
+  for (const UnitH& u : L.units) {
+    size_t n = B * u.Co * HW;
+    T->z.push_back(T->alloc(n)); T->xn.push_back(T->alloc(n)); T->y.push_back(T->alloc(n));
+    T->mean.push_back(T->alloc(u.Co)); T->var.push_back(T->alloc(u.Co));
+  }
+  const size_t act = B * d.K * HW;
+  for (int i = 0; i <= d.SharedLayers; i++) T->cur.push_back(i == 0 ? nullptr : T->alloc(act));
+  T->X = T->alloc(B * d.F * HW); T->Pi = T->alloc(B * d.A1); T->V = T->alloc(B);
+  T->logits = T->alloc(B * d.A1); T->h1 = T->alloc(B * d.FC); T->vraw = T->alloc(B);
+  T->dlog = T->alloc(B * d.A1); T->dv = T->alloc(B); T->dh1 = T->alloc(B * d.FC);
+  T->dph = T->alloc(B * 2 * HW); T->dvh = T->alloc(B * HW);
+  T->dcur = T->alloc(act); T->dprev = T->alloc(act); T->tmp = T->alloc(act); T->dl = T->alloc(act);
+  T->cost = T->alloc(1);
+  T->grads = T->alloc(L.total);
+}
+void train_ws_free(TrainWS& ws) {
+  TrainImpl* T = (TrainImpl*)ws.impl;
+  if (!T) return;
+  for (void* p : T->allocs) cudaFree(p);
+  delete T;
+  ws.impl = nullptr;
+}
+float* train_ws_grads(TrainWS& ws) { return ((TrainImpl*)ws.impl)->grads; }
+float* train_ws_cost(TrainWS& ws) { return ((TrainImpl*)ws.impl)->cost; }
+void train_ws_inputs(TrainWS& ws, float** X, float** Pi, float** V) {
+  TrainImpl* T = (TrainImpl*)ws.impl;
+  *X = T->X; *Pi = T->Pi; *V = T->V;
+}
+
+// forward + backward: fills grads (every Model() tensor gets exactly one contribution) and cost
+void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStream_t st, unsigned long long* launches) {
+  TrainImpl* T = (TrainImpl*)ws.impl;
+  const NetDims& d = L.d;
+  const int B = d.B, H = d.H, W = d.W, HW = d.HW(), K = d.K, A = d.A1, FC = d.FC;
+  const int Lr = d.SharedLayers, pu = 1 + 2 * Lr, vu = pu + 1;
+  auto Pp = [&](int i) { return P + L.desc[i].offset; };
+  auto Gp = [&](int i) { return T->grads + L.desc[i].offset; };
+  unsigned long long nl = 0;
+  auto unit_fwd = [&](int ui, const float* x) {
+    const UnitH& u = L.units[ui];
+    size_t n = (size_t)B * u.Co * HW;
+    k_conv_fwd<<<nblk(n), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
+    k_bn_stats<<<u.Co, 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
+    k_bn_apply<<<nblk(n), 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], Pp(u.gamma), Pp(u.beta), T->xn[ui], T->y[ui], n, u.Co, HW);
+    nl += 3;
+  };
+  // ---- forward
+  unit_fwd(0, T->X);
+  const float* cur = T->y[0];
+  const size_t act = (size_t)B * K * HW;
+  for (int i = 0; i < Lr; i++) {
+    unit_fwd(1 + 2 * i, cur);
+    unit_fwd(2 + 2 * i, cur);
+    k_add_relu<<<nblk(act), 256, 0, st>>>(T->y[1 + 2 * i], T->y[2 + 2 * i], T->cur[i + 1], act);
+    nl++;
+    cur = T->cur[i + 1];
+  }
+  unit_fwd(pu, cur);
+  unit_fwd(vu, cur);
+  k_linear_fwd<<<nblk((size_t)B * A), 256, 0, st>>>(T->y[pu], Pp(L.pW), Pp(L.pB), T->logits, B, 2 * HW, A, 0);
+  k_linear_fwd<<<nblk((size_t)B * FC), 256, 0, st>>>(T->y[vu], Pp(L.vW), Pp(L.vB), T->h1, B, HW, FC, 1);
+  k_linear_fwd<<<nblk(B), 256, 0, st>>>(T->h1, Pp(L.voW), Pp(L.voB), T->vraw, B, FC, 1, 0);
+  k_loss<<<1, 256, 0, st>>>(T->logits, T->Pi, T->vraw, T->V, T->dlog, T->dv, T->cost, B, A);
+  nl += 4;
+  // ---- backward: heads
+  CUDA_CHECK(cudaMemcpyAsync(Gp(L.pB), T->dlog, (size_t)B * A * 4, cudaMemcpyDeviceToDevice, st));
+  k_linear_bwd_w<<<nblk((size_t)2 * HW * A), 256, 0, st>>>(T->y[pu], T->dlog, Gp(L.pW), B, 2 * HW, A);
+  k_linear_bwd_in<<<nblk((size_t)B * 2 * HW), 256, 0, st>>>(Pp(L.pW), T->dlog, T->dph, B, 2 * HW, A);
+  CUDA_CHECK(cudaMemcpyAsync(Gp(L.voB), T->dv, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  k_linear_bwd_w<<<nblk(FC), 256, 0, st>>>(T->h1, T->dv, Gp(L.voW), B, FC, 1);
+  k_linear_bwd_in<<<nblk((size_t)B * FC), 256, 0, st>>>(Pp(L.voW), T->dv, T->dh1, B, FC, 1);
+  k_relu_mask<<<nblk((size_t)B * FC), 256, 0, st>>>(T->h1, T->dh1, (size_t)B * FC);
+  CUDA_CHECK(cudaMemcpyAsync(Gp(L.vB), T->dh1, (size_t)B * FC * 4, cudaMemcpyDeviceToDevice, st));
+  k_linear_bwd_w<<<nblk((size_t)HW * FC), 256, 0, st>>>(T->y[vu], T->dh1, Gp(L.vW), B, HW, FC);
+  k_linear_bwd_in<<<nblk((size_t)B * HW), 256, 0, st>>>(Pp(L.vW), T->dh1, T->dvh, B, HW, FC);
+  nl += 7;
+  // ---- backward: units
+  auto unit_bwd = [&](int ui, const float* x, const float* dy, float* dx) {
+    const UnitH& u = L.units[ui];
+    size_t n = (size_t)B * u.Co * HW;
+    k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n);
+    k_bn_bwd_apply<<<u.Co, 256, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
+    k_conv_bwd_w<<<u.Co * u.Ci, 256, 0, st>>>(x, T->tmp, Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
+    nl += 3;
+    if (dx) { k_conv_bwd_in<<<nblk((size_t)B * u.Ci * HW), 256, 0, st>>>(Pp(u.filter), T->tmp, dx, B, u.Ci, u.Co, H, W, u.k); nl++; }
+  };
+  CUDA_CHECK(cudaMemsetAsync(T->dcur, 0, act * 4, st));
+  unit_bwd(pu, cur, T->dph, T->dcur);
+  unit_bwd(vu, cur, T->dvh, T->dcur);
+  for (int i = Lr - 1; i >= 0; i--) {
+    // out = relu(l1 + l2): gate on the block output
+    CUDA_CHECK(cudaMemcpyAsync(T->dl, T->dcur, act * 4, cudaMemcpyDeviceToDevice, st));
+    k_relu_mask<<<nblk(act), 256, 0, st>>>(T->cur[i + 1], T->dl, act);
+    nl++;
+    CUDA_CHECK(cudaMemsetAsync(T->dprev, 0, act * 4, st));
+    const float* xin = i == 0 ? T->y[0] : T->cur[i];
+    unit_bwd(1 + 2 * i, xin, T->dl, T->dprev);
+    unit_bwd(2 + 2 * i, xin, T->dl, T->dprev);
+    std::swap(T->dcur, T->dprev);
+  }
+  unit_bwd(0, T->X, T->dcur, nullptr);
+  if (launches) *launches += nl;
+}
+
+void train_sgd(TrainWS& ws, const NetLayout& L, float* P, float lr, float gscale, cudaStream_t st, unsigned long long* launches) {
+  TrainImpl* T = (TrainImpl*)ws.impl;
+  k_sgd<<<nblk(L.total), 256, 0, st>>>(P, T->grads, lr, gscale, L.total);
+  if (launches) (*launches)++;
+}

@@ -1,0 +1,366 @@
+"""Host-side mirror of gorgonia/agogo's API layer for the self-play path, over the C ABI.
+
+The reference's host is Go (agogo.go, arena.go, agent.go); this image has no Go toolchain, so the same
+composition — same names, argument meaning and error behaviour — is provided here in Python over
+`ctypes` (the cgo equivalent is go/agogo_b200.go + INTEGRATION.md).  Everything numeric happens inside
+the engine library; this file only sequences calls the way `AZ.Learn` (agogo.go:100-172) does and
+replaces the reference's time-seeded RNGs by the injected splitmix64 streams of DESIGN.md §2.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi as K
+
+_M64 = (1 << 64) - 1
+
+
+def _splitmix(state):
+    state = (state + 0x9E3779B97F4A7C15) & _M64
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return state, z ^ (z >> 31)
+
+
+def derive_seed(seed, stream):
+    s = (seed ^ ((0xD1B54A32D192ED03 * (stream + 1)) & _M64)) & _M64
+    return _splitmix(s)[1]
+
+
+class Rng:
+    def __init__(self, seed):
+        self.s = seed & _M64
+
+    def intn(self, n):
+        self.s, v = _splitmix(self.s)
+        return v % n
+
+
+@dataclass
+class DualConfig:
+    """dual.Config (dualnet/config.go:4-16)."""
+    K: int = 0
+    SharedLayers: int = 0
+    FC: int = 0
+    L2: float = 0.0
+    BatchSize: int = 0
+    Width: int = 0
+    Height: int = 0
+    Features: int = 0
+    ActionSpace: int = 0
+    FwdOnly: bool = False
+
+    def IsValid(self):  # config.go:33-42
+        return (self.K >= 1 and self.ActionSpace >= 3 and self.SharedLayers >= 0 and self.FC > 1 and
+                self.BatchSize >= 1 and self.Features > 0)
+
+
+def dual_round(a):  # config.go:44-59
+    n = a - 1
+    for sh in (1, 2, 4, 8, 16):
+        n |= n >> sh
+    n += 1
+    lt = n // 2
+    return lt if (a - lt) < (n - a) else n
+
+
+def DefaultConf(m, n, actionSpace):  # config.go:18-31
+    k = dual_round((m * n) // 3)
+    return DualConfig(K=k, SharedLayers=m, FC=2 * k, BatchSize=256, Width=n, Height=m, Features=18,
+                      ActionSpace=actionSpace)
+
+
+@dataclass
+class MCTSConfig:
+    """mcts.Config (mcts/tree.go:15-29) + Sims (the fixed-iteration mode the reference lacks)."""
+    PUCT: float = 1.0
+    Timeout: int = 0
+    M: int = 0
+    N: int = 0
+    RandomCount: int = 0
+    Budget: int = 0
+    RandomMinVisits: int = 0
+    RandomTemperature: float = 0.0
+    DumbPass: bool = True
+    ResignPercentage: float = 0.0
+    PassPreference: int = K.DONT_PREFER_PASS
+    Sims: int = 100
+
+    def IsValid(self):  # tree.go:43-45
+        return 0 < self.PUCT <= 1
+
+
+def DefaultConfig(boardSize):  # mcts/tree.go:31-41
+    return MCTSConfig(PUCT=1.0, Timeout=100_000_000, M=boardSize, N=boardSize, DumbPass=True,
+                      PassPreference=K.DONT_PREFER_PASS, Budget=10000)
+
+
+@dataclass
+class Game:
+    """Which game.State the engine instantiates (mnk.New / c4.New / wq.New)."""
+    kind: int
+    m: int
+    n: int
+    k: int = 0
+    komi: float = 0.0
+    max_moves: int = 0
+    zobrist_seed: int = 12345
+
+
+@dataclass
+class Config:
+    """agogo.Config (datatypes.go:14-25).  Encoder is an az_encoder_kind; Augmenter stays a Python callable."""
+    Name: str = ""
+    NNConf: DualConfig = field(default_factory=DualConfig)
+    MCTSConf: MCTSConfig = field(default_factory=MCTSConfig)
+    UpdateThreshold: float = 0.0
+    MaxExamples: int = 0
+    Encoder: int = K.ENC_TWO_PLANE
+    Augmenter: object = None
+
+
+@dataclass
+class Example:  # datatypes.go:38-42
+    Board: np.ndarray
+    Policy: np.ndarray
+    Value: float
+
+
+class Agent:
+    """agent.go:14-121 — a view on one of the engine's two agents."""
+
+    def __init__(self, az, idx):
+        self._az, self.idx, self.Player = az, idx, K.NONE
+
+    @property
+    def Wins(self):
+        return self._az.engine.stats(self.idx)[0]
+
+    @property
+    def Loss(self):
+        return self._az.engine.stats(self.idx)[1]
+
+    @property
+    def Draw(self):
+        return self._az.engine.stats(self.idx)[2]
+
+    def SwitchToInference(self):  # agent.go:42-57
+        self._az.engine.set_inferer(self.idx, K.INF_DUAL)
+
+    def useDummy(self):  # agent.go:105-113: captures the agent's current colour
+        self._az.engine.set_inferer(self.idx, K.INF_DUMMY, self.Player)
+
+    def NNOutput(self, planes):  # agent.go:83-89
+        return self._az.engine.infer(self.idx, planes)
+
+    def resetStats(self):
+        self._az.engine.reset_stats(self.idx)
+
+
+def shuffle_rows(Xs, Pi, V, rng):
+    """shuffleBatch (meta.go:57-102): Fisher-Yates over rows with j = r.Intn(i+1) (same stream as az_train)."""
+    for i in range(len(V)):
+        j = rng.intn(i + 1)
+        if i != j:
+            Xs[[i, j]] = Xs[[j, i]]
+            Pi[[i, j]] = Pi[[j, i]]
+            V[[i, j]] = V[[j, i]]
+
+
+class AZ:
+    """agogo.AZ (agogo.go:21-39): New / SelfPlay / Learn / Save / Load over one engine handle.
+
+    Multi-GPU: one AZ per rank (`dist` = an initialised torch.distributed module or None).
+    Self-play and arena games are sharded by game with no communication; examples are all-gathered so every
+    rank prepares the same batches and trains on its share of them; gradients are averaged across ranks every
+    step — inside the engine over NCCL when `az_comm_init` succeeded, otherwise by the host through `dist`
+    (the CPU/gloo tests) — so all replicas hold identical weights; win counts are summed."""
+
+    def __init__(self, game, conf, lib=None, n_games=None, seed=1, device=0, flags=0, dist=None,
+                 host_allreduce=False):  # agogo.New, agogo.go:41-73
+        if not conf.NNConf.IsValid():
+            raise RuntimeError("NNConf is not valid. Unable to proceed")  # the reference panics
+        if not conf.MCTSConf.IsValid():
+            raise RuntimeError("MCTSConf is not valid. Unable to proceed")
+        self.lib = lib if lib is not None else K.load()
+        self.conf, self.game, self.seed = conf, game, seed
+        self.n_games = n_games or 64
+        d = K.EngineDesc()
+        d.game = K.GameDesc(game.kind, game.m, game.n, game.k, game.komi, game.max_moves, game.zobrist_seed)
+        m, n = conf.MCTSConf, conf.NNConf
+        d.mcts = K.MCTSConfig(m.PUCT, m.Timeout, m.M, m.N, m.RandomCount, m.Budget, m.RandomMinVisits,
+                              m.RandomTemperature, int(m.DumbPass), m.ResignPercentage, m.PassPreference, m.Sims)
+        d.nn = K.DualConfig(n.K, n.SharedLayers, n.FC, n.L2, n.BatchSize, n.Width, n.Height, n.Features, n.ActionSpace,
+                            int(n.FwdOnly))
+        d.encoder, d.n_games, d.device, d.flags = conf.Encoder, self.n_games, device, flags
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        d.seed = derive_seed(seed, 102 if self.rank == 0 else 102 + 7919 * self.rank)  # per-rank coin stream
+        self.engine = self.lib.create(d)
+        self.engine_comm = False
+        self.host_allreduce = host_allreduce
+        if self.world > 1 and not host_allreduce:
+            self._init_engine_comm()
+        self.engine.net_init(0, derive_seed(seed, 100))  # a.Init(), b.Init() (agogo.go:52-57)
+        self.engine.net_init(1, derive_seed(seed, 101))
+        self.A, self.B = Agent(self, 0), Agent(self, 1)
+        self.useDummy = True
+        self.epoch = 0
+        self.log = []
+
+    def _init_engine_comm(self):
+        """NCCL communicator inside the engine: rank 0 creates the id, the host group broadcasts it."""
+        import torch
+        try:
+            uid = K.comm_unique_id(self.lib)  # every rank probes; rank 0's id is the one used
+        except K.AZError:
+            return  # library without NCCL (the oracle): gradients go through the host group instead
+        t = torch.tensor(list(uid), dtype=torch.uint8)
+        if self.dist.get_backend() == "nccl":
+            t = t.cuda()
+        self.dist.broadcast(t, 0)
+        self.engine.comm_init(self.rank, self.world, bytes(t.cpu().tolist()))
+        self.engine_comm = True
+
+    def _share(self, n):
+        """games of this rank when n games are sharded round-robin"""
+        return len(range(self.rank, n, self.world))
+
+    def _gather_examples(self, ex):
+        if self.world == 1:
+            return ex
+        out = [None] * self.world
+        self.dist.all_gather_object(out, [(x.Board, x.Policy, x.Value) for x in ex])
+        return [Example(b, p, v) for part in out for (b, p, v) in part]
+
+    def _train(self, Xs, Pi, V, batches, nniters, seed):
+        """dual.Train (meta.go:16-54) on this rank's share of the batches, gradients averaged over ranks."""
+        e, bs = self.engine, self.conf.NNConf.BatchSize
+        if self.world == 1 and not self.host_allreduce:
+            return e.train(1, Xs, Pi, V, batches, nniters, lr=0.1, shuffle_seed=seed)
+        usable = (batches // self.world) * self.world
+        if usable == 0:
+            raise RuntimeError("batches is nil, probably too few examples regarding the batchsize")
+        mine = [b for b in range(usable) if b % self.world == self.rank]
+        rows = np.concatenate([np.arange(b * bs, (b + 1) * bs) for b in mine])
+        Xl, Pl, Vl = Xs[rows].copy(), Pi[rows].copy(), V[rows].copy()
+        lseed = (seed + self.rank) & _M64
+        if self.engine_comm:
+            return e.train(1, Xl, Pl, Vl, len(mine), nniters, lr=0.1, shuffle_seed=lseed)
+        import torch
+        costs, rng = [], Rng(lseed)
+        for _ in range(nniters):
+            for bat in range(len(mine)):
+                sl = slice(bat * bs, (bat + 1) * bs)
+                g, c = e.train_grads(1, Xl[sl], Pl[sl], Vl[sl])
+                if self.world > 1:
+                    t = torch.from_numpy(g)
+                    self.dist.all_reduce(t)
+                    g = (t / self.world).numpy()
+                e.train_apply(1, g, 0.1)
+                costs.append(c)
+            shuffle_rows(Xl, Pl, Vl, rng)
+        return np.array(costs, np.float32)
+
+    def _global_stats(self):
+        aw, al, ad = self.engine.stats(0)
+        bw, bl, bd = self.engine.stats(1)
+        v = np.array([aw, al, ad, bw, bl, bd], np.float64)
+        if self.world > 1:
+            import torch
+            t = torch.from_numpy(v)
+            if self.dist.get_backend() == "nccl":
+                t = t.cuda()
+            self.dist.all_reduce(t)
+            v = t.cpu().numpy()
+        return tuple(np.float32(x) for x in v)
+
+    # ---- self-play -----------------------------------------------------------------------------
+    def setupSelfPlay(self, it):  # agogo.go:75-90
+        self.A.SwitchToInference()
+        self.B.SwitchToInference()
+        if it == 0 and self.useDummy:
+            self.A.useDummy()
+            self.B.useDummy()
+
+    def _play(self, n, record):
+        """n x (Arena.Play(record, nil, aug); game.Reset()) (agogo.go:93-97,144-148), concurrently."""
+        e = self.engine
+        e.examples(clear=True)
+        if n <= 0:
+            return []
+        e.arena_play(n, record)
+        last = e.game_record(n - 1)
+        self.A.Player = last["a_player"]
+        self.B.Player = K.WHITE if last["a_player"] == K.BLACK else K.BLACK
+        boards, pols, vals = e.examples(clear=True)
+        ex = [Example(boards[i], pols[i], float(vals[i])) for i in range(len(vals))]
+        if record and self.conf.Augmenter is not None:
+            ex = [y for x in ex for y in self.conf.Augmenter(x)]
+        return ex
+
+    def SelfPlay(self, episodes=1):
+        return self._play(episodes, True)
+
+    @staticmethod
+    def shuffleExamples(ex, seed):  # agogo.go:251-257 with an injected seed
+        r = Rng(seed)
+        for i in range(len(ex)):
+            j = r.intn(i + 1)
+            ex[i], ex[j] = ex[j], ex[i]
+
+    def prepareExamples(self, ex, seed):  # agogo.go:211-249
+        self.shuffleExamples(ex, seed)
+        bs = self.conf.NNConf.BatchSize
+        batches = len(ex) // bs
+        total = batches * bs
+        if batches == 0:
+            return None, None, None, 0
+        Xs = np.stack([x.Board for x in ex[:total]]).astype(np.float32)
+        Pi = np.stack([x.Policy for x in ex[:total]]).astype(np.float32)
+        V = np.array([x.Value for x in ex[:total]], np.float32)
+        return Xs, Pi, V, batches
+
+    # ---- AZ.Learn (agogo.go:100-172) ----------------------------------------------------------
+    def Learn(self, iters, episodes, nniters, arenaGames):
+        e = self.engine
+        for self.epoch in range(iters):
+            ep = self.epoch
+            self.setupSelfPlay(ep)
+            ex = self._gather_examples(self._play(self._share(episodes), True))
+            if self.conf.MaxExamples > 0 and len(ex) > self.conf.MaxExamples:
+                self.shuffleExamples(ex, derive_seed(self.seed, 1000 + 10 * ep))
+                ex = ex[:self.conf.MaxExamples]
+            Xs, Pi, V, batches = self.prepareExamples(ex, derive_seed(self.seed, 1001 + 10 * ep))
+            if batches == 0:
+                raise RuntimeError("batches is nil, probably too few examples regarding the batchsize")
+            costs = self._train(Xs, Pi, V, batches, nniters, derive_seed(self.seed, 1002 + 10 * ep))
+            self.B.SwitchToInference()
+            self.A.resetStats()
+            self.B.resetStats()
+            self._play(self._share(arenaGames), False)
+            aw, al, ad, bw, bl, bd = self._global_stats()
+            with np.errstate(invalid="ignore", divide="ignore"):
+                ratio = np.float32(bw) / (np.float32(bw) + np.float32(aw))
+            promoted = bool(ratio > np.float32(self.conf.UpdateThreshold))  # NaN (0/0) never promotes
+            if promoted:
+                e.net_copy(0, 1)  # A.NN = B.NN (agogo.go:161)
+            e.net_init(1, derive_seed(self.seed, 200 + ep))  # newB (arena.go:205-224)
+            self.log.append(dict(a=(float(aw), float(al), float(ad)), b=(float(bw), float(bl), float(bd)), n_examples=len(ex), batches=batches, promoted=promoted,
+                                 first_cost=float(costs[0]), last_cost=float(costs[-1])))
+        return None
+
+    # ---- checkpoint: Model()-ordered flat payload (the gob container stays on the Go side) ---------
+    def Save(self, filename):
+        nt, _ = self.engine.param_count()
+        descs = [self.engine.param_desc(i) for i in range(nt)]
+        np.savez(filename, params=self.engine.net_get(0), names=np.array([d[0] for d in descs]),
+                 shapes=np.array([list(d[1]) + [1] * (4 - len(d[1])) for d in descs]))
+
+    def Load(self, filename):  # agogo.go:187-209: both A and B get the stored net, useDummy is cleared
+        z = np.load(filename if str(filename).endswith(".npz") else str(filename) + ".npz")
+        self.engine.net_set(0, z["params"])
+        self.engine.net_set(1, z["params"])
+        self.useDummy = False

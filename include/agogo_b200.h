@@ -186,7 +186,18 @@ int az_rules_status(az_engine* e, int32_t n, const int32_t* boards, const int32_
 int az_train(az_engine* e, int32_t net, float* Xs, float* Pi, float* V, int32_t batches, int32_t iterations,
              float lr, uint64_t shuffle_seed, float* costs_out);
 
-/* ---- multi-GPU: gradient all-reduce only -------------------------------------- */
+/* One Train step split at the solver boundary (meta.go:36-41: RunAll, then solver.Step): gradients
+ * of one batch of exactly batch_size samples for every Model() tensor, flat in Model() order, and
+ * their application w -= lr * g.  Lets a host all-reduce the gradients itself (the gloo tests do). */
+int az_train_grads(az_engine* e, int32_t net, const float* X, const float* Pi, const float* V, float* grads_out,
+                   float* cost_out);
+int az_train_apply(az_engine* e, int32_t net, const float* grads, float lr);
+
+/* ---- multi-GPU: gradient all-reduce only --------------------------------------
+ * az_comm_init joins an NCCL communicator (one rank per GPU/process; id from az_comm_unique_id on
+ * rank 0, distributed by the host).  With a communicator, every az_train step all-reduces (sum)
+ * the flat gradient buffer over NVLink and applies w -= lr * g / world, so replicas stay identical;
+ * every rank must call az_train with the same batches/iterations. */
 int az_comm_unique_id(uint8_t id[128]);
 int az_comm_init(az_engine* e, int32_t rank, int32_t world, const uint8_t id[128]);
 

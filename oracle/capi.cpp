@@ -369,6 +369,24 @@ int az_train(az_engine* e, int32_t net, float* Xs, float* Pi, float* V, int32_t 
   return AZ_OK;
 }
 
+int az_train_grads(az_engine* e, int32_t net, const float* X, const float* Pi, const float* V, float* grads_out,
+                   float* cost_out) {
+  if (net < 0 || net > 1) return AZ_ERR_INVALID;
+  GUARD_BEGIN
+  std::vector<float> g;
+  float c = dual_train_step(*e->nets[net], X, Pi, V, 0.0f, &g);
+  if (grads_out) memcpy(grads_out, g.data(), g.size() * 4);
+  if (cost_out) *cost_out = c;
+  GUARD_END(e)
+  return AZ_OK;
+}
+int az_train_apply(az_engine* e, int32_t net, const float* grads, float lr) {
+  if (net < 0 || net > 1) return AZ_ERR_INVALID;
+  std::vector<float>& p = e->nets[net]->params;
+  for (size_t i = 0; i < p.size(); i++) p[i] = p[i] - lr * grads[i];  // VanillaSolver (meta.go:20,39)
+  return AZ_OK;
+}
+
 int az_comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return AZ_ERR_UNSUPPORTED; }
 int az_comm_init(az_engine*, int32_t, int32_t, const uint8_t*) { return AZ_ERR_UNSUPPORTED; }
 

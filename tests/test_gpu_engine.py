@@ -204,3 +204,74 @@ def test_tc_selfplay_runs(oracle, engine_lib):
     for ra, rb in zip(a["records"], b["records"]):
         assert list(ra["moves"]) == list(rb["moves"])
     assert a["counters"]["evals"] == b["counters"]["evals"]
+
+
+def _train_data(rng, B, plane, A1):
+    X = rng.choice([0.001, 1.0, -1.0], size=(B, plane)).astype(np.float32)
+    Pi = np.zeros((B, A1), np.float32)
+    Pi[np.arange(B), rng.integers(0, A1, B)] = 1
+    V = rng.choice([-1.0, 0.0, 1.0], B).astype(np.float32)
+    return X, Pi, V
+
+
+@pytest.mark.parametrize("kind,m,n,k,nn", [
+    (K.GAME_MNK, 3, 3, 3, dict(k=3, shared_layers=3, fc=8, batch_size=20, features=2, action_space=10)),   # cmd/tictactoe
+    (K.GAME_C4, 6, 7, 4, dict(k=16, shared_layers=2, fc=32, batch_size=16, features=2, action_space=8)),   # C4 shapes
+])
+def test_train_grads_vs_oracle(oracle, engine_lib, kind, m, n, k, nn):
+    """One Train step (BN train mode, xent-on-logits + MSE, reverse mode): CUDA gradients of every
+    Model() tensor against the oracle's (itself pinned by finite differences)."""
+    def desc():
+        return K.make_desc(kind, m, n, k, sims=2, n_games=2, seed=1, nn=nn, flags=K.FLAG_FP32_TOWER)
+    eo, eg = oracle.create(desc()), engine_lib.create(desc())
+    H.tame_gammas([eo, eg], 1, 17, target=0.05)
+    rng = np.random.default_rng(2)
+    X, Pi, V = _train_data(rng, nn["batch_size"], 2 * m * n, nn["action_space"])
+    go, co = eo.train_grads(1, X, Pi, V)
+    gg, cg = eg.train_grads(1, X, Pi, V)
+    assert abs(co - cg) <= 1e-5 * max(1, abs(co))
+    scale = np.abs(go).max()
+    assert np.abs(go - gg).max() <= 2e-4 * scale, (np.abs(go - gg).max(), scale)
+    # and the solver step
+    eo.train_apply(1, go, 0.1); eg.train_apply(1, gg, 0.1)
+    assert np.abs(eo.net_get(1) - eg.net_get(1)).max() <= 1e-4 * max(1.0, scale)
+
+
+def test_train_loop_vs_oracle(oracle, engine_lib):
+    """dual.Train (meta.go:16-54): 3 batches x 5 passes with the per-pass row shuffle; costs and weights."""
+    nn = dict(k=3, shared_layers=3, fc=8, batch_size=20, features=2, action_space=10)
+    def desc():
+        return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=2, n_games=2, seed=1, nn=nn, flags=K.FLAG_FP32_TOWER)
+    eo, eg = oracle.create(desc()), engine_lib.create(desc())
+    H.tame_gammas([eo, eg], 1, 17, target=0.05)
+    X, Pi, V = _train_data(np.random.default_rng(4), 60, 18, 10)
+    co = eo.train(1, X.copy(), Pi.copy(), V.copy(), 3, 5, lr=0.1, shuffle_seed=99)
+    cg = eg.train(1, X.copy(), Pi.copy(), V.copy(), 3, 5, lr=0.1, shuffle_seed=99)
+    assert np.isfinite(cg).all()
+    assert np.abs(co - cg).max() <= 2e-3 * np.abs(co).max(), (co, cg)
+    assert co[-1] < co[0]
+    po, pg = eo.net_get(1), eg.net_get(1)
+    assert np.abs(po - pg).max() <= 5e-3 * np.abs(po).max()
+
+
+def test_c1_learn_on_device(oracle, engine_lib):
+    """BASELINE config C1 shape on the device through the host mirror: tic-tac-toe AZ.Learn — epoch 0
+    self-play (dummy inferer) is bit-exact against the oracle run; the whole loop completes with
+    finite costs and a decision per epoch."""
+    from agogo_b200 import host
+    from tests.test_host_learn import _c1_conf
+    conf = _c1_conf(batch=20, sims=20)
+    ag = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=engine_lib, n_games=16, seed=42)
+    ao = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle, n_games=16, seed=42)
+    for az in (ag, ao):
+        az.setupSelfPlay(0)
+    xg, xo = ag._play(12, True), ao._play(12, True)
+    assert len(xg) == len(xo)
+    for a, b in zip(xg, xo):
+        assert (a.Board == b.Board).all() and (a.Policy == b.Policy).all() and a.Value == b.Value
+    ag2 = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=engine_lib, n_games=16, seed=43)
+    ag2.Learn(2, 12, 4, 10)
+    assert len(ag2.log) == 2
+    for l in ag2.log:
+        assert np.isfinite(l["first_cost"]) and np.isfinite(l["last_cost"]) and l["n_examples"] > 0
+        assert sum(l["a"]) == 10 and sum(l["b"]) == 10

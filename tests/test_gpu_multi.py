@@ -1,0 +1,41 @@
+"""Multi-GPU (needs >= 2 devices; skipped otherwise): sharded AZ.Learn with the engine's own NCCL
+gradient all-reduce — replicas must end bit-identical."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from agogo_b200 import _capi as K
+    from agogo_b200 import host
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    nn = host.DualConfig(K=16, SharedLayers=2, FC=32, BatchSize=16, Width=7, Height=6, Features=2, ActionSpace=8)
+    mc = host.MCTSConfig(PUCT=1.0, M=6, N=7, Sims=16)
+    conf = host.Config(NNConf=nn, MCTSConf=mc, UpdateThreshold=0.52)
+    az = host.AZ(host.Game(K.GAME_C4, 6, 7, 4), conf, n_games=8, seed=5, dist=dist, device=rank, flags=K.FLAG_FP32_TOWER)
+    assert az.engine_comm
+    az.Learn(2, 8, 2, 6)
+    np.save(os.path.join(out_dir, "params_%d.npy" % rank), np.concatenate([az.engine.net_get(0), az.engine.net_get(1)]))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_learn_nccl(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    p0, p1 = np.load(tmp_path / "params_0.npy"), np.load(tmp_path / "params_1.npy")
+    assert np.isfinite(p0).all()
+    assert (p0.view(np.uint32) == p1.view(np.uint32)).all(), "replicas diverged"

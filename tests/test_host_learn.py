@@ -1,0 +1,66 @@
+"""AZ.Learn composition (agogo.go:100-172): the host-side mirror (agogo_b200/host.py) driving the
+C ABI must reproduce the oracle's native restatement of the same loop, epoch by epoch — statistics,
+example counts, promotion decisions, training costs and the final weights (BASELINE config C1:
+tic-tac-toe, cmd/tictactoe shapes; "plumbing, no GPU")."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from agogo_b200 import _capi as K
+from agogo_b200 import host
+
+
+def _c1_conf(batch, sims):
+    nn = host.DefaultConf(3, 3, 10)  # cmd/tictactoe/main.go:63-70
+    nn.BatchSize, nn.Features, nn.K, nn.SharedLayers = batch, 2, 3, 3
+    mc = host.MCTSConfig(PUCT=1.0, M=3, N=3, Timeout=100_000_000, PassPreference=K.DONT_PREFER_PASS, Budget=1000,
+                         DumbPass=True, RandomCount=0, Sims=sims)
+    return host.Config(Name="Tic Tac Toe", NNConf=nn, MCTSConf=mc, UpdateThreshold=0.52, Encoder=K.ENC_TWO_PLANE)
+
+
+def _native_learn(oracle, az, iters, episodes, nniters, arena_games, threshold):
+    """oracle::AZ::Learn through the oracle-only entry point azo_learn."""
+    d = K.EngineDesc.from_buffer_copy(bytes(az.engine.desc))
+    d.seed = az.seed
+    f = oracle.dll.azo_learn
+    f.restype = C.c_int
+    log = np.zeros((iters, 11), np.float32)
+    nfl = az.engine.param_count()[1]
+    final = np.zeros(nfl, np.float32)
+    rc = f(C.byref(d), C.c_double(threshold), C.c_int32(0), C.c_int32(iters), C.c_int32(episodes), C.c_int32(nniters),
+           C.c_int32(arena_games), log.ctypes.data_as(C.POINTER(C.c_float)), final.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0, oracle.dll.az_last_error(None)
+    return log, final
+
+
+def test_c1_learn_host_vs_native_oracle(oracle):
+    conf = _c1_conf(batch=20, sims=20)
+    az = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle, n_games=8, seed=42)
+    assert az.engine.param_desc(0)[0] == "FilterInit"
+    iters, episodes, nniters, arena_games = 3, 12, 4, 10
+    az.Learn(iters, episodes, nniters, arena_games)
+    log, final = _native_learn(oracle, az, iters, episodes, nniters, arena_games, conf.UpdateThreshold)
+    for ep in range(iters):
+        h, n = az.log[ep], log[ep]
+        assert h["a"] == tuple(n[0:3]) and h["b"] == tuple(n[3:6]), (ep, h, n)
+        assert h["n_examples"] == int(n[6]) and h["batches"] == int(n[7]) and int(h["promoted"]) == int(n[8])
+        assert np.float32(h["first_cost"]) == n[9] and np.float32(h["last_cost"]) == n[10], (ep, h, n)
+    assert (az.engine.net_get(0).view(np.uint32) == final.view(np.uint32)).all()
+
+
+def test_invalid_configs_panic(oracle):
+    conf = _c1_conf(20, 10)
+    conf.MCTSConf.PUCT = 1.5  # mcts.Config.IsValid (tree.go:43-45)
+    with pytest.raises(RuntimeError):
+        host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle)
+    conf = _c1_conf(20, 10)
+    conf.NNConf.ActionSpace = 2  # dual.Config.IsValid (config.go:33-42)
+    with pytest.raises(RuntimeError):
+        host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle)
+
+
+def test_round_kats():
+    from tests.golden import rules_golden as G
+    for a, want in G.ROUND:
+        assert host.dual_round(a) == want
