@@ -228,6 +228,81 @@ __global__ void k_heads_f32(const float* __restrict__ ph, const float* __restric
   for (int a = threadIdx.x; a < A1; a += blockDim.x) policy[(size_t)b * ldp + a] = __fdiv_rn(logits[a], ssum);
 }
 
+// Throughput version of the heads for the tensor-core path: SB samples per block share every weight
+// load (the per-sample kernel above re-reads Policy_w from L2 for each sample).  Accumulation per
+// output still runs in ascending j; the softmax sum and the final dot product use warp reductions.
+template <int SB>
+__global__ void k_heads_tiled(const float* __restrict__ ph, const float* __restrict__ vh, const float* __restrict__ Wp,
+                              const float* __restrict__ bp, const float* __restrict__ Wv, const float* __restrict__ bv,
+                              const float* __restrict__ Wo, const float* __restrict__ bo, float* policy, int ldp,
+                              float* value, const int* __restrict__ n_dev, int n_max, int HW, int A1, int FC) {
+  extern __shared__ float sm[];
+  const int n = min(*n_dev, n_max);
+  const int b0 = blockIdx.x * SB;
+  if (b0 >= n) return;
+  const int nb = min(SB, n - b0);
+  const int J2 = 2 * HW;
+  float* phs = sm;                  // [SB][2HW]
+  float* vhs = phs + SB * J2;       // [SB][HW]
+  float* lg = vhs + SB * HW;        // [SB][A1]
+  float* hh = lg + SB * A1;         // [SB][FC]
+  for (int i = threadIdx.x; i < SB * J2; i += blockDim.x) { int s = i / J2; phs[i] = s < nb ? ph[(size_t)b0 * J2 + i] : 0.0f; }
+  for (int i = threadIdx.x; i < SB * HW; i += blockDim.x) { int s = i / HW; vhs[i] = s < nb ? vh[(size_t)b0 * HW + i] : 0.0f; }
+  __syncthreads();
+  for (int a = threadIdx.x; a < A1; a += blockDim.x) {
+    float acc[SB];
+#pragma unroll
+    for (int s = 0; s < SB; s++) acc[s] = 0.0f;
+    for (int j = 0; j < J2; j++) {
+      const float w = __ldg(Wp + (size_t)j * A1 + a);
+#pragma unroll
+      for (int s = 0; s < SB; s++) acc[s] = fmaf(phs[s * J2 + j], w, acc[s]);
+    }
+    const float bias = bp[a];
+#pragma unroll
+    for (int s = 0; s < SB; s++) lg[s * A1 + a] = expf(acc[s] + bias);
+  }
+  for (int f = threadIdx.x; f < FC; f += blockDim.x) {
+    float acc[SB];
+#pragma unroll
+    for (int s = 0; s < SB; s++) acc[s] = 0.0f;
+    for (int j = 0; j < HW; j++) {
+      const float w = __ldg(Wv + (size_t)j * FC + f);
+#pragma unroll
+      for (int s = 0; s < SB; s++) acc[s] = fmaf(vhs[s * HW + j], w, acc[s]);
+    }
+    const float bias = bv[f];
+#pragma unroll
+    for (int s = 0; s < SB; s++) { float v = acc[s] + bias; hh[s * FC + f] = v > 0.0f ? v : 0.0f; }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int s = warp; s < nb; s += nw) {
+    float sum = 0.0f, dot = 0.0f;
+    for (int a = lane; a < A1; a += 32) sum += lg[s * A1 + a];
+    for (int f = lane; f < FC; f += 32) dot = fmaf(hh[s * FC + f], Wo[f], dot);
+#pragma unroll
+    for (int off = 16; off; off >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, off); dot += __shfl_xor_sync(0xffffffffu, dot, off); }
+    for (int a = lane; a < A1; a += 32) policy[(size_t)(b0 + s) * ldp + a] = lg[s * A1 + a] / sum;
+    if (lane == 0) value[b0 + s] = tanhf(dot + bo[0]);
+  }
+}
+
+void heads_tiled(const NetLayout& L, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
+                 float* policy, int ldp, float* value, cudaStream_t st, unsigned long long* launches) {
+  const NetDims& d = L.d;
+  constexpr int SB = 8;
+  const size_t sm = (size_t)SB * (3 * d.HW() + d.A1 + d.FC) * 4;
+  static size_t configured = 0;
+  if (sm > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    configured = sm;
+  }
+  k_heads_tiled<SB><<<(n_max + SB - 1) / SB, 256, sm, st>>>(ph, vh, s.d + s.pW, s.d + s.pB, s.d + s.vW, s.d + s.vB, s.d + s.voW,
+                                                          s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC);
+  if (launches) (*launches)++;
+}
+
 void fp32_scratch_alloc(Fp32Scratch& s, const NetDims& d, int n_max) {
   size_t act = (size_t)n_max * d.K * d.HW();
   CUDA_CHECK(cudaMalloc(&s.a, act * 4));

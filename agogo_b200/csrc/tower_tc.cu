@@ -303,19 +303,51 @@ __global__ void k_pack_planes(const float* __restrict__ planes, const int* __res
   hi[o] = h;
   lo[o] = __float2half_rn(v - __half2float(h));
 }
-// tower output (NHWC hi/lo, scaled) -> dense fp32 NCHW for the heads
-__global__ void k_unpack_tower(const __half* __restrict__ hi, const __half* __restrict__ lo, const int* __restrict__ n_dev,
-                               int n_max, int K, int H, int W, int guard, float inv_scale, float* out) {
+// The two 1x1 head convs (K->2 policy, K->1 value; dual.go:70,85) + BN-test affine + ReLU straight
+// from the tower's NHWC hi/lo output: one warp per board point, lanes split the channels
+// (coalesced 16-byte loads), three dot products reduced with shuffles.
+//   ph [n][2][HW], vh [n][HW]  (the layout the linear layers consume)
+__global__ void k_head_convs_nhwc(const __half* __restrict__ hi, const __half* __restrict__ lo, const int* __restrict__ n_dev,
+                                  int n_max, int K, int H, int W, int guard, float inv_scale, const float* __restrict__ wp,
+                                  const float* __restrict__ gp, const float* __restrict__ bp, const float* __restrict__ wv,
+                                  const float* __restrict__ gv, const float* __restrict__ bv, float* ph, float* vh) {
   const int n = min(*n_dev, n_max);
   const int HW = H * W, Wp = W + 1, S = (H + 1) * Wp;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)n * HW * K) return;
-  const int c = (int)(idx % K);
-  const int hw = (int)((idx / K) % HW);
-  const int b = (int)(idx / ((size_t)K * HW));
+  const int lane = threadIdx.x & 31;
+  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (size_t)n * HW) return;
+  const int b = (int)(wid / HW), hw = (int)(wid - (size_t)b * HW);
   const int y = hw / W, x = hw - y * W;
-  const size_t i = ((size_t)guard + (size_t)b * S + y * Wp + x) * K + c;
-  out[((size_t)b * K + c) * HW + hw] = (__half2float(hi[i]) + __half2float(lo[i])) * inv_scale;
+  const size_t row = (size_t)guard + (size_t)b * S + y * Wp + x;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+  for (int c0 = lane * 8; c0 < K; c0 += 256) {
+    const uint4 h4 = *(const uint4*)(hi + row * K + c0);
+    const uint4 l4 = *(const uint4*)(lo + row * K + c0);
+    const __half* hh = (const __half*)&h4;
+    const __half* ll = (const __half*)&l4;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float v = (__half2float(hh[i]) + __half2float(ll[i])) * inv_scale;
+      a0 = fmaf(v, __ldg(wp + c0 + i), a0);
+      a1 = fmaf(v, __ldg(wp + K + c0 + i), a1);
+      a2 = fmaf(v, __ldg(wv + c0 + i), a2);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+  }
+  if (lane == 0) {
+    const float isd = 1.0f / sqrtf(1e-5f);
+    float p0 = gp[hw] * (a0 * isd) + bp[hw];
+    float p1 = gp[HW + hw] * (a1 * isd) + bp[HW + hw];
+    float v0 = gv[hw] * (a2 * isd) + bv[hw];
+    ph[((size_t)b * 2 + 0) * HW + hw] = p0 > 0.0f ? p0 : 0.0f;
+    ph[((size_t)b * 2 + 1) * HW + hw] = p1 > 0.0f ? p1 : 0.0f;
+    vh[(size_t)b * HW + hw] = v0 > 0.0f ? v0 : 0.0f;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -360,7 +392,6 @@ struct Impl {
   __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
   std::vector<Layer> layers;
-  float* tower_f32 = nullptr;  // [n_max][K][HW]
   // profiling
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -418,7 +449,6 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
   auto alloc_h = [&](size_t n) { __half* p; CUDA_CHECK(cudaMalloc(&p, n * 2)); CUDA_CHECK(cudaMemset(p, 0, n * 2)); return p; };
   I->xin_hi = alloc_h((size_t)I->rows_alloc * 64); I->xin_lo = alloc_h((size_t)I->rows_alloc * 64);
   for (int i = 0; i < 2; i++) { I->x_hi[i] = alloc_h((size_t)I->rows_alloc * d.K); I->x_lo[i] = alloc_h((size_t)I->rows_alloc * d.K); }
-  CUDA_CHECK(cudaMalloc(&I->tower_f32, (size_t)n_max * d.K * d.HW() * 4));
   I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM);
   for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM); }
   // layers: init (single), then SharedLayers fused pairs
@@ -443,7 +473,6 @@ void tc_tower_free(TcTower& t) {
   if (!I) return;
   cudaFree(I->xin_hi); cudaFree(I->xin_lo);
   for (int i = 0; i < 2; i++) { cudaFree(I->x_hi[i]); cudaFree(I->x_lo[i]); }
-  cudaFree(I->tower_f32);
   for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); }
   for (cudaEvent_t e : I->ev_pool) cudaEventDestroy(e);
   delete I;
@@ -529,12 +558,15 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
     cur ^= 1;
   }
   {
-    size_t total = (size_t)n_max * d.HW() * d.K;
-    k_unpack_tower<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(I->x_hi[cur], I->x_lo[cur], n_dev, n_max, d.K, d.H, d.W,
-                                                                   I->guard, 1.0f / scale, I->tower_f32);
+    const SnapUnit& pu = s.units[1 + 2 * d.SharedLayers];
+    const SnapUnit& vu = s.units[2 + 2 * d.SharedLayers];
+    size_t warps = (size_t)n_max * d.HW();
+    k_head_convs_nhwc<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+        I->x_hi[cur], I->x_lo[cur], n_dev, n_max, d.K, d.H, d.W, I->guard, 1.0f / scale, s.d + pu.filter, s.d + pu.gamma,
+        s.d + pu.beta, s.d + vu.filter, s.d + vu.gamma, s.d + vu.beta, sc.ph, sc.vh);
     if (launches) (*launches)++;
   }
-  heads_fp32(NL, s, sc, I->tower_f32, n_dev, n_max, policy, ldp, value, st, launches);
+  heads_tiled(NL, s, sc.ph, sc.vh, n_dev, n_max, policy, ldp, value, st, launches);
   if (I->profile) I->fwd_spans.push_back({f0, I->ev_get(st)});
 }
 

@@ -165,6 +165,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # torchrun pins OMP_NUM_THREADS=1; the reference arm gets every host thread (set before libgomp loads)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
         r = cpu_reference_run(w, args.steps, warmup)
         line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": r["value"], "unit": "sims/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
@@ -266,6 +268,9 @@ def main():
                "d2h_bytes_per_step": d2h, "step": "az_arena_step: one full ply (1 root eval + %d sims per game) + example read-back"
                % w["sims"], "seconds": te[0].item(), "moves_per_sec": world * n_games / te[0].item()}
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
     peaks, peak_src = load_peaks()
@@ -294,7 +299,8 @@ def main():
                 "share_of_step": conv_s / dt, "note": "3 tensor-core passes per algorithmic MAC (fp32-faithful split): "
                 "frac of the bf16 peak tops out at 1/3 x 361/400 (zero-border padding) = 0.30"}
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
+        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
         r = cpu_reference_run(w, args.cpu_steps, 1)
         cpu_baseline = {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
                         "sample": "oracle, 1 game x %d pipeline iterations (1 leaf eval each, useful-work batch 1), %.1f s"

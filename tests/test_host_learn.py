@@ -64,3 +64,30 @@ def test_round_kats():
     from tests.golden import rules_golden as G
     for a, want in G.ROUND:
         assert host.dual_round(a) == want
+
+
+def test_cpp_host_learn_equals_python_host(oracle, tmp_path):
+    """host/agogo.hpp (C++ host layer) linked against the oracle library reproduces the Python host's
+    AZ.Learn exactly: same per-epoch lines and the same final weights."""
+    import os
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "tictactoe_oracle")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", os.path.join(root, "host", "tictactoe.cpp"), "-o", exe,
+                           "-L" + os.path.join(root, "oracle"), "-lazoracle", "-Wl,-rpath," + os.path.join(root, "oracle"),
+                           "-fopenmp"])
+    out = subprocess.check_output([exe, "2", "10", "3", "8", "16", "20", "77"], cwd=str(tmp_path)).decode().splitlines()
+    conf = _c1_conf(batch=20, sims=16)
+    az = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle, n_games=64, seed=77)
+    az.Learn(2, 10, 3, 8)
+    for ep, l in enumerate(az.log):
+        want = "epoch %d A %g %g %g B %g %g %g examples %d batches %d promoted %d cost %.9g %.9g" % (
+            ep, *l["a"], *l["b"], l["n_examples"], l["batches"], int(l["promoted"]), np.float32(l["first_cost"]),
+            np.float32(l["last_cost"]))
+        assert out[ep] == want, (out[ep], want)
+    p = az.engine.net_get(0)
+    h = 2166136261
+    for byte in p.tobytes():
+        h = ((h ^ byte) * 16777619) & 0xFFFFFFFF
+    assert out[-1].split()[1] == "%08x" % h
