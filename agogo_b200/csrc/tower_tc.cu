@@ -21,6 +21,7 @@
 #include <cuda_fp16.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -123,6 +124,7 @@ struct ConvArgs {
   __half* out_lo;
   float act_scale;    // 2^ea
   int* err;
+  int passes;         // 3: hi*hi + hi*lo + lo*hi (fp32-faithful, default); 2: drops lo*hi; 1: hi*hi only
 };
 
 template <int BN, bool PAIR>
@@ -213,8 +215,8 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int ks = 0; ks < BK / 16; ks++) {
             const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 fp16 = 32 B along K inside the swizzle atom
             umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | ks) ? 1u : 0u);
-            umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
-            umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
+            if (a.passes >= 2) umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            if (a.passes >= 3) umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
           }
           umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above have read it
         }
@@ -387,7 +389,7 @@ struct Layer {
 };
 struct Impl {
   NetDims d;
-  int n_max, ea, guard, S, rows_alloc, num_sms;
+  int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3;
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
   __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
@@ -415,7 +417,7 @@ void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUt
   ConvArgs a;
   a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
   a.cin = L.cin; a.n_total = L.n_total; a.cout = I.d.K; a.aff = L.aff; a.out_hi = ohi; a.out_lo = olo;
-  a.act_scale = ldexpf(1.0f, I.ea); a.err = err;
+  a.act_scale = ldexpf(1.0f, I.ea); a.err = err; a.passes = I.passes;
   const int max_tiles = ((I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
   const int grid = std::min(I.num_sms, max_tiles);
   k_conv3x3_tc<BN, PAIR><<<grid, NTHREADS, smem_bytes(BN), st>>>(ah, al, L.mB_hi, L.mB_lo, a);
@@ -440,6 +442,7 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
   Impl* I = new Impl;
   t.impl = I;
   I->d = d; I->n_max = n_max; I->ea = act_scale_log2;
+  if (const char* ps = getenv("AZ_TC_PASSES")) { int v = atoi(ps); if (v >= 1 && v <= 3) I->passes = v; }  // experiments only
   I->guard = ((d.W + 2 + 7) / 8) * 8;
   I->S = (d.H + 1) * (d.W + 1);
   I->rows_alloc = I->guard + n_max * I->S + I->guard + BM;

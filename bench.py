@@ -182,9 +182,9 @@ def main():
         print(json.dumps(line))
         return 0
 
-    import torch  # plumbing only: process group for barrier / max-over-ranks
-    dist = None
-    if world > 1:
+    dist = torch = None
+    if world > 1:  # plumbing only: process group for barrier / max-over-ranks
+        import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -194,9 +194,10 @@ def main():
     n_games = w["n_games"]
 
     def barrier():
+        e.counters()  # synchronises the engine's stream (all of this process's GPU work)
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize(local_rank)
+            torch.cuda.synchronize(local_rank)
 
     # step generator: waves continue across move boundaries
     state = {"in_search": False, "left": 0}
@@ -224,7 +225,6 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         one_step()
-    torch.cuda.synchronize(local_rank)
     prof = e.profile(False)  # synchronises the engine stream, collects event timings
     barrier()
     dt = time.perf_counter() - t0
@@ -232,16 +232,15 @@ def main():
     cnt = e.counters()
     sims = cnt["sims"]
     evals = cnt["evals"]
-    tt = torch.tensor([dt, float(sims), float(evals), float(cnt["kernel_launches"])], dtype=torch.float64,
-                      device="cuda:%d" % local_rank)
+    tot = [dt, float(sims), float(evals), float(cnt["kernel_launches"])]
+    dt_max = dt
     if dist is not None:
+        tt = torch.tensor(tot, dtype=torch.float64, device="cuda:%d" % local_rank)
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        dt_max = mx[0].item()
-    else:
-        dt_max = dt
-    tot_sims, tot_evals, tot_launch = tt[1].item(), tt[2].item(), tt[3].item()
+        dt_max, tot = mx[0].item(), tt.tolist()
+    tot_sims, tot_evals, tot_launch = tot[1], tot[2], tot[3]
     value = tot_sims / dt_max
 
     # ---- e2e: one full Arena.Play ply through az_arena_step, examples read back to host
@@ -257,16 +256,18 @@ def main():
         barrier()
         t1 = time.perf_counter()
         e.arena_step()
-        torch.cuda.synchronize(local_rank)
         barrier()
         dt_e = time.perf_counter() - t1
-        te = torch.tensor([dt_e], dtype=torch.float64, device="cuda:%d" % local_rank)
         if dist is not None:
+            te = torch.tensor([dt_e], dtype=torch.float64, device="cuda:%d" % local_rank)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dt_e = te[0].item()
         d2h = n_games * (18 * w["size"] ** 2 + w["size"] ** 2 + 1 + 2) * 4 + 8
-        e2e = {"value": world * n_games * w["sims"] / te[0].item(), "unit": "sims/s", "h2d_bytes_per_step": n_games * 4,
+        e2e = {"value": world * n_games * w["sims"] / dt_e, "unit": "sims/s", "h2d_bytes_per_step": n_games * 4,
                "d2h_bytes_per_step": d2h, "step": "az_arena_step: one full ply (1 root eval + %d sims per game) + example read-back"
-               % w["sims"], "seconds": te[0].item(), "moves_per_sec": world * n_games / te[0].item()}
+               % w["sims"], "seconds": dt_e, "moves_per_sec": world * n_games / dt_e,
+               "note": "the path's inputs are the two nets' weights, uploaded once per epoch by az_net_set_params / "
+                       "az_agent_set_inferer, not per ply; per ply the host sends the coin flips and receives the examples"}
 
     if dist is not None:
         dist.barrier()

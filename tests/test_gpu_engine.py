@@ -275,3 +275,22 @@ def test_c1_learn_on_device(oracle, engine_lib):
     for l in ag2.log:
         assert np.isfinite(l["first_cost"]) and np.isfinite(l["last_cost"]) and l["n_examples"] > 0
         assert sum(l["a"]) == 10 and sum(l["b"]) == 10
+
+
+def test_tc_tower_full_depth_c3(oracle, engine_lib):
+    """The headline net (20 blocks x 256, 19x19, FC 512) end to end against the oracle: the fp16 hi/lo
+    3-pass tower must hold 1e-4 through all 41 conv layers."""
+    size, A1 = 19, 362
+    def desc(flags):
+        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4, flags=flags,
+                           nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=A1))
+    eo, etc = oracle.create(desc(0)), engine_lib.create(desc(0))
+    H.tame_gammas([eo, etc], 0, 99)
+    for e in (eo, etc):
+        e.set_inferer(0, K.INF_DUAL)
+    planes = _wq_planes(np.random.default_rng(8), 3, size)
+    po, vo = eo.infer(0, planes)
+    ptc, vtc = etc.infer(0, planes)
+    print("C3 depth: dp=%.3g dv=%.3g pmax=%.3g |v|max=%.3g" % (np.abs(ptc - po).max(), np.abs(vtc - vo).max(), po.max(), np.abs(vo).max()))
+    assert np.isfinite(po).all() and np.abs(vo).max() < 0.9999
+    assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
