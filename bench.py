@@ -117,7 +117,7 @@ def cpu_reference_run(w, steps, warmup, threads=None):
     """One step = one pipeline() iteration (1 leaf evaluation at useful-work batch 1) of ONE game on the
     oracle, OpenMP over the host cores inside the conv loops."""
     lib = oracle_lib()
-    ncores = os.cpu_count()
+    ncores = len(os.sched_getaffinity(0))
     # small train batch: the oracle only reads batch row 0 at inference; keeps its memory modest
     e = lib.create(make_desc(w, 1, 0, 1234, batch=2))
     setup_nets(e, 1234)
@@ -165,8 +165,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # torchrun pins OMP_NUM_THREADS=1; the reference arm gets every host thread (set before libgomp loads)
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+        # torchrun pins OMP_NUM_THREADS=1; the reference arm gets every host thread this process may run on
+        # (set before libgomp loads); passive waiting keeps it sane on shared hosts
+        if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+            os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         r = cpu_reference_run(w, args.steps, warmup)
         line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": r["value"], "unit": "sims/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
@@ -301,7 +304,7 @@ def main():
                 "frac of the bf16 peak tops out at 1/3 x 361/400 (zero-border padding) = 0.30"}
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
-        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")
         r = cpu_reference_run(w, args.cpu_steps, 1)
         cpu_baseline = {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
                         "sample": "oracle, 1 game x %d pipeline iterations (1 leaf eval each, useful-work batch 1), %.1f s"

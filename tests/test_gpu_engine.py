@@ -294,3 +294,22 @@ def test_tc_tower_full_depth_c3(oracle, engine_lib):
     print("C3 depth: dp=%.3g dv=%.3g pmax=%.3g |v|max=%.3g" % (np.abs(ptc - po).max(), np.abs(vtc - vo).max(), po.max(), np.abs(vo).max()))
     assert np.isfinite(po).all() and np.abs(vo).max() < 0.9999
     assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
+
+
+def test_c2_shapes_selfplay(oracle, engine_lib):
+    """BASELINE config C2 shapes (9x9 wq, 6-block x 64 net, FC 128, WQEncoder) at reduced game/sim counts:
+    tensor-core tower in the loop, move sequences and evaluation counts equal to the oracle's."""
+    def desc():
+        return K.make_desc(K.GAME_WQ, 9, 9, 0, komi=7.5, sims=32, n_games=8, seed=77, max_moves=5,
+                           nn=dict(k=64, shared_layers=6, fc=128, batch_size=2, features=18, action_space=82))
+    eo, eg = oracle.create(desc()), engine_lib.create(desc())
+    H.tame_gammas([eo, eg], 0, 41); H.tame_gammas([eo, eg], 1, 42)
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUAL); e.set_inferer(1, K.INF_DUAL)
+    a, b = H.play_and_collect(eo, 8, dump_trees=False), H.play_and_collect(eg, 8, dump_trees=False)
+    for ra, rb in zip(a["records"], b["records"]):
+        assert list(ra["moves"]) == list(rb["moves"])
+    for k in ("sims", "evals", "null_results", "created"):
+        assert a["counters"][k] == b["counters"][k], k
+    xa, xb = a["examples"], b["examples"]
+    assert (xa[0].view(np.uint32) == xb[0].view(np.uint32)).all()  # WQEncoder planes incl. -0.0
