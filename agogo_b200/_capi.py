@@ -46,6 +46,11 @@ class EngineDesc(C.Structure):
                 ("act_scale_log2", C.c_int32), ("max_nodes_per_tree", C.c_int32)]
 
 
+class State(C.Structure):
+    _fields_ = [("board", C.POINTER(C.c_int32)), ("to_move", C.c_int32), ("move_number", C.c_int32), ("passes", C.c_int32),
+                ("n_hist", C.c_int32), ("hist", C.POINTER(C.c_int32))]
+
+
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("searches", "sims", "null_results", "evals", "select_children",
                                           "select_levels", "created", "backup_nodes", "kernel_launches")] + \
@@ -59,7 +64,7 @@ SYMBOLS = [
     "az_arena_step", "az_arena_finish", "az_search_begin", "az_search_run", "az_search_end", "az_game_record",
     "az_game_state", "az_examples_count", "az_examples_read", "az_examples_clear", "az_tree_dump", "az_rules_apply",
     "az_rules_status", "az_train", "az_comm_unique_id", "az_comm_init", "az_counters_get", "az_counters_reset",
-    "az_build_info", "az_profile", "az_train_grads", "az_train_apply",
+    "az_build_info", "az_profile", "az_train_grads", "az_train_apply", "az_search",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -217,6 +222,16 @@ class Engine:
 
     def search_end(self):
         self._ck(self.lib.dll.az_search_end(self.h))
+
+    def search(self, agent, board, to_move, player, move_number=0, passes=0, hist=None):
+        """Agent.Search on an external position: returns (best move, visit counts by move, Pass last)."""
+        board = np.ascontiguousarray(board, np.int32)
+        hist = np.zeros((0, self.cells), np.int32) if hist is None else np.ascontiguousarray(hist, np.int32).reshape(-1, self.cells)
+        st = State(_p(board, C.c_int32), to_move, move_number, passes, hist.shape[0], _p(hist, C.c_int32))
+        best = C.c_int32()
+        visits = np.zeros(self.action_space + 1, np.float32)
+        self._ck(self.lib.dll.az_search(self.h, agent, C.byref(st), player, C.byref(best), _p(visits, C.c_float)))
+        return best.value, visits
 
     def game_record(self, game, cap=4096):
         moves = np.empty(cap, np.int32)

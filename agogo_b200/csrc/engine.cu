@@ -584,6 +584,87 @@ int az_arena_play(az_engine* e, int32_t n_games, int32_t record) {
   return AZ_OK;
 }
 
+int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, int32_t* best, float* child_visits) {
+  if (agent < 0 || agent > 1 || !st || !st->board || st->n_hist < 0 || st->n_hist > 8) return AZ_ERR_INVALID;
+  if (e->in_play) { e->err = "az_search during a running arena"; return AZ_ERR_STATE; }
+  if (e->E.inf[agent].kind < 0) { e->err = "agent has no inferer"; return AZ_ERR_STATE; }
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  const GameP& P = e->P;
+  const EngineDev& E = e->E;
+  // fresh slot 0 (board, scalars, trees), then overwrite it with the caller's position
+  int coin = 0;
+  CUDA_CHECK(cudaMemcpyAsync(e->coins_dev, &coin, 4, cudaMemcpyHostToDevice, e->stream));
+  launch_arena_begin(P, E, 1, e->coins_dev, e->stream); e->launches++;
+  std::vector<uint8_t> b(E.cellsP, 0);
+  for (int i = 0; i < P.cells; i++) b[i] = (uint8_t)st->board[i];
+  std::vector<uint8_t> ring(P.hist_len ? (size_t)8 * E.cellsP : 1, 0);
+  if (P.hist_len)
+    for (int i = 0; i < st->n_hist; i++) {
+      int h = st->move_number - st->n_hist + i;  // Historical(h) = board before move h
+      if (h < 0) continue;
+      for (int c = 0; c < P.cells; c++) ring[(size_t)(h & 7) * E.cellsP + c] = (uint8_t)st->hist[(size_t)i * P.cells + c];
+    }
+  int32_t gi[GI_COUNT] = {0};
+  const int opp_player = player == AZ_BLACK ? AZ_WHITE : AZ_BLACK;
+  gi[GI_TO_MOVE] = st->to_move; gi[GI_MOVE_NUMBER] = st->move_number;
+  gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : (P.kind == KIND_WQ ? st->passes : 0);
+  gi[GI_C4_PASS] = P.kind == KIND_C4 ? st->passes : 0;
+  gi[GI_ACTIVE] = 1; gi[GI_CUR_AGENT] = P.shared_tree ? 0 : agent;
+  gi[GI_A_PLAYER] = (P.shared_tree || agent == 0) ? player : opp_player;
+  if (P.kind == KIND_WQ) {  // clean Zobrist hash of the position (wq/zobrist.go:44-56)
+    std::vector<int32_t> zt((size_t)P.cells * 2);
+    CUDA_CHECK(cudaMemcpy(zt.data(), E.ztable, zt.size() * 4, cudaMemcpyDeviceToHost));
+    int32_t h = 0;
+    for (int i = 0; i < P.cells; i++) if (st->board[i]) h ^= zt[i * 2 + (st->board[i] == AZ_BLACK ? 0 : 1)];
+    gi[GI_ZHASH] = h;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  CUDA_CHECK(cudaMemcpy(E.board, b.data(), b.size(), cudaMemcpyHostToDevice));
+  if (P.hist_len) CUDA_CHECK(cudaMemcpy(E.hist, ring.data(), ring.size(), cudaMemcpyHostToDevice));
+  CUDA_CHECK(cudaMemcpy(E.gi, gi, sizeof gi, cudaMemcpyHostToDevice));
+  e->in_play = true; e->record = false; e->n_play = 1;
+  e->ex_by_game.assign(1, {});
+  int rc = az_search_begin(e);
+  if (!rc) rc = az_search_run(e, P.sims);
+  // visit counts of the root's children, before the epilogue permutes/applies anything that matters to us
+  if (!rc && child_visits) {
+    const int t = P.shared_tree ? 0 : agent;
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    int32_t ti[TI_COUNT];
+    CUDA_CHECK(cudaMemcpy(ti, E.ti + (size_t)t * TI_COUNT, sizeof ti, cudaMemcpyDeviceToHost));
+    for (int i = 0; i <= P.A; i++) child_visits[i] = 0;
+    if (ti[TI_ROOT] >= 0) {
+      const size_t tb = (size_t)t * P.max_nodes;
+      uint32_t rmeta; int32_t rfirst;
+      CUDA_CHECK(cudaMemcpy(&rmeta, E.meta + tb + ti[TI_ROOT], 4, cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(&rfirst, E.first + tb + ti[TI_ROOT], 4, cudaMemcpyDeviceToHost));
+      const int nc = META_NCHILD(rmeta);
+      std::vector<uint32_t> cm(nc), cn(nc);
+      if (nc) {
+        CUDA_CHECK(cudaMemcpy(cm.data(), E.meta + tb + rfirst, (size_t)nc * 4, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(cn.data(), E.N + tb + rfirst, (size_t)nc * 4, cudaMemcpyDeviceToHost));
+      }
+      for (int j = 0; j < nc; j++) {
+        int mv = META_MOVE(cm[j]);
+        if (mv == AZ_PASS) child_visits[P.A] = (float)cn[j];
+        else if (mv >= 0 && mv < P.A) child_visits[mv] = (float)cn[j];
+      }
+    }
+  }
+  if (!rc) rc = az_search_end(e);
+  if (!rc && best) {
+    int16_t mv;
+    CUDA_CHECK(cudaMemcpy(&mv, E.moves, 2, cudaMemcpyDeviceToHost));
+    *best = mv;
+  }
+  e->in_play = false;
+  e->ex_by_game.clear();
+  if (rc) return rc;
+  GUARD_END(e)
+  return AZ_OK;
+}
+
 int az_game_record(const az_engine* ce, int32_t game, int32_t* moves, int32_t cap, int32_t* n_moves, int32_t* winner,
                    int32_t* a_player, int32_t* n_examples) {
   az_engine* e = const_cast<az_engine*>(ce);

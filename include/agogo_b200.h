@@ -148,6 +148,20 @@ int az_search_begin(az_engine* e);                   /* updateRoot + prepareRoot
 int az_search_run(az_engine* e, int32_t n_iterations); /* n x pipeline (search.go:209-257) per game */
 int az_search_end(az_engine* e);                     /* bestMove, example, Apply, switchPlayer */
 
+/* Agent.Search on an EXTERNAL position (agent.go:77-80: MCTS.SetGame(g); MCTS.Search(a.Player)) — the
+ * README's inference use.  The Go shim marshals game.State getters into az_state: Board(), ToMove(),
+ * MoveNumber(), Passes() and, for the WQEncoder, Historical(MoveNumber-n_hist .. MoveNumber-1).
+ * A fresh tree is searched for `mcts.sims` iterations (no reuse across calls).  Returns the chosen move
+ * and, optionally, the root children's visit counts indexed by move (Pass at index ActionSpace).
+ * Not callable while an arena is running; uses game slot 0. */
+typedef struct az_state {
+  const int32_t* board; /* [m*n] colours */
+  int32_t to_move, move_number, passes;
+  int32_t n_hist;       /* 0..8 */
+  const int32_t* hist;  /* [n_hist][m*n], oldest first */
+} az_state;
+int az_search(az_engine* e, int32_t agent, const az_state* s, int32_t player, int32_t* best, float* child_visits);
+
 /* per-game results of the last begin..finish: moves played, winner (AZ_NONE/BLACK/WHITE),
  * colour of agent A, number of examples kept */
 int az_game_record(const az_engine* e, int32_t game, int32_t* moves, int32_t cap, int32_t* n_moves,

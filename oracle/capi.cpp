@@ -246,6 +246,58 @@ int az_arena_play(az_engine* e, int32_t n_games, int32_t record) {
   return AZ_OK;
 }
 
+int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, int32_t* best, float* child_visits) {
+  if (agent < 0 || agent > 1 || !st || !st->board) return AZ_ERR_INVALID;
+  if (e->in_play) { e->err = "az_search during a running arena"; return AZ_ERR_STATE; }
+  if (!e->inferers[agent]) { e->err = "agent has no inferer"; return AZ_ERR_STATE; }
+  GUARD_BEGIN
+  const az_game_desc& g = e->d.game;
+  const int cells = g.m * g.n;
+  std::unique_ptr<State> state;
+  if (g.kind == AZ_GAME_MNK) {
+    MNK* t = new MNK(g.m, g.n, g.k);
+    t->board.assign(st->board, st->board + cells);
+    t->history.assign(st->move_number, PlayerMove{None, 0}); t->histPtr = st->move_number; t->nextToMove = st->to_move;
+    state.reset(t);
+  } else if (g.kind == AZ_GAME_C4) {
+    C4* t = new C4(g.m, g.n, g.k);
+    t->data.assign(st->board, st->board + cells); t->nextToMove = st->to_move; t->passCount = st->passes;
+    state.reset(t);
+  } else {
+    WQ* t = new WQ(g.m, 0, g.komi, g.zobrist_seed);
+    t->board.data.assign(st->board, st->board + cells);
+    for (int i = 0; i < cells; i++) if (st->board[i]) t->board.zupdate(PlayerMove{st->board[i], (Single)i});  // clean hash
+    t->nextToMove = st->to_move; t->passes = st->passes; t->moveCount = st->move_number;
+    t->history.assign(st->move_number, PlayerMove{None, -1}); t->histPtr = st->move_number;
+    for (int i = 0; i < st->n_hist; i++) {
+      auto hn = std::make_shared<WQ::HistNode>();
+      hn->board.assign(st->hist + (size_t)i * cells, st->hist + (size_t)(i + 1) * cells);
+      hn->prev = t->hist; hn->idx = st->move_number - st->n_hist + i;
+      t->hist = hn;
+    }
+    state.reset(t);
+  }
+  Agent ag;
+  ag.NN = e->nets[agent]; ag.enc = e->d.encoder; ag.player = player; ag.inferer = e->inferers[agent];
+  ag.mcts.reset(new MCTS(state.get(), e->mc, &ag, derive_seed(e->d.seed, 1)));
+  Single b = ag.Search(state.get());
+  add_counters(e->base, ag.mcts->cnt);
+  if (best) *best = b;
+  if (child_visits) {
+    int A = state->ActionSpace();
+    for (int i = 0; i <= A; i++) child_visits[i] = 0;
+    const MCTS& t = *ag.mcts;
+    if (t.root != nilNode)
+      for (int kid : t.children[t.root]) {
+        int mv = t.nodes[kid].move;
+        if (mv == PassMove) child_visits[A] = (float)t.nodes[kid].visits;
+        else if (mv >= 0 && mv < A) child_visits[mv] = (float)t.nodes[kid].visits;
+      }
+  }
+  GUARD_END(e)
+  return AZ_OK;
+}
+
 int az_game_record(const az_engine* e, int32_t game, int32_t* moves, int32_t cap, int32_t* n_moves, int32_t* winner,
                    int32_t* a_player, int32_t* n_examples) {
   const GameRecord* r = nullptr;

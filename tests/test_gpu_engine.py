@@ -313,3 +313,38 @@ def test_c2_shapes_selfplay(oracle, engine_lib):
         assert a["counters"][k] == b["counters"][k], k
     xa, xb = a["examples"], b["examples"]
     assert (xa[0].view(np.uint32) == xb[0].view(np.uint32)).all()  # WQEncoder planes incl. -0.0
+
+
+def test_search_external_positions(oracle, engine_lib):
+    """az_search (Agent.Search on a caller-supplied game.State): best move and root visit counts equal
+    the oracle's for mnk, c4 and wq positions (history planes included for wq)."""
+    rng = np.random.default_rng(11)
+    cases = [
+        (lambda: K.make_desc(K.GAME_MNK, 3, 3, 3, sims=60, nn=H.tiny_nn(3, 3, 10), n_games=2, seed=1),
+         dict(board=[1, 1, 0, 2, 2, 0, 0, 0, 0], to_move=K.BLACK, player=K.BLACK, move_number=4)),
+        (lambda: K.make_desc(K.GAME_C4, 6, 7, 4, sims=50, nn=H.tiny_nn(6, 7, 8), n_games=2, seed=1),
+         dict(board=[0] * 35 + [1, 2, 1, 2, 0, 0, 0], to_move=K.WHITE, player=K.WHITE, move_number=1)),
+    ]
+    for mk, st in cases:
+        eo, eg = oracle.create(mk()), engine_lib.create(mk())
+        for e in (eo, eg):
+            e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+        for agent in (0, 1):
+            bo, vo = eo.search(agent, st["board"], st["to_move"], st["player"], st["move_number"])
+            bg, vg = eg.search(agent, st["board"], st["to_move"], st["player"], st["move_number"])
+            assert bo == bg and (vo == vg).all(), (st, agent, bo, bg)
+    # wq with a dual net (fp32 tower) and real history: positions produced by a short oracle game
+    def wdesc():
+        return K.make_desc(K.GAME_WQ, 7, 7, 0, komi=7.5, sims=30, n_games=2, seed=3, max_moves=12, flags=K.FLAG_FP32_TOWER,
+                           nn=dict(k=4, shared_layers=1, fc=8, batch_size=4, features=18, action_space=50))
+    eo, eg = oracle.create(wdesc()), engine_lib.create(wdesc())
+    H.tame_gammas([eo, eg], 0, 5); H.tame_gammas([eo, eg], 1, 6)
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUAL); e.set_inferer(1, K.INF_DUAL)
+    hist, board = [], np.zeros(49, np.int32)
+    for mv, col in zip(rng.permutation(49)[:9], [1, 2] * 5):
+        hist.append(board.copy())
+        board = board.copy(); board[mv] = col
+    bo, vo = eo.search(0, board, K.WHITE, K.WHITE, move_number=9, hist=np.array(hist[-8:]))
+    bg, vg = eg.search(0, board, K.WHITE, K.WHITE, move_number=9, hist=np.array(hist[-8:]))
+    assert bo == bg and np.abs(vo - vg).max() <= 1, (bo, bg, vo, vg)
