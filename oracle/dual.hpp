@@ -140,7 +140,7 @@ struct Dual {
 // fp32 kernels (NCHW).  conv: cross-correlation, "same" padding (k-1)/2, stride 1, no bias.
 inline void conv_fwd(const float* x, const float* w, float* y, int B, int Ci, int Co, int H, int W, int k) {
   int pad = (k - 1) / 2, HW = H * W;
-  const bool par = (double)B * Co * Ci * HW * k * k > 2e6;  // threads only pay off on big layers
+  const bool par = (double)B * Co * Ci * HW * k * k > 5e7;  // threads only pay off on big layers (128-way fork/join costs ~ms)
 #pragma omp parallel for collapse(2) schedule(static) if (par)
   for (int b = 0; b < B; b++)
     for (int co = 0; co < Co; co++) {
@@ -168,7 +168,7 @@ inline void conv_fwd(const float* x, const float* w, float* y, int B, int Ci, in
 inline void conv_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int Ci, int Co,
                      int H, int W, int k) {
   int pad = (k - 1) / 2, HW = H * W;
-  const bool par = (double)B * Co * Ci * HW * k * k > 2e6;
+  const bool par = (double)B * Co * Ci * HW * k * k > 5e7;
   if (dx) {
 #pragma omp parallel for collapse(2) schedule(static) if (par)
     for (int b = 0; b < B; b++)
@@ -223,7 +223,7 @@ inline void unit_infer(const Dual& net, const ConvBN& u, const float* x, float* 
   const float* g = net.P(u.gamma);  // row 0 of [B,Co,H,W]
   const float* be = net.P(u.beta);
   size_t chw = (size_t)u.Co * HW;
-#pragma omp parallel for schedule(static) if ((double)n * chw > 1e6)
+#pragma omp parallel for schedule(static) if ((double)n * chw > 2e7)
   for (int b = 0; b < n; b++)
     for (size_t i = 0; i < chw; i++) {
       float t = z[b * chw + i] / s;
@@ -253,7 +253,7 @@ inline void dual_infer(const Dual& net, const float* planes, int n, float* polic
   const float* Wp = net.P(net.pW); const float* bp = net.P(net.pB);
   const float* Wv = net.P(net.vW); const float* bv = net.P(net.vB);
   const float* Wo = net.P(net.voW); const float* bo = net.P(net.voB);
-#pragma omp parallel for schedule(static) if ((double)n * HW * A > 1e6)
+#pragma omp parallel for schedule(static) if ((double)n * HW * A > 2e7)
   for (int b = 0; b < n; b++) {
     std::vector<float> logits(A);
     for (int a = 0; a < A; a++) {  // linear: xw + b (ermahagerdmonards.go:75-84), bias row 0
