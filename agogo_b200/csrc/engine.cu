@@ -2,6 +2,7 @@
 // No CPU fallback: creation fails with AZ_ERR_CUDA when there is no usable CUDA device.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -80,6 +81,13 @@ struct az_engine {
   float *h_ex_board = nullptr, *h_ex_policy = nullptr, *h_ex_value = nullptr;
   int32_t* h_ex_valid = nullptr;
   int32_t* h_small = nullptr;  // [n_active, err]
+  // one MCTS wave (select -> evaluate -> expand/backup) captured as a CUDA graph: every kernel argument is
+  // device-resident state, so the captured launch sequence is replayed for each of the `sims` waves
+  cudaGraphExec_t wave_graph = nullptr;
+  int wave_graph_n = -1;
+  uint64_t wave_graph_version = 0, cfg_version = 1;
+  unsigned long long wave_graph_launches = 0;
+  bool graphs_enabled = true, profiling = false;
   TrainWS train;
   void* comm = nullptr;  // ncclComm_t
   int rank = 0, world = 1;
@@ -157,6 +165,7 @@ void az_engine_destroy(az_engine* e) {
   for (void* p : e->allocs) cudaFree(p);
   for (int a = 0; a < 2; a++) { tc_tower_free(e->tc[a]); }
   train_ws_free(e->train);
+  if (e->wave_graph) cudaGraphExecDestroy(e->wave_graph);
   if (e->comm) { try { nccl_api().CommDestroy((ncclComm_t)e->comm); } catch (...) {} }
   fp32_scratch_free(e->fp32);
   if (e->h_ex_board) cudaFreeHost(e->h_ex_board);
@@ -252,6 +261,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     }
     for (int a = 0; a < 2; a++) { E.inf[a].kind = -1; E.inf[a].L = n.action_space; E.inf[a].dummy_value = 0; E.inf[a].table = nullptr; E.inf[a].table_values = nullptr; E.inf[a].table_rows = 0; }
     e->coins_dev = e->dalloc<int>(G);
+    if (const char* ng = getenv("AZ_NO_GRAPH")) e->graphs_enabled = !(ng[0] == '1');
     e->coin_state = derive_seed(desc->seed, 0);
     mcts_set_smem_limits(P, E.cellsP);
 
@@ -359,6 +369,7 @@ int az_agent_set_inferer(az_engine* e, int32_t agent, int32_t kind, int32_t dumm
     I.kind = INF_TABLE;
   } else return AZ_ERR_INVALID;
   e->inf_kind[agent] = kind;
+  e->cfg_version++;
   GUARD_END(e)
   return AZ_OK;
 }
@@ -375,6 +386,7 @@ int az_agent_set_table(az_engine* e, int32_t agent, int32_t n_rows, int32_t row_
   InfererDev& I = e->E.inf[agent];
   I.kind = INF_TABLE; I.L = row_len; I.table = t; I.table_values = v; I.table_rows = n_rows;
   e->inf_kind[agent] = AZ_INF_TABLE;
+  e->cfg_version++;
   GUARD_END(e)
   return AZ_OK;
 }
@@ -476,13 +488,31 @@ int az_search_begin(az_engine* e) {
   GUARD_END(e)
   return AZ_OK;
 }
+static void run_wave(az_engine* e) {
+  launch_select(e->P, e->E, e->n_play, e->stream); e->launches++;
+  eval_pending(e);
+}
 int az_search_run(az_engine* e, int32_t n) {
   if (!e->in_play) return AZ_ERR_STATE;
   GUARD_BEGIN
   CUDA_CHECK(cudaSetDevice(e->device));
-  for (int i = 0; i < n; i++) {
-    launch_select(e->P, e->E, e->n_play, e->stream); e->launches++;
-    eval_pending(e);
+  if (e->graphs_enabled && !e->profiling && n >= 1) {
+    if (!e->wave_graph || e->wave_graph_n != e->n_play || e->wave_graph_version != e->cfg_version) {
+      if (e->wave_graph) { cudaGraphExecDestroy(e->wave_graph); e->wave_graph = nullptr; }
+      const unsigned long long l0 = e->launches;
+      cudaGraph_t g = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+      try { run_wave(e); } catch (...) { cudaStreamEndCapture(e->stream, &g); if (g) cudaGraphDestroy(g); throw; }
+      CUDA_CHECK(cudaStreamEndCapture(e->stream, &g));
+      CUDA_CHECK(cudaGraphInstantiate(&e->wave_graph, g, 0));
+      cudaGraphDestroy(g);
+      e->wave_graph_launches = e->launches - l0;
+      e->launches = l0;
+      e->wave_graph_n = e->n_play; e->wave_graph_version = e->cfg_version;
+    }
+    for (int i = 0; i < n; i++) { CUDA_CHECK(cudaGraphLaunch(e->wave_graph, e->stream)); e->launches += e->wave_graph_launches; }
+  } else {
+    for (int i = 0; i < n; i++) run_wave(e);
   }
   GUARD_END(e)
   return AZ_OK;
@@ -948,6 +978,7 @@ int az_profile(az_engine* e, int32_t enable, double out[8]) {
     if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile_collect(e->tc[a], e->stream, &out[0], &out[1], &out[2], &out[3]);
   }
   if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile(e->tc[a], enable != 0);
+  e->profiling = enable != 0;  // event records inside the wave: replay the plain launch sequence instead of the graph
   GUARD_END(e)
   return AZ_OK;
 }

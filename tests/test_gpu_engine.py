@@ -348,3 +348,49 @@ def test_search_external_positions(oracle, engine_lib):
     bo, vo = eo.search(0, board, K.WHITE, K.WHITE, move_number=9, hist=np.array(hist[-8:]))
     bg, vg = eg.search(0, board, K.WHITE, K.WHITE, move_number=9, hist=np.array(hist[-8:]))
     assert bo == bg and np.abs(vo - vg).max() <= 1, (bo, bg, vo, vg)
+
+
+def test_engine_error_paths(engine_lib):
+    """Loud failures instead of silent fallbacks: invalid configs (the reference panics, agogo.go:42-47),
+    unsupported search options, a tree pool that is too small, calls out of sequence."""
+    with pytest.raises(K.AZError):
+        d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=5, nn=H.tiny_nn(3, 3, 10)); d.mcts.puct = 0.0
+        engine_lib.create(d)
+    with pytest.raises(K.AZError):
+        d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=5, nn=H.tiny_nn(3, 3, 10)); d.nn.action_space = 2
+        engine_lib.create(d)
+    with pytest.raises(K.AZError):
+        d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=5, nn=H.tiny_nn(3, 3, 10)); d.mcts.random_count = 3
+        engine_lib.create(d)
+    d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=30, nn=H.tiny_nn(3, 3, 10), n_games=2)
+    d.max_nodes_per_tree = 12
+    e = engine_lib.create(d)
+    with pytest.raises(K.AZError):
+        e.arena_begin(2, False)          # no inferer yet
+    e.set_inferer(0, K.INF_DUMMY, 0); e.set_inferer(1, K.INF_DUMMY, 0)
+    with pytest.raises(K.AZError):
+        e.search_run(1)                  # no arena running
+    e.arena_begin(2, False)
+    with pytest.raises(K.AZError) as ei:
+        for _ in range(9):
+            e.arena_step()
+    assert "pool" in str(ei.value)
+    # empty inference batch
+    e2 = engine_lib.create(K.make_desc(K.GAME_MNK, 3, 3, 3, sims=5, nn=H.tiny_nn(3, 3, 10), n_games=2))
+    e2.net_init(0, 1); e2.set_inferer(0, K.INF_DUAL)
+    p, v = e2.infer(0, np.zeros((0, 18), np.float32))
+    assert p.shape == (0, 10) and v.shape == (0,)
+
+
+def test_graph_replay_equals_plain_launches(engine_lib):
+    """The CUDA-graph replay of a wave and the plain launch sequence produce identical trees."""
+    import os
+    def run(no_graph):
+        os.environ["AZ_NO_GRAPH"] = "1" if no_graph else "0"
+        e = engine_lib.create(K.make_desc(K.GAME_C4, 6, 7, 4, sims=40, nn=H.tiny_nn(6, 7, 8), n_games=8, seed=5))
+        e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+        return H.play_and_collect(e, 8)
+    try:
+        H.assert_same_run(run(True), run(False), "graph")
+    finally:
+        os.environ.pop("AZ_NO_GRAPH", None)
