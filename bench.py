@@ -155,7 +155,7 @@ def main():
     fpe = flops_per_eval(w)
     config = {"workload": "%s: %dx%d Go (wq) self-play, %d games/GPU, %d sims/move, %d-block x %d dual net, two random-init "
                           "nets" % (args.workload, w["size"], w["size"], w["n_games"], w["sims"], w["blocks"], w["k"]),
-              "games_per_gpu": w["n_games"], "sims_per_move": w["sims"], "net": "%dx%d" % (w["blocks"], w["k"]),
+              "games_per_gpu": w["n_games"], "sims_per_move": w["sims"],
               "parallelism": "games sharded across %d GPU(s), no collective on the self-play path" % world,
               "step": "one MCTS wave = n_games simulations (select -> batched dual-net eval -> expand/backup)",
               "l2": "inputs larger than L2: activations ~%d MB per conv layer per agent vs 126 MB L2" %
