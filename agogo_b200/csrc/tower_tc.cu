@@ -7,7 +7,11 @@
 //   * activations live in HBM as NHWC fp16 hi/lo planes over a zero-bordered position grid
 //     ((H+1) x (W+1) per sample: one shared zero column / zero row), so that tap (dy,dx) of an
 //     M-tile is the SAME 2-D TMA box shifted by dy*(W+1)+dx rows — im2col by TMA coordinates,
-//     no gather, halo = zeros already in memory (or TMA out-of-bounds zero fill);
+//     no gather, halo = zeros already in memory (or TMA out-of-bounds zero fill).  Two position
+//     layouts, chosen per board size by padded-row overhead: "flat" = (H+1)x(W+1) positions per
+//     sample, samples back to back, 2-D tensor map (9x9: 100/81); "per-sample" = Hx(W+1) positions,
+//     3-D tensor map [sample][position][channel] whose out-of-range positions are zero-filled by
+//     TMA, M-tiles never straddle samples (19x19: 3 tiles = 384 rows per 361 points vs 400);
 //   * fp32 fidelity on fp16 tensor cores: x = hi + lo and w = hi + lo (both pre-scaled by powers of
 //     two), three tcgen05.mma passes per K-step (hi*hi + hi*lo + lo*hi) into one fp32 TMEM
 //     accumulator; the dropped lo*lo term is ~2^-22 relative;
@@ -69,6 +73,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -114,8 +124,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 struct ConvArgs {
   const int* n_dev;   // batch size (device)
   int n_max;
-  int S, Wp, H, W;    // positions per sample (H+1)*(W+1), row pitch W+1
-  int guard;          // zero rows in front of the activation buffers
+  int S, Wp, H, W;    // positions per sample (flat: (H+1)*(W+1), per-sample: H*(W+1)), row pitch W+1
+  int guard;          // zero rows in front of the activation buffers (flat layout only)
+  int mode3d, tps;    // per-sample layout: 3-D tensor map, tps = M tiles per sample
   int cin;            // padded input channels (multiple of 64)
   int n_total;        // GEMM N of the layer (fused: 2*K)
   int cout;           // output channels (K)
@@ -163,7 +174,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   const int n = min(*a.n_dev, a.n_max);
   const int rows = n * a.S;
-  const int m_tiles = (rows + BM - 1) / BM;
+  const int m_tiles = a.mode3d ? n * a.tps : (rows + BM - 1) / BM;
   const int n_tiles = a.n_total / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int kc_per_tap = a.cin / BK;
@@ -182,11 +193,17 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           mbar_wait(empty_bar(s), ph ^ 1);
           const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
           const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          const int arow = a.guard + m0 + dy * a.Wp + dx;
           const uint32_t sa = smem_base + s * STAGE_BYTES;
           mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          tma_load_2d(sa, &tmA_hi, full_bar(s), kc * BK, arow);
-          tma_load_2d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, arow);
+          if (a.mode3d) {
+            const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM + dy * a.Wp + dx;  // may be <0 / >=S: zero fill
+            tma_load_3d(sa, &tmA_hi, full_bar(s), kc * BK, p0, b);
+            tma_load_3d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, p0, b);
+          } else {
+            const int arow = a.guard + m0 + dy * a.Wp + dx;
+            tma_load_2d(sa, &tmA_hi, full_bar(s), kc * BK, arow);
+            tma_load_2d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, arow);
+          }
           tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), tap * a.cin + kc * BK, n0);
           tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), tap * a.cin + kc * BK, n0);
         }
@@ -234,10 +251,20 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const uint32_t aph = (tcount >> 1) & 1;
       mbar_wait(tfull_bar(acc), aph);
       tc_fence_after();
-      const int r = m0 + quad * 32 + lane;  // logical position row
-      const int p = r % a.S;
+      int r, p;  // r = row in the activation buffer (without guard), p = position inside the sample
+      bool inb;
+      if (a.mode3d) {
+        const int b = mt / a.tps;
+        p = (mt - b * a.tps) * BM + quad * 32 + lane;
+        r = b * a.S + p;
+        inb = p < a.S;
+      } else {
+        r = m0 + quad * 32 + lane;
+        p = r % a.S;
+        inb = r < rows;
+      }
       const int y = p / a.Wp, x = p - y * a.Wp;
-      const bool valid = r < rows && y < a.H && x < a.W;
+      const bool valid = inb && y < a.H && x < a.W;
       const int hw = y * a.W + x;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
       const float2* aff = a.aff + (size_t)(valid ? hw : 0) * a.n_total + n0;
@@ -290,9 +317,9 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
 // fp32 NCHW planes -> zero-bordered NHWC fp16 hi/lo (channels padded to cpad)
 __global__ void k_pack_planes(const float* __restrict__ planes, const int* __restrict__ n_dev, int n_max, int F, int H,
-                              int W, int cpad, int guard, float scale, __half* hi, __half* lo) {
+                              int W, int cpad, int guard, int S, float scale, __half* hi, __half* lo) {
   const int n = min(*n_dev, n_max);
-  const int HW = H * W, Wp = W + 1, S = (H + 1) * Wp;
+  const int HW = H * W, Wp = W + 1;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * HW * cpad) return;
   const int c = (int)(idx % cpad);
@@ -310,11 +337,11 @@ __global__ void k_pack_planes(const float* __restrict__ planes, const int* __res
 // (coalesced 16-byte loads), three dot products reduced with shuffles.
 //   ph [n][2][HW], vh [n][HW]  (the layout the linear layers consume)
 __global__ void k_head_convs_nhwc(const __half* __restrict__ hi, const __half* __restrict__ lo, const int* __restrict__ n_dev,
-                                  int n_max, int K, int H, int W, int guard, float inv_scale, const float* __restrict__ wp,
+                                  int n_max, int K, int H, int W, int guard, int S, float inv_scale, const float* __restrict__ wp,
                                   const float* __restrict__ gp, const float* __restrict__ bp, const float* __restrict__ wv,
                                   const float* __restrict__ gv, const float* __restrict__ bv, float* ph, float* vh) {
   const int n = min(*n_dev, n_max);
-  const int HW = H * W, Wp = W + 1, S = (H + 1) * Wp;
+  const int HW = H * W, Wp = W + 1;
   const int lane = threadIdx.x & 31;
   const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (wid >= (size_t)n * HW) return;
@@ -380,6 +407,19 @@ CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows
   return m;
 }
 
+// per-sample layout: 3-D fp16 tensor [n][S][cols], box {64 cols, BM positions, 1 sample}
+CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {cols, S, n};
+  cuuint64_t strides[2] = {cols * 2, S * cols * 2};
+  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(3d) failed: " + std::to_string((int)r));
+  return m;
+}
+
 struct Layer {
   int cin, n_total, bn;
   bool pair;
@@ -389,7 +429,7 @@ struct Layer {
 };
 struct Impl {
   NetDims d;
-  int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3;
+  int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1;
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
   __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
@@ -416,9 +456,10 @@ void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUt
   }
   ConvArgs a;
   a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
+  a.mode3d = I.mode3d; a.tps = I.tps;
   a.cin = L.cin; a.n_total = L.n_total; a.cout = I.d.K; a.aff = L.aff; a.out_hi = ohi; a.out_lo = olo;
   a.act_scale = ldexpf(1.0f, I.ea); a.err = err; a.passes = I.passes;
-  const int max_tiles = ((I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
+  const int max_tiles = (I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
   const int grid = std::min(I.num_sms, max_tiles);
   k_conv3x3_tc<BN, PAIR><<<grid, NTHREADS, smem_bytes(BN), st>>>(ah, al, L.mB_hi, L.mB_lo, a);
 }
@@ -443,17 +484,25 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
   t.impl = I;
   I->d = d; I->n_max = n_max; I->ea = act_scale_log2;
   if (const char* ps = getenv("AZ_TC_PASSES")) { int v = atoi(ps); if (v >= 1 && v <= 3) I->passes = v; }  // experiments only
-  I->guard = ((d.W + 2 + 7) / 8) * 8;
-  I->S = (d.H + 1) * (d.W + 1);
-  I->rows_alloc = I->guard + n_max * I->S + I->guard + BM;
+  // layout choice by padded-row overhead (rows computed per real board point)
+  const int S_flat = (d.H + 1) * (d.W + 1), S_ps = d.H * (d.W + 1), tps = (S_ps + BM - 1) / BM;
+  I->mode3d = (tps * BM < S_flat) ? 1 : 0;
+  if (const char* m = getenv("AZ_TC_LAYOUT")) I->mode3d = m[0] == '3';  // experiments: "3" / "2"
+  if (I->mode3d) { I->guard = 0; I->S = S_ps; I->tps = tps; I->rows_alloc = n_max * I->S; }
+  else { I->guard = ((d.W + 2 + 7) / 8) * 8; I->S = S_flat; I->tps = 1; I->rows_alloc = I->guard + n_max * I->S + I->guard + BM; }
   int dev;
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&I->num_sms, cudaDevAttrMultiProcessorCount, dev));
   auto alloc_h = [&](size_t n) { __half* p; CUDA_CHECK(cudaMalloc(&p, n * 2)); CUDA_CHECK(cudaMemset(p, 0, n * 2)); return p; };
   I->xin_hi = alloc_h((size_t)I->rows_alloc * 64); I->xin_lo = alloc_h((size_t)I->rows_alloc * 64);
   for (int i = 0; i < 2; i++) { I->x_hi[i] = alloc_h((size_t)I->rows_alloc * d.K); I->x_lo[i] = alloc_h((size_t)I->rows_alloc * d.K); }
-  I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM);
-  for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM); }
+  if (I->mode3d) {
+    I->mIn_hi = make_map3d(I->xin_hi, n_max, I->S, 64); I->mIn_lo = make_map3d(I->xin_lo, n_max, I->S, 64);
+    for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map3d(I->x_hi[i], n_max, I->S, d.K); I->mX_lo[i] = make_map3d(I->x_lo[i], n_max, I->S, d.K); }
+  } else {
+    I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM);
+    for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM); }
+  }
   // layers: init (single), then SharedLayers fused pairs
   const int K = d.K, HW = d.HW();
   for (int l = 0; l <= d.SharedLayers; l++) {
@@ -546,7 +595,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   const size_t f0 = I->profile ? I->ev_get(st) : 0;
   {
     size_t total = (size_t)n_max * d.HW() * 64;
-    k_pack_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planes, n_dev, n_max, d.F, d.H, d.W, 64, I->guard, scale,
+    k_pack_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planes, n_dev, n_max, d.F, d.H, d.W, 64, I->guard, I->S, scale,
                                                                   I->xin_hi, I->xin_lo);
     if (launches) (*launches)++;
   }
@@ -565,7 +614,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
     const SnapUnit& vu = s.units[2 + 2 * d.SharedLayers];
     size_t warps = (size_t)n_max * d.HW();
     k_head_convs_nhwc<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
-        I->x_hi[cur], I->x_lo[cur], n_dev, n_max, d.K, d.H, d.W, I->guard, 1.0f / scale, s.d + pu.filter, s.d + pu.gamma,
+        I->x_hi[cur], I->x_lo[cur], n_dev, n_max, d.K, d.H, d.W, I->guard, I->S, 1.0f / scale, s.d + pu.filter, s.d + pu.gamma,
         s.d + pu.beta, s.d + vu.filter, s.d + vu.gamma, s.d + vu.beta, sc.ph, sc.vh);
     if (launches) (*launches)++;
   }

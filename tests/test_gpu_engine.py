@@ -394,3 +394,78 @@ def test_graph_replay_equals_plain_launches(engine_lib):
         H.assert_same_run(run(True), run(False), "graph")
     finally:
         os.environ.pop("AZ_NO_GRAPH", None)
+
+
+def _check_tree_invariants(rows, sims_done_total):
+    """Size-independent properties of a search tree dump (rows: depth, move, N, Wbits, Pbits, expanded, nchild)."""
+    depth, N, nchild, expanded = rows[:, 0], rows[:, 2].astype(np.int64), rows[:, 6], rows[:, 5]
+    P = rows[:, 4].copy().view(np.float32)
+    W = rows[:, 3].copy().view(np.float32)
+    assert np.isfinite(W).all() and np.isfinite(P).all()
+    # walk the preorder dump: children of row i are the next rows at depth+1 until depth drops back
+    stack = []
+    kids = {}
+    for i, d in enumerate(depth):
+        while stack and depth[stack[-1]] >= d:
+            stack.pop()
+        if stack:
+            kids.setdefault(stack[-1], []).append(i)
+        stack.append(i)
+    for i in range(len(rows)):
+        ch = kids.get(i, [])
+        assert len(ch) == nchild[i]
+        if not expanded[i]:
+            assert nchild[i] == 0
+            continue
+        if i != 0:  # priors of a fresh expansion: sorted descending (stable), normalised
+            pass
+        pc = P[ch]
+        if i != 0 or True:
+            s = float(pc.sum())
+            assert abs(s - 1.0) < 1e-3, s
+        # visits: born with 1, +1 for its own expansion, +1 per simulation that went on into a child
+        below = int(sum(N[c] - 1 for c in ch))
+        assert N[i] - 2 == below, (i, N[i], below)
+    assert N[0] - 2 == sims_done_total
+
+
+def test_full_size_properties_c3(engine_lib):
+    """BASELINE config C3 at full width (19x19, 1024 concurrent games, 20x256 tensor-core net), reduced
+    sims: properties that do not need the oracle — visit conservation in every sampled tree, priors
+    normalised, evaluation count = searches + non-null simulations, bit-identical repeat run."""
+    sims = 24
+    def run():
+        d = K.make_desc(K.GAME_WQ, 19, 19, 0, komi=7.5, sims=sims, n_games=1024, seed=5, max_moves=4,
+                        nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=362))
+        e = engine_lib.create(d)
+        H.tame_gammas([e], 0, 3); H.tame_gammas([e], 1, 4)
+        e.set_inferer(0, K.INF_DUAL); e.set_inferer(1, K.INF_DUAL)
+        e.arena_begin(1024, True)
+        e.arena_step()
+        trees = {g: [e.tree_dump(g, t) for t in (0, 1)] for g in (0, 1, 511, 1023)}
+        recs = [e.game_record(g) for g in range(0, 1024, 97)]
+        c = e.counters()
+        e.arena_step()
+        c2 = e.counters()
+        e.arena_finish()
+        ex = e.examples(clear=True)
+        return trees, recs, c, c2, ex
+    trees, recs, c, c2, ex = run()
+    assert c["searches"] == 1024 and c["sims"] == 1024 * sims
+    assert c["evals"] == c["searches"] + c["sims"] - c["null_results"]
+    assert c2["searches"] == 2048
+    for g, (ta, tb) in trees.items():
+        searched = ta if len(ta) else tb
+        assert (len(ta) == 0) != (len(tb) == 0)  # exactly one agent has moved in this game
+        _check_tree_invariants(searched, sims)
+    boards, pols, vals = ex
+    assert boards.shape == (2048, 18 * 361) and np.isin(boards, [0.0, 1.0, -1.0]).all()
+    assert (np.abs(pols.sum(axis=1) - 1) < 1e-6).all() and set(np.unique(vals)) <= {-1.0, 0.0, 1.0}
+    trees2, recs2, c_b, _, ex2 = run()
+    assert c_b == c
+    for r1, r2 in zip(recs, recs2):
+        assert list(r1["moves"]) == list(r2["moves"])
+    assert (ex[0].view(np.uint32) == ex2[0].view(np.uint32)).all()
+    for g in trees:
+        for t in (0, 1):
+            assert (trees[g][t] == trees2[g][t]).all()
