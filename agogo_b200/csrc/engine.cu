@@ -217,8 +217,9 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     if (desc->encoder == AZ_ENC_TWO_PLANE && n.features != 2) throw std::runtime_error("two-plane encoder produces 2 planes");
     P.max_plies = gd.max_moves > 0 ? gd.max_moves + 2 : (gd.kind == AZ_GAME_MNK ? P.cells + 2 : 1024);
     const bool reuse = gd.kind == AZ_GAME_MNK;
-    long long auto_nodes = (long long)(m.sims + 2) * (P.A + 1) * (reuse ? (P.cells + 1) : 1) + 16;
+    long long auto_nodes = (long long)(m.sims + 2) * (P.A + 1 + 3) * (reuse ? (P.cells + 1) : 1) + 16;  // +3: block alignment
     P.max_nodes = desc->max_nodes_per_tree > 0 ? desc->max_nodes_per_tree : (int)std::min<long long>(auto_nodes, 1LL << 30);
+    P.max_nodes = (P.max_nodes + 3) & ~3;
     if (P.maxDepth < 1) throw std::runtime_error("mcts.Config M*N must be >= 1");
 
     EngineDev& E = e->E;

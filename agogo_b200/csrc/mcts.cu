@@ -161,8 +161,8 @@ __device__ inline void backup(const EngineDev& E, size_t tb, const int* path, in
 }
 
 __device__ inline int alloc_nodes(const EngineDev& E, const GameP& P, int* ti, int n, int lane) {
-  int a = ti[TI_ALLOC];
-  if (a + n > P.max_nodes) { raise(E, ERR_POOL_EXHAUSTED, lane); return -1; }
+  int a = (ti[TI_ALLOC] + 3) & ~3;  // 4-node (16 B per array) alignment of every child block
+  if (a + n + 4 > P.max_nodes) { raise(E, ERR_POOL_EXHAUSTED, lane); return -1; }  // +4: vector loads may touch the pad
   __syncwarp();
   if (lane == 0) ti[TI_ALLOC] = a + n;
   __syncwarp();
@@ -421,25 +421,43 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
       }
       break;
     }
-    // ---- Node.Select (node.go:170-237)
+    // ---- Node.Select (node.go:170-237).  Child blocks start on a 4-node boundary, so each lane pulls
+    // four consecutive children's N / W / P with one 128-bit load per array (coalesced 512 B per warp).
     const int nc = META_NCHILD(meta), first = E.first[tb + node];
+    const uint32_t* Nb = E.N + tb + first;
+    const float* Wb = E.W + tb + first;
+    const float* Pb = E.Pr + tb + first;
     uint32_t pv = 0;
-    for (int j = lane; j < nc; j += 32) pv += E.N[tb + first + j];
+    for (int j0 = lane * 4; j0 < nc; j0 += 128) {
+      const uint4 n4 = *reinterpret_cast<const uint4*>(Nb + j0);
+      pv += n4.x;
+      if (j0 + 1 < nc) pv += n4.y;
+      if (j0 + 2 < nc) pv += n4.z;
+      if (j0 + 3 < nc) pv += n4.w;
+    }
 #pragma unroll
     for (int off = 16; off; off >>= 1) pv += __shfl_xor_sync(FULL, pv, off);
     const float numerator = __fsqrt_rn(__uint2float_rn(pv));
     float bestv = -INFINITY;
     int besti = 0x7fffffff;
-    for (int j = lane; j < nc; j += 32) {
-      const size_t ci = tb + first + j;
-      const uint32_t visits = E.N[ci];
-      const float qsa = evaluate(E.W[ci], visits, player);  // visits >= 1 always (tree.go:110): fpu is dead
-      const float psa = E.Pr[ci];
-      const float denominator = __fadd_rn(1.0f, __uint2float_rn(visits));
-      const float lastTerm = __fdiv_rn(numerator, denominator);
-      const float puct = __fmul_rn(__fmul_rn(P.puct, psa), lastTerm);
-      const float usa = __fadd_rn(qsa, puct);
-      if (usa > bestv) { bestv = usa; besti = j; }  // strict >: earliest child wins ties
+    for (int j0 = lane * 4; j0 < nc; j0 += 128) {
+      const uint4 n4 = *reinterpret_cast<const uint4*>(Nb + j0);
+      const float4 w4 = *reinterpret_cast<const float4*>(Wb + j0);
+      const float4 p4 = *reinterpret_cast<const float4*>(Pb + j0);
+      const uint32_t nn[4] = {n4.x, n4.y, n4.z, n4.w};
+      const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+      const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (j0 + i >= nc) break;
+        const uint32_t visits = nn[i];
+        const float qsa = evaluate(ww[i], visits, player);  // visits >= 1 always (tree.go:110): fpu is dead
+        const float denominator = __fadd_rn(1.0f, __uint2float_rn(visits));
+        const float lastTerm = __fdiv_rn(numerator, denominator);
+        const float puct = __fmul_rn(__fmul_rn(P.puct, pp[i]), lastTerm);
+        const float usa = __fadd_rn(qsa, puct);
+        if (usa > bestv) { bestv = usa; besti = j0 + i; }  // strict >: earliest child wins ties
+      }
     }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {

@@ -138,30 +138,40 @@ struct Dual {
 
 // ---------------------------------------------------------------------------------------------
 // fp32 kernels (NCHW).  conv: cross-correlation, "same" padding (k-1)/2, stride 1, no bias.
+// Per output point the taps are accumulated in ascending (ci, ky, kx) order with an unfused multiply
+// and add.  The input is zero-padded once so that every tap is one long contiguous
+// `acc[i] += w * src[i]` sweep (vectorisable); a tap that falls outside the board then adds w*0 = +-0,
+// which leaves the running fp32 sum bit-identical to skipping it.
 inline void conv_fwd(const float* x, const float* w, float* y, int B, int Ci, int Co, int H, int W, int k) {
-  int pad = (k - 1) / 2, HW = H * W;
+  const int pad = (k - 1) / 2, HW = H * W, Hp = H + 2 * pad, Wp = W + 2 * pad, PP = Hp * Wp;
+  const int span = (H - 1) * Wp + W;  // flat sweep over rows of pitch Wp (pad columns hold garbage, never stored)
   const bool par = (double)B * Co * Ci * HW * k * k > 5e7;  // threads only pay off on big layers (128-way fork/join costs ~ms)
+  std::vector<float> xp((size_t)B * Ci * PP, 0.0f);
+  for (int b = 0; b < B; b++)
+    for (int ci = 0; ci < Ci; ci++) {
+      const float* xi = x + ((size_t)b * Ci + ci) * HW;
+      float* xo = xp.data() + ((size_t)b * Ci + ci) * PP + pad * Wp + pad;
+      for (int yy = 0; yy < H; yy++)
+        for (int xx = 0; xx < W; xx++) xo[yy * Wp + xx] = xi[yy * W + xx];
+    }
 #pragma omp parallel for collapse(2) schedule(static) if (par)
   for (int b = 0; b < B; b++)
     for (int co = 0; co < Co; co++) {
-      float* yo = y + ((size_t)b * Co + co) * HW;
-      for (int i = 0; i < HW; i++) yo[i] = 0;
+      std::vector<float> accv((size_t)H * Wp, 0.0f);
+      float* acc = accv.data();
       for (int ci = 0; ci < Ci; ci++) {
-        const float* xi = x + ((size_t)b * Ci + ci) * HW;
+        const float* xi = xp.data() + ((size_t)b * Ci + ci) * PP;
         const float* wk = w + ((size_t)co * Ci + ci) * k * k;
         for (int ky = 0; ky < k; ky++)
           for (int kx = 0; kx < k; kx++) {
-            float wv = wk[ky * k + kx];
-            int dy = ky - pad, dx = kx - pad;
-            int y0 = dy < 0 ? -dy : 0, y1 = dy > 0 ? H - dy : H;
-            int x0 = dx < 0 ? -dx : 0, x1 = dx > 0 ? W - dx : W;
-            for (int yy = y0; yy < y1; yy++) {
-              const float* xr = xi + (yy + dy) * W + dx;
-              float* yr = yo + yy * W;
-              for (int xx = x0; xx < x1; xx++) yr[xx] = yr[xx] + wv * xr[xx];
-            }
+            const float wv = wk[ky * k + kx];
+            const float* src = xi + ky * Wp + kx;
+            for (int i = 0; i < span; i++) acc[i] = acc[i] + wv * src[i];
           }
       }
+      float* yo = y + ((size_t)b * Co + co) * HW;
+      for (int yy = 0; yy < H; yy++)
+        for (int xx = 0; xx < W; xx++) yo[yy * W + xx] = acc[yy * Wp + xx];
     }
 }
 // dX += conv_transpose(dY, w) ; dW += corr(x, dY)
