@@ -89,8 +89,17 @@ struct az_engine {
   unsigned long long wave_graph_launches = 0;
   bool graphs_enabled = true, profiling = false;
   TrainWS train;
-  void* comm = nullptr;  // ncclComm_t
+  void* comm = nullptr;  // ncclComm_t (bootstrap of the peer-memory path; plain all-reduce as the checked alternative)
   int rank = 0, world = 1;
+  // peer-memory collective (K8): IPC-mapped gradient / parameter / flag buffers of every rank
+  bool p2p = false;
+  std::vector<void*> ipc_opened;
+  float** d_peer_grads = nullptr;
+  float** d_peer_params[2] = {nullptr, nullptr};
+  int** d_peer_flags = nullptr;
+  int* my_flags = nullptr;
+  unsigned int* done_counter = nullptr;
+  int epoch = 0, num_sms = 148;
   mutable std::string err;
 
   template <class T>
@@ -108,6 +117,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   ncclResult_t (*CommDestroy)(ncclComm_t);
   const char* (*GetErrorString)(ncclResult_t);
 };
@@ -120,9 +130,10 @@ static NcclApi& nccl_api() {
     api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
     api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
     api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy || !api.GetErrorString)
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.AllGather || !api.CommDestroy || !api.GetErrorString)
       throw std::runtime_error("libnccl.so.2: missing symbols");
     ok = true;
   }
@@ -166,6 +177,7 @@ void az_engine_destroy(az_engine* e) {
   for (int a = 0; a < 2; a++) { tc_tower_free(e->tc[a]); }
   train_ws_free(e->train);
   if (e->wave_graph) cudaGraphExecDestroy(e->wave_graph);
+  for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->comm) { try { nccl_api().CommDestroy((ncclComm_t)e->comm); } catch (...) {} }
   fp32_scratch_free(e->fp32);
   if (e->h_ex_board) cudaFreeHost(e->h_ex_board);
@@ -271,7 +283,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     nd.F = n.features; nd.A1 = n.action_space;
     e->L = build_layout(nd);
     for (int a = 0; a < 2; a++) {
-      e->net_params[a] = e->dalloc<float>(e->L.total);
+      e->net_params[a] = e->dalloc<float>(e->L.total + 4);  // +4: the fused collective moves float4s
       e->snap[a] = make_snapshot_layout(e->L);
       e->snap[a].d = e->dalloc<float>(e->snap[a].total);
     }
@@ -875,6 +887,11 @@ static void shuffle_rows(std::vector<float>& Xs, std::vector<float>& Pi, std::ve
 // one step on the batch already staged in the workspace: grads, [all-reduce], SGD
 static void train_one(az_engine* e, int net, float lr) {
   train_step_grads(e->train, e->L, e->net_params[net], e->stream, &e->launches);
+  if (e->p2p) {  // K8: reduce-scatter + SGD + all-gather in one kernel over NVLink peer memory
+    train_allreduce_sgd_p2p(e->d_peer_grads, e->d_peer_params[net], e->d_peer_flags, e->my_flags, e->rank, e->world, e->L.total,
+                            lr, ++e->epoch, e->done_counter, e->num_sms, e->stream, &e->launches);
+    return;
+  }
   float gscale = 1.0f;
   if (e->comm) {
     nccl_allreduce_sum(e, train_ws_grads(e->train), e->L.total);
@@ -967,6 +984,43 @@ int az_comm_init(az_engine* e, int32_t rank, int32_t world, const uint8_t id[128
   ncclResult_t r = n.CommInitRank(&c, world, u, rank);
   if (r != ncclSuccess) throw std::runtime_error(std::string("ncclCommInitRank: ") + n.GetErrorString(r));
   e->comm = c; e->rank = rank; e->world = world;
+  // ---- peer-memory path: exchange CUDA IPC handles of {grads, params A, params B, flags} over the new communicator
+  const char* mode = getenv("AZ_TRAIN_COLLECTIVE");  // "nccl" keeps the plain ncclAllReduce + SGD (A/B checks)
+  if (world > 1 && !(mode && strcmp(mode, "nccl") == 0)) {
+    ensure_train(e);
+    CUDA_CHECK(cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device));
+    e->my_flags = e->dalloc<int>(2 * world);
+    e->done_counter = e->dalloc<unsigned int>(1);
+    void* mine[4] = {train_ws_grads(e->train), e->net_params[0], e->net_params[1], e->my_flags};
+    std::vector<cudaIpcMemHandle_t> hs((size_t)4 * world);
+    for (int k = 0; k < 4; k++) CUDA_CHECK(cudaIpcGetMemHandle(&hs[(size_t)4 * rank + k], mine[k]));
+    cudaIpcMemHandle_t* dh = e->dalloc<cudaIpcMemHandle_t>((size_t)4 * world);
+    CUDA_CHECK(cudaMemcpy(dh + (size_t)4 * rank, &hs[(size_t)4 * rank], 4 * sizeof(cudaIpcMemHandle_t), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    ncclResult_t ar = n.AllGather(dh + (size_t)4 * rank, dh, 4 * sizeof(cudaIpcMemHandle_t), ncclChar, c, e->stream);
+    if (ar != ncclSuccess) throw std::runtime_error(std::string("ncclAllGather(ipc handles): ") + n.GetErrorString(ar));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    CUDA_CHECK(cudaMemcpy(hs.data(), dh, hs.size() * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost));
+    std::vector<float*> pg(world), pa(world), pb(world);
+    std::vector<int*> pf(world);
+    for (int r2 = 0; r2 < world; r2++) {
+      void* ptr[4];
+      for (int k = 0; k < 4; k++) {
+        if (r2 == rank) { ptr[k] = mine[k]; continue; }
+        CUDA_CHECK(cudaIpcOpenMemHandle(&ptr[k], hs[(size_t)4 * r2 + k], cudaIpcMemLazyEnablePeerAccess));
+        e->ipc_opened.push_back(ptr[k]);
+      }
+      pg[r2] = (float*)ptr[0]; pa[r2] = (float*)ptr[1]; pb[r2] = (float*)ptr[2]; pf[r2] = (int*)ptr[3];
+    }
+    e->d_peer_grads = e->dalloc<float*>(world); e->d_peer_params[0] = e->dalloc<float*>(world);
+    e->d_peer_params[1] = e->dalloc<float*>(world); e->d_peer_flags = e->dalloc<int*>(world);
+    CUDA_CHECK(cudaMemcpy(e->d_peer_grads, pg.data(), world * sizeof(void*), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(e->d_peer_params[0], pa.data(), world * sizeof(void*), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(e->d_peer_params[1], pb.data(), world * sizeof(void*), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(e->d_peer_flags, pf.data(), world * sizeof(void*), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    e->p2p = true;
+  }
   GUARD_END(e)
   return AZ_OK;
 }

@@ -6,6 +6,7 @@
 // output, block reductions, no atomics => deterministic); the tensor-core version of the conv
 // passes is the next optimisation row.  Semantics are pinned against oracle/dual.hpp
 // (dual_train_step), whose backward is itself pinned by a finite-difference check.
+#include <algorithm>
 #include <stdexcept>
 #include <vector>
 
@@ -264,7 +265,8 @@ void train_ws_alloc(TrainWS& ws, const NetLayout& L) {
   T->dph = T->alloc(B * 2 * HW); T->dvh = T->alloc(B * HW);
   T->dcur = T->alloc(act); T->dprev = T->alloc(act); T->tmp = T->alloc(act); T->dl = T->alloc(act);
   T->cost = T->alloc(1);
-  T->grads = T->alloc(L.total);
+  T->grads = T->alloc(L.total + 4);  // +4: the fused collective moves float4s
+  CUDA_CHECK(cudaMemset(T->grads, 0, (L.total + 4) * 4));
 }
 void train_ws_free(TrainWS& ws) {
   TrainImpl* T = (TrainImpl*)ws.impl;
@@ -353,6 +355,67 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   }
   unit_bwd(0, T->X, T->dcur, nullptr);
   if (launches) *launches += nl;
+}
+
+// K8: gradient all-reduce fused with the SGD step, over NVLink peer memory (no NCCL on this path).
+// Every rank runs this kernel on its own stream after its backward pass.  One-shot algorithm sized
+// for NVSwitch (every peer at full bandwidth): rank r owns the r-th slice of the flat Model()
+// buffer; it sums that slice of every rank's gradient straight out of peer HBM (fixed rank order,
+// so the result is deterministic and — being computed once — identical everywhere), applies
+// w -= lr * g / world to its slice and writes the updated slice into every rank's parameter buffer.
+// Cross-GPU ordering uses epoch flags in peer memory: (A) "my gradients are complete" before anyone
+// reads them, (B) "my slice is written everywhere" before anyone's next kernel may start.
+__global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float* const* __restrict__ peer_params,
+                                    int* const* __restrict__ peer_flags, int* my_flags, int rank, int world, size_t n,
+                                    float lr_over_world, int epoch, unsigned int* done_counter) {
+  __shared__ int s_last;
+  // (A) publish "gradients ready", then wait for everybody's
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    ((volatile int*)peer_flags[threadIdx.x])[rank] = epoch;
+  }
+  if (threadIdx.x < world) {
+    while (((volatile int*)my_flags)[threadIdx.x] < epoch) {}
+  }
+  __syncthreads();
+  __threadfence_system();
+  const size_t shard = (((n + world - 1) / world) + 3) & ~(size_t)3;
+  const size_t lo = (size_t)rank * shard;
+  const size_t hi = lo + shard < n ? lo + shard : ((n + 3) & ~(size_t)3);  // buffers are padded to a multiple of 4
+  float* mine = peer_params[rank];
+  for (size_t i = lo + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += (size_t)gridDim.x * blockDim.x * 4) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < world; r++) {
+      const float4 v = *reinterpret_cast<const float4*>(peer_grads[r] + i);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    }
+    float4 p = *reinterpret_cast<const float4*>(mine + i);
+    p.x -= lr_over_world * g.x; p.y -= lr_over_world * g.y; p.z -= lr_over_world * g.z; p.w -= lr_over_world * g.w;
+    for (int r = 0; r < world; r++) *reinterpret_cast<float4*>(peer_params[r] + i) = p;
+  }
+  // (B) the last block of this rank publishes "slice written" and waits for everybody's
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x < world) {
+      ((volatile int*)peer_flags[threadIdx.x])[world + rank] = epoch;
+      while (((volatile int*)my_flags)[world + threadIdx.x] < epoch) {}
+    }
+    if (threadIdx.x == 0) *done_counter = 0;
+  }
+}
+
+void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params, int* const* peer_flags, int* my_flags,
+                             int rank, int world, size_t n, float lr, int epoch, unsigned int* done_counter, int num_sms,
+                             cudaStream_t st, unsigned long long* launches) {
+  const size_t shard = (((n + world - 1) / world) + 3) & ~(size_t)3;
+  int blocks = (int)std::min<size_t>((shard / 4 + 255) / 256, (size_t)num_sms * 2);
+  if (blocks < 1) blocks = 1;
+  k_allreduce_sgd_p2p<<<blocks, 256, 0, st>>>(peer_grads, peer_params, peer_flags, my_flags, rank, world, n, lr / (float)world, epoch,
+                                             done_counter);
+  if (launches) (*launches)++;
 }
 
 void train_sgd(TrainWS& ws, const NetLayout& L, float* P, float lr, float gscale, cudaStream_t st, unsigned long long* launches) {

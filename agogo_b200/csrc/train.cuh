@@ -10,3 +10,7 @@ float* train_ws_cost(TrainWS& ws);   // device scalar
 void train_ws_inputs(TrainWS& ws, float** X, float** Pi, float** V);  // device staging of one batch
 void train_step_grads(TrainWS& ws, const NetLayout& L, const float* params, cudaStream_t st, unsigned long long* launches);
 void train_sgd(TrainWS& ws, const NetLayout& L, float* params, float lr, float gscale, cudaStream_t st, unsigned long long* launches);
+// K8: one kernel = reduce-scatter over peer memory + SGD on the owned slice + all-gather into every peer
+void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params, int* const* peer_flags, int* my_flags,
+                             int rank, int world, size_t n, float lr, int epoch, unsigned int* done_counter, int num_sms,
+                             cudaStream_t st, unsigned long long* launches);

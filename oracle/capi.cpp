@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstring>
 #include <exception>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "../include/agogo_b200.h"
 #include "arena.hpp"
@@ -457,6 +460,16 @@ int az_counters_reset(az_engine* e) {
   e->base = Counters();
   for (auto& s : e->slots) { s->A.mcts->cnt = Counters(); s->B.mcts->cnt = Counters(); }
   return AZ_OK;
+}
+
+// Oracle-only extra: OpenMP thread count of the conv loops (bench.py picks the fastest setting on the box).
+int azo_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }
 
 // Oracle-only extra: the reference's own AZ.Learn loop (agogo.go:100-172) run natively, used to

@@ -10,8 +10,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, collective):
     sys.path.insert(0, ROOT)
+    os.environ["AZ_TRAIN_COLLECTIVE"] = collective
     import torch
     import torch.distributed as dist
     from agogo_b200 import _capi as K
@@ -25,7 +26,8 @@ def _worker(rank, world, port, out_dir):
     az = host.AZ(host.Game(K.GAME_C4, 6, 7, 4), conf, n_games=8, seed=5, dist=dist, device=rank, flags=K.FLAG_FP32_TOWER)
     assert az.engine_comm
     az.Learn(2, 8, 2, 6)
-    np.save(os.path.join(out_dir, "params_%d.npy" % rank), np.concatenate([az.engine.net_get(0), az.engine.net_get(1)]))
+    np.save(os.path.join(out_dir, "params_%s_%d.npy" % (collective, rank)),
+            np.concatenate([az.engine.net_get(0), az.engine.net_get(1)]))
     dist.destroy_process_group()
 
 
@@ -39,7 +41,13 @@ def test_two_gpu_learn_nccl(tmp_path):
         pytest.skip("needs 2 GPUs")  # (decided without importing torch: a cold import costs minutes on a fresh box)
     import torch.multiprocessing as mp
     port = 29700 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    p0, p1 = np.load(tmp_path / "params_0.npy"), np.load(tmp_path / "params_1.npy")
-    assert np.isfinite(p0).all()
-    assert (p0.view(np.uint32) == p1.view(np.uint32)).all(), "replicas diverged"
+    res = {}
+    for i, collective in enumerate(("p2p", "nccl")):  # the fused peer-memory kernel, and plain ncclAllReduce + SGD
+        mp.spawn(_worker, args=(2, port + i, str(tmp_path), collective), nprocs=2, join=True)
+        p0 = np.load(tmp_path / ("params_%s_0.npy" % collective))
+        p1 = np.load(tmp_path / ("params_%s_1.npy" % collective))
+        assert np.isfinite(p0).all()
+        assert (p0.view(np.uint32) == p1.view(np.uint32)).all(), "replicas diverged (%s)" % collective
+        res[collective] = p0
+    # same mathematics, different summation order inside the collective
+    assert np.abs(res["p2p"] - res["nccl"]).max() <= 1e-4 * max(1.0, np.abs(res["nccl"]).max())
