@@ -322,12 +322,20 @@ def main():
         cpu_baseline = {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
                         "sample": "oracle, 1 game x %d pipeline iterations (1 leaf eval each, useful-work batch 1), %.1f s"
                                   % (args.cpu_steps, r["seconds"])}
+    # tree-kernel traffic from COUNTED events: 12 B per child scanned by Select (N, W, P), 8 B per level
+    # (meta, first), 20 B per node created, 8 B read-modify-write per node backed up
+    tree_bytes = 12 * cnt["select_children"] + 8 * cnt["select_levels"] + 20 * cnt["created"] + 8 * cnt["backup_nodes"]
+    tree = {"counted_bytes_per_sim": tree_bytes / max(sims, 1), "select_children_per_sim": cnt["select_children"] / max(sims, 1),
+            "levels_per_sim": cnt["select_levels"] / max(sims, 1), "nodes_created_per_eval": cnt["created"] / max(evals, 1),
+            "null_results": cnt["null_results"],
+            "note": "k_select + k_expand_backup take ~0.14 ms of a ~45 ms wave (profiles/r01_summary.md): latency-bound "
+                    "pointer chase, not bandwidth-bound"}
     line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split on tcgen05, fp32 accumulate; outputs within 1e-4 of fp32)",
             "data": "synthetic", "config": config, "moves_per_sec": value / (w["sims"] + 1),
             "evals_per_sec": tot_evals / dt_max, "tflops_algorithmic": tot_evals / dt_max * fpe / 1e12,
-            "e2e": e2e, "gpu_launches": int(tot_launch), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": int(tot_launch), "roofline": roofline, "tree": tree, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary()}
     print(json.dumps(line))
     return 0
