@@ -20,6 +20,7 @@ enum {
   ERR_ACT_OVERFLOW = 8,      // tcgen05 tower: fp16 activation overflow (raise act_scale headroom)
   ERR_NAN_PRIOR = 16,        // NaN prior reached the sort (Go's sort order is unspecified there)
   ERR_PATH_OVERFLOW = 32,
+  ERR_RESIGN_APPLIED = 64,   // Arena applies Resign: every game.State.Apply indexes board[-2] and panics
 };
 
 // Game + search parameters, passed by value to every kernel.
@@ -33,6 +34,8 @@ struct GameP {
   float puct;
   int sims;
   int dont_prefer_pass;
+  int dumb_pass, dont_resign;  // mcts.Config.DumbPass, PassPreference == DontResign
+  float resign_pct;            // mcts.Config.ResignPercentage
   int shared_tree;
   int encoder;        // 0 two-plane, 1 wq18
   int F;              // feature planes

@@ -160,6 +160,7 @@ static int device_error_to_rc(az_engine* e, int bits) {
   if (bits & ERR_ACT_OVERFLOW) m += " fp16 activation overflow in the tcgen05 tower (lower act_scale_log2)";
   if (bits & ERR_NAN_PRIOR) m += " NaN prior";
   if (bits & ERR_PATH_OVERFLOW) m += " per-game move capacity exceeded (set game.max_moves)";
+  if (bits & ERR_RESIGN_APPLIED) m += " index out of range (Arena applied Resign: State.Apply indexes board[-2])";
   e->err = m;
   return AZ_ERR_PANIC;
 }
@@ -203,8 +204,6 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
   if (gd.kind == AZ_GAME_WQ && gd.m != gd.n) { g_create_error = "wq boards are square"; return AZ_ERR_INVALID; }
   if (desc->encoder == AZ_ENC_WQ18 && gd.kind != AZ_GAME_WQ) { g_create_error = "WQEncoder needs State.Historical, which only wq provides on clones"; return AZ_ERR_UNSUPPORTED; }
   if (m.random_count > 0) { g_create_error = "RandomCount > 0 (temperature sampling, tree.go:212-247) is not implemented on device"; return AZ_ERR_UNSUPPORTED; }
-  if (!m.dumb_pass) { g_create_error = "DumbPass=false is not implemented on device"; return AZ_ERR_UNSUPPORTED; }
-  if (m.resign_percentage != 0 && m.pass_preference != 2) { g_create_error = "ResignPercentage != 0 is not implemented on device"; return AZ_ERR_UNSUPPORTED; }
   if (n.width != gd.n || n.height != gd.m) { g_create_error = "nn width/height must match the board"; return AZ_ERR_INVALID; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -222,7 +221,8 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     P.kind = gd.kind; P.m = gd.m; P.n = gd.n; P.k = gd.k; P.cells = gd.m * gd.n;
     P.A = gd.kind == AZ_GAME_C4 ? gd.n : P.cells;
     P.komi = gd.komi; P.max_moves = gd.max_moves; P.maxDepth = m.m * m.n; P.puct = m.puct; P.sims = m.sims;
-    P.dont_prefer_pass = m.pass_preference == 0; P.shared_tree = (desc->flags & AZ_FLAG_SHARED_TREE) ? 1 : 0;
+    P.dont_prefer_pass = m.pass_preference == 0; P.dumb_pass = m.dumb_pass != 0; P.dont_resign = m.pass_preference == 2;
+    P.resign_pct = m.resign_percentage; P.shared_tree = (desc->flags & AZ_FLAG_SHARED_TREE) ? 1 : 0;
     P.encoder = desc->encoder; P.F = n.features; P.plane = n.features * P.cells;
     P.hist_len = desc->encoder == AZ_ENC_WQ18 ? 8 : 0;
     if (desc->encoder == AZ_ENC_WQ18 && n.features != 18) throw std::runtime_error("WQEncoder produces 18 planes");
@@ -653,7 +653,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   gi[GI_TO_MOVE] = st->to_move; gi[GI_MOVE_NUMBER] = st->move_number;
   gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : (P.kind == KIND_WQ ? st->passes : 0);
   gi[GI_C4_PASS] = P.kind == KIND_C4 ? st->passes : 0;
-  gi[GI_ACTIVE] = 1; gi[GI_CUR_AGENT] = P.shared_tree ? 0 : agent;
+  gi[GI_ACTIVE] = 1; gi[GI_CUR_AGENT] = P.shared_tree ? 0 : agent; gi[GI_LAST_MOVE] = st->last_move;
   gi[GI_A_PLAYER] = (P.shared_tree || agent == 0) ? player : opp_player;
   if (P.kind == KIND_WQ) {  // clean Zobrist hash of the position (wq/zobrist.go:44-56)
     std::vector<int32_t> zt((size_t)P.cells * 2);

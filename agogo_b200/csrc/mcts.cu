@@ -194,6 +194,7 @@ __global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __re
       gi[GI_CUR_AGENT] = coin == 0 ? 0 : 1;
       gi[GI_TO_MOVE] = C_BLACK;  // SetToMove(currentPlayer.Player), arena.go:91
       gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : 0;
+      gi[GI_LAST_MOVE] = MV_PASS;  // State.LastMove() of an empty history (mnk.go:84-89)
     }
   }
   __syncwarp();
@@ -677,10 +678,19 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
       E.N[ci] = w.st[0][i]; E.W[ci] = __uint_as_float(w.st[1][i]); E.Pr[ci] = __uint_as_float(w.st[2][i]);
       E.meta[ci] = w.st[3][i]; E.first[ci] = (int)w.st[4][i];
       w.ib[w.ia[i]] = META_MOVE(w.st[3][i]);  // moves in sorted order
+      w.fb[w.ia[i]] = w.fa[i];                 // Evaluate(player) in sorted order
     }
     __syncwarp();
     best = w.ib[0];
-    if (P.dont_prefer_pass && best == MV_PASS) {  // noPassBestMove (search.go:538-563)
+    float bestScore = w.fb[0];
+    // search.go:366-389: pass preferences, then resignation
+    const float rootScore = E.Pr[tb + root];
+    const bool passing_loses = (rootScore > 0.0f && player == C_WHITE) || (rootScore < 0.0f && player == C_BLACK);
+    bool want_nopass = false;
+    if (P.dont_prefer_pass && best == MV_PASS) want_nopass = true;
+    else if (!P.dumb_pass && best == MV_PASS) want_nopass = passing_loses;
+    else if (!P.dumb_pass && gi[GI_LAST_MOVE] == MV_PASS) { if (!passing_loses) best = MV_PASS; }
+    if (want_nopass) {  // noPassBestMove (search.go:538-563): first child in sorted order that is not Pass and is legal
       if (P.kind == KIND_WQ) { wq_analyze(P, w.board, w.wq, lane); analyzed = true; }
       int found = -1;
       for (int base = 0; base < nc && found < 0; base += 32) {
@@ -696,8 +706,19 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
         unsigned m = __ballot_sync(FULL, ok);
         if (m) found = base + __ffs(m) - 1;
       }
-      if (found >= 0) best = w.ib[found];
+      if (found >= 0) { best = w.ib[found]; bestScore = w.fb[found]; }  // visits >= 1 always: never the "not visited" 1.0
     }
+    // shouldResign (search.go:502-535)
+    if (best == MV_PASS && !P.dont_resign && P.resign_pct != 0.0f) {
+      const int move_number = P.kind == KIND_C4 ? 1 : gi[GI_MOVE_NUMBER];
+      const float thr = P.resign_pct < 0.0f ? 0.1f : P.resign_pct;
+      if (move_number > P.maxDepth / 4 && !(bestScore > thr)) best = MV_RESIGN;
+    }
+  }
+  if (best == MV_RESIGN) {  // arena.go:127: Apply(Resign) indexes board[-2] in mnk, c4 and wq alike
+    raise(E, ERR_RESIGN_APPLIED, lane);
+    if (lane == 0) gi[GI_ACTIVE] = 0;
+    return;
   }
   // ---- t.prev = clone(current); cachedPolicies[{hash, best}]++ (search.go:152,161)
   const uint32_t hash = (uint32_t)wv[WV_HASH];
@@ -745,17 +766,22 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   s.passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
   int zhash = gi[GI_ZHASH];
   int c4pass = gi[GI_C4_PASS];
+  int last_move = gi[GI_LAST_MOVE];  // State.LastMove(): the last entry State.Apply appended to history
   if (P.kind == KIND_MNK) {
     if (simple_check(P, w.board, best)) {
       if (lane == 0) E.hmoves[(size_t)g * P.max_plies + s.move_number] = (int16_t)best;
       state_apply(P, w, E.cellsP, s, player, best, lane, &analyzed, nullptr, nullptr);
+      last_move = best;
     }
   } else if (P.kind == KIND_C4) {
-    if (best == MV_PASS || (best >= 0 && best < P.n && c4_drop_row(P, w.board, best) >= 0))
+    if (best == MV_PASS || (best >= 0 && best < P.n && c4_drop_row(P, w.board, best) >= 0)) {
       state_apply(P, w, E.cellsP, s, player, best, lane, &analyzed, nullptr, nullptr);
+      last_move = best;
+    }
     c4pass = best == MV_PASS ? c4pass + 1 : 0;  // c4/game.go:66-70
   } else {
     state_apply(P, w, E.cellsP, s, player, best, lane, &analyzed, &zhash, E.ztable);
+    last_move = best;
   }
   __syncwarp();
   for (int i = lane; i < P.cells; i += 32) gb[i] = w.board[i];
@@ -780,7 +806,7 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
     gi[GI_N_MOVES] = n_moves + 1;
     gi[GI_TO_MOVE] = s.to_move; gi[GI_MOVE_NUMBER] = s.move_number;
     if (P.kind == KIND_WQ) gi[GI_PASSES] = s.passes;
-    gi[GI_ZHASH] = zhash; gi[GI_C4_PASS] = c4pass;
+    gi[GI_ZHASH] = zhash; gi[GI_C4_PASS] = c4pass; gi[GI_LAST_MOVE] = last_move;
     gi[GI_ARENA_PASS] = arena_pass;
     gi[GI_CUR_AGENT] ^= 1;  // switchPlayer
     gi[GI_ACTIVE] = active ? 1 : 0;

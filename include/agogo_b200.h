@@ -157,6 +157,7 @@ int az_search_end(az_engine* e);                     /* bestMove, example, Apply
 typedef struct az_state {
   const int32_t* board; /* [m*n] colours */
   int32_t to_move, move_number, passes;
+  int32_t last_move;    /* LastMove().Single; AZ_PASS for an empty history (mnk.go:84-89) */
   int32_t n_hist;       /* 0..8 */
   const int32_t* hist;  /* [n_hist][m*n], oldest first */
 } az_state;

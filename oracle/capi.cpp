@@ -260,18 +260,19 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   if (g.kind == AZ_GAME_MNK) {
     MNK* t = new MNK(g.m, g.n, g.k);
     t->board.assign(st->board, st->board + cells);
-    t->history.assign(st->move_number, PlayerMove{None, 0}); t->histPtr = st->move_number; t->nextToMove = st->to_move;
+    t->history.assign(st->move_number, PlayerMove{None, st->last_move}); t->histPtr = st->move_number; t->nextToMove = st->to_move;
     state.reset(t);
   } else if (g.kind == AZ_GAME_C4) {
     C4* t = new C4(g.m, g.n, g.k);
     t->data.assign(st->board, st->board + cells); t->nextToMove = st->to_move; t->passCount = st->passes;
+    if (st->last_move != PassMove || st->move_number > 0) { t->history.assign(1, PlayerMove{None, st->last_move}); t->histPtr = 1; }
     state.reset(t);
   } else {
     WQ* t = new WQ(g.m, 0, g.komi, g.zobrist_seed);
     t->board.data.assign(st->board, st->board + cells);
     for (int i = 0; i < cells; i++) if (st->board[i]) t->board.zupdate(PlayerMove{st->board[i], (Single)i});  // clean hash
     t->nextToMove = st->to_move; t->passes = st->passes; t->moveCount = st->move_number;
-    t->history.assign(st->move_number, PlayerMove{None, -1}); t->histPtr = st->move_number;
+    t->history.assign(st->move_number, PlayerMove{None, st->last_move}); t->histPtr = st->move_number;
     for (int i = 0; i < st->n_hist; i++) {
       auto hn = std::make_shared<WQ::HistNode>();
       hn->board.assign(st->hist + (size_t)i * cells, st->hist + (size_t)(i + 1) * cells);

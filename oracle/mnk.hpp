@@ -39,6 +39,7 @@ struct MNK : State {
 
   State* Apply(PlayerMove mv) override {  // mnk.go:117-137 — mutates in place, returns self
     if (!Check(mv)) return this;
+    if (mv.single < 0) throw std::runtime_error("index out of range");  // Resign passes Check, then board[-2] panics
     std::vector<int32_t> hb = board;
     board[mv.single] = mv.player;
     histPtr++;

@@ -465,3 +465,19 @@ def test_full_size_properties_c3(engine_lib):
     for g in trees:
         for t in (0, 1):
             assert (trees[g][t] == trees2[g][t]).all()
+
+
+@pytest.mark.parametrize("kind,m,n,k,dumb,pref", [
+    (K.GAME_C4, 6, 7, 4, 0, K.DONT_PREFER_PASS), (K.GAME_C4, 6, 7, 4, 0, K.PREFER_PASS), (K.GAME_C4, 6, 7, 4, 1, K.DONT_RESIGN),
+    (K.GAME_WQ, 5, 5, 0, 0, K.PREFER_PASS), (K.GAME_WQ, 5, 5, 0, 0, K.DONT_PREFER_PASS), (K.GAME_MNK, 3, 3, 3, 0, K.PREFER_PASS),
+])
+def test_parity_pass_preferences(oracle, engine_lib, kind, m, n, k, dumb, pref):
+    """bestMove's pass heuristics (search.go:366-389): DumbPass=false and every PassPreference."""
+    A = n if kind == K.GAME_C4 else m * n
+    def desc():
+        return K.make_desc(kind, m, n, k, komi=7.5, sims=20, n_games=6, seed=15, max_moves=30, dumb_pass=dumb,
+                           pass_preference=pref, nn=H.tiny_nn(m, n, A + 1, features=18 if kind == K.GAME_WQ else 2))
+    eo, eg = oracle.create(desc()), engine_lib.create(desc())
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    H.assert_same_run(H.play_and_collect(eo, 6), H.play_and_collect(eg, 6), "pass-pref")
