@@ -36,6 +36,9 @@ struct GameP {
   int dont_prefer_pass;
   int dumb_pass, dont_resign;  // mcts.Config.DumbPass, PassPreference == DontResign
   float resign_pct;            // mcts.Config.ResignPercentage
+  int random_count;            // mcts.Config.RandomCount / RandomMinVisits / RandomTemperature (tree.go:212-247)
+  unsigned random_min_visits;
+  float random_temperature;
   int shared_tree;
   int encoder;        // 0 two-plane, 1 wq18
   int F;              // feature planes

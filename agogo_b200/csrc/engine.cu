@@ -203,7 +203,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
   if (gd.kind < 0 || gd.kind > 2 || gd.m < 1 || gd.n < 1 || desc->n_games < 1) { g_create_error = "invalid game/n_games"; return AZ_ERR_INVALID; }
   if (gd.kind == AZ_GAME_WQ && gd.m != gd.n) { g_create_error = "wq boards are square"; return AZ_ERR_INVALID; }
   if (desc->encoder == AZ_ENC_WQ18 && gd.kind != AZ_GAME_WQ) { g_create_error = "WQEncoder needs State.Historical, which only wq provides on clones"; return AZ_ERR_UNSUPPORTED; }
-  if (m.random_count > 0) { g_create_error = "RandomCount > 0 (temperature sampling, tree.go:212-247) is not implemented on device"; return AZ_ERR_UNSUPPORTED; }
+  if (m.random_count > 0 && !(m.random_temperature > 0)) { g_create_error = "RandomCount > 0 needs RandomTemperature > 0"; return AZ_ERR_INVALID; }
   if (n.width != gd.n || n.height != gd.m) { g_create_error = "nn width/height must match the board"; return AZ_ERR_INVALID; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -222,7 +222,8 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     P.A = gd.kind == AZ_GAME_C4 ? gd.n : P.cells;
     P.komi = gd.komi; P.max_moves = gd.max_moves; P.maxDepth = m.m * m.n; P.puct = m.puct; P.sims = m.sims;
     P.dont_prefer_pass = m.pass_preference == 0; P.dumb_pass = m.dumb_pass != 0; P.dont_resign = m.pass_preference == 2;
-    P.resign_pct = m.resign_percentage; P.shared_tree = (desc->flags & AZ_FLAG_SHARED_TREE) ? 1 : 0;
+    P.resign_pct = m.resign_percentage;
+    P.random_count = m.random_count; P.random_min_visits = m.random_min_visits; P.random_temperature = m.random_temperature; P.shared_tree = (desc->flags & AZ_FLAG_SHARED_TREE) ? 1 : 0;
     P.encoder = desc->encoder; P.F = n.features; P.plane = n.features * P.cells;
     P.hist_len = desc->encoder == AZ_ENC_WQ18 ? 8 : 0;
     if (desc->encoder == AZ_ENC_WQ18 && n.features != 18) throw std::runtime_error("WQEncoder produces 18 planes");
@@ -238,6 +239,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     const int G = desc->n_games;
     E.G = G; E.T = P.shared_tree ? 1 : 2; E.cellsP = (P.cells + 15) & ~15;
     E.Lmax = std::max(n.action_space, P.A + 1);
+    E.tree_seed = derive_seed(desc->seed, 1);
     E.board = e->dalloc<uint8_t>((size_t)G * E.cellsP);
     E.hist = e->dalloc<uint8_t>(P.hist_len ? (size_t)G * 8 * E.cellsP : 1);
     E.gi = e->dalloc<int32_t>((size_t)G * GI_COUNT);

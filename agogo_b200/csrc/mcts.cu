@@ -15,13 +15,13 @@ struct WS {
   uint8_t* hist;
   WqScratch wq;
   float *fa, *fb;
-  int *ia, *ib;
+  int *ia, *ib, *ic;
   uint32_t* st[5];
 };
 __host__ __device__ inline size_t ws_bytes(const GameP& P, int cellsP) {
   size_t n = cellsP + (size_t)(P.hist_len ? 8 * cellsP : 0);
   n += 3 * (size_t)cellsP * 4;                 // label, libcnt, gsize
-  n += 9 * (size_t)((P.A + 2 + 3) & ~3) * 4;   // fa fb ia ib st[5]
+  n += 10 * (size_t)((P.A + 2 + 3) & ~3) * 4;  // fa fb ia ib ic st[5]
   return (n + 15) & ~(size_t)15;
 }
 __device__ inline WS make_ws(const GameP& P, int cellsP, uint8_t* base) {
@@ -36,6 +36,7 @@ __device__ inline WS make_ws(const GameP& P, int cellsP, uint8_t* base) {
   w.fb = (float*)base; base += AP * 4;
   w.ia = (int*)base; base += AP * 4;
   w.ib = (int*)base; base += AP * 4;
+  w.ic = (int*)base; base += AP * 4;
   for (int i = 0; i < 5; i++) { w.st[i] = (uint32_t*)base; base += AP * 4; }
   return w;
 }
@@ -181,7 +182,8 @@ __global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __re
   if (P.hist_len) for (int i = lane; i < 8 * E.cellsP; i += 32) E.hist[(size_t)g * 8 * E.cellsP + i] = 0;
   for (int t = 0; t < E.T; t++) {
     int* ti = E.ti + ((size_t)g * E.T + t) * TI_COUNT;
-    if (lane < TI_COUNT) ti[lane] = lane == TI_ROOT ? -1 : 0;
+    if (lane < TI_COUNT)
+      ti[lane] = lane == TI_ROOT ? -1 : (lane == TI_RNG_LO ? (int)(unsigned)(E.tree_seed & 0xffffffffu) : (lane == TI_RNG_HI ? (int)(unsigned)(E.tree_seed >> 32) : 0));
   }
   if (lane < WV_COUNT) E.wv[(size_t)g * WV_COUNT + lane] = 0;
   __syncwarp();
@@ -673,6 +675,50 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
       w.ia[i] = rank;
     }
     __syncwarp();
+    if (P.random_count > 0 && (P.kind == KIND_C4 ? 1 : gi[GI_MOVE_NUMBER]) < P.random_count) {
+      // randomizeChildren (tree.go:212-247) on the sorted list: temperature sample, then the reference's
+      // swap loop.  Sequential by construction (cumulative fp32 sums, one RNG draw): one lane.
+      for (int i = lane; i < nc; i += 32) w.ib[w.ia[i]] = i;  // sorted position -> original child
+      __syncwarp();
+      if (lane == 0) {
+        for (int p = 0; p < nc; p++) w.ic[p] = p;  // content (sorted index) at each list position
+        float accum = 0.0f, norm = 0.0f;
+        int nacc = 0;
+        bool abort = false;
+        for (int p = 0; p < nc; p++) {
+          const uint32_t visits = w.st[0][w.ib[p]];
+          if (norm == 0.0f) {
+            norm = __uint2float_rn(visits);
+            if (visits <= P.random_min_visits) { abort = true; break; }
+          }
+          if (visits > P.random_min_visits) {
+            // math32.Pow = float32(math.Pow(float64(x), float64(y)))
+            const float x = __fdiv_rn(__uint2float_rn(visits), norm), y = __fdiv_rn(1.0f, P.random_temperature);
+            accum = __fadd_rn(accum, (float)pow((double)x, (double)y));
+            w.fb[nacc++] = accum;
+          }
+        }
+        if (!abort) {
+          unsigned long long rs = ((unsigned long long)(unsigned)ti[TI_RNG_HI] << 32) | (unsigned)ti[TI_RNG_LO];
+          unsigned long long z = (rs += 0x9E3779B97F4A7C15ull);
+          z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+          z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+          z = z ^ (z >> 31);
+          ti[TI_RNG_LO] = (int)(unsigned)(rs & 0xffffffffu); ti[TI_RNG_HI] = (int)(unsigned)(rs >> 32);
+          const float rnd = __fmul_rn((float)(z >> 40) * (1.0f / 16777216.0f), accum);
+          int index = 0;
+          for (int i = 0; i < nacc; i++) if (rnd < w.fb[i]) { index = i; break; }
+          if (index != 0)
+            for (int i = 0; i < nc - index; i++) { int t0 = w.ic[i]; w.ic[i] = w.ic[i + index]; w.ic[i + index] = t0; }
+        }
+        for (int p = 0; p < nc; p++) w.ib[w.ic[p]] = p;  // sorted index -> final position (reuses ib)
+      }
+      __syncwarp();
+      for (int i = lane; i < nc; i += 32) w.ic[i] = w.ib[w.ia[i]];
+      __syncwarp();
+      for (int i = lane; i < nc; i += 32) w.ia[i] = w.ic[i];
+      __syncwarp();
+    }
     for (int i = lane; i < nc; i += 32) {  // the sort is in place in the reference (children slice aliases)
       size_t ci = tb + first + w.ia[i];
       E.N[ci] = w.st[0][i]; E.W[ci] = __uint_as_float(w.st[1][i]); E.Pr[ci] = __uint_as_float(w.st[2][i]);

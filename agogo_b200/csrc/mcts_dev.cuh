@@ -16,7 +16,7 @@
 
 enum { GI_TO_MOVE, GI_MOVE_NUMBER, GI_PASSES, GI_ACTIVE, GI_WINNER, GI_ARENA_PASS, GI_A_PLAYER, GI_CUR_AGENT,
        GI_N_MOVES, GI_ZHASH, GI_N_EX, GI_C4_PASS, GI_N_HMOVES, GI_LAST_MOVE, GI_COUNT = 16 };
-enum { TI_ROOT, TI_ALLOC, TI_PREV_VALID, TI_PREV_MN, TI_NPOL, TI_COUNT = 8 };
+enum { TI_ROOT, TI_ALLOC, TI_PREV_VALID, TI_PREV_MN, TI_NPOL, TI_RNG_LO, TI_RNG_HI, TI_COUNT = 8 };
 enum { WV_STATUS, WV_PATHLEN, WV_TO_MOVE, WV_MOVE_NUMBER, WV_PASSES, WV_SLOT, WV_AGENT, WV_FLAGS, WV_TREE,
        WV_PLAYER, WV_HASH, WV_COUNT = 16 };
 enum { ST_IDLE = 0, ST_LEAF = 1, ST_DONE = 2 };
@@ -71,5 +71,6 @@ struct EngineDev {
   unsigned long long* counters;  // [CNT_COUNT]
   int32_t* n_active;      // [1]
   int cellsP, T, Lmax, G;
+  unsigned long long tree_seed;  // MCTS.rand seed (tree.go:84), injected
   InfererDev inf[2];
 };

@@ -159,7 +159,8 @@ struct MCTS {
         if (visits <= conf.RandomMinVisits) return;
       }
       if (visits > conf.RandomMinVisits) {
-        accum += powf((float)visits / norm, 1 / conf.RandomTemperature);
+        // math32.Pow(x, y) = float32(math.Pow(float64(x), float64(y)))
+        accum += (float)std::pow((double)((float)visits / norm), (double)(1 / conf.RandomTemperature));
         accumVector.push_back(accum);
       }
     }

@@ -481,3 +481,20 @@ def test_parity_pass_preferences(oracle, engine_lib, kind, m, n, k, dumb, pref):
     for e in (eo, eg):
         e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
     H.assert_same_run(H.play_and_collect(eo, 6), H.play_and_collect(eg, 6), "pass-pref")
+
+
+@pytest.mark.parametrize("kind,m,n,k,temp,minv", [(K.GAME_MNK, 3, 3, 3, 1.0, 0), (K.GAME_C4, 6, 7, 4, 0.5, 1), (K.GAME_MNK, 5, 5, 4, 2.0, 1)])
+def test_parity_temperature_sampling(oracle, engine_lib, kind, m, n, k, temp, minv):
+    """RandomCount > 0: randomizeChildren (tree.go:212-247) — (visits/maxVisits)^(1/T) sampling and the
+    reference's swap loop, with the injected tree RNG."""
+    A = n if kind == K.GAME_C4 else m * n
+    def desc():
+        d = K.make_desc(kind, m, n, k, sims=24, n_games=8, seed=23, max_moves=30, nn=H.tiny_nn(m, n, A + 1))
+        d.mcts.random_count, d.mcts.random_temperature, d.mcts.random_min_visits = 6, temp, minv
+        return d
+    eo, eg = oracle.create(desc()), engine_lib.create(desc())
+    for e in (eo, eg):
+        e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    a, b = H.play_and_collect(eo, 8), H.play_and_collect(eg, 8)
+    H.assert_same_run(a, b, "temperature")
+    assert len({tuple(r["moves"][:4]) for r in a["records"]}) >= 1
