@@ -64,7 +64,7 @@ SYMBOLS = [
     "az_arena_step", "az_arena_finish", "az_search_begin", "az_search_run", "az_search_end", "az_game_record",
     "az_game_state", "az_examples_count", "az_examples_read", "az_examples_clear", "az_tree_dump", "az_rules_apply",
     "az_rules_status", "az_train", "az_comm_unique_id", "az_comm_init", "az_counters_get", "az_counters_reset",
-    "az_build_info", "az_profile", "az_train_grads", "az_train_apply", "az_search",
+    "az_build_info", "az_profile", "az_train_grads", "az_train_apply", "az_search", "az_comm_bench",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -331,6 +331,11 @@ class Engine:
         out = (C.c_double * 8)()
         self._ck(self.lib.dll.az_profile(self.h, int(enable), out))
         return dict(conv_ms=out[0], conv_launches=out[1], forward_ms=out[2], forward_calls=out[3])
+
+    def comm_bench(self, net=1, iters=10):
+        ms, nbytes = C.c_double(), C.c_double()
+        self._ck(self.lib.dll.az_comm_bench(self.h, net, iters, C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value
 
     def counters(self):
         c = Counters()

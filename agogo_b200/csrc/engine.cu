@@ -1027,6 +1027,33 @@ int az_comm_init(az_engine* e, int32_t rank, int32_t world, const uint8_t id[128
   return AZ_OK;
 }
 
+int az_comm_bench(az_engine* e, int32_t net, int32_t iters, double* ms_out, double* bytes_out) {
+  if (net < 0 || net > 1 || iters < 1) return AZ_ERR_INVALID;
+  if (!e->comm) { e->err = "az_comm_bench: no communicator"; return AZ_ERR_STATE; }
+  GUARD_BEGIN
+  CUDA_CHECK(cudaSetDevice(e->device));
+  ensure_train(e);
+  cudaEvent_t a, b;
+  CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+  auto step = [&]() {
+    if (e->p2p) train_allreduce_sgd_p2p(e->d_peer_grads, e->d_peer_params[net], e->d_peer_flags, e->my_flags, e->rank, e->world,
+                                        e->L.total, 0.0f, ++e->epoch, e->done_counter, e->num_sms, e->stream, &e->launches);
+    else { nccl_allreduce_sum(e, train_ws_grads(e->train), e->L.total); train_sgd(e->train, e->L, e->net_params[net], 0.0f, 1.0f, e->stream, &e->launches); }
+  };
+  for (int i = 0; i < 2; i++) step();  // warm-up
+  CUDA_CHECK(cudaEventRecord(a, e->stream));
+  for (int i = 0; i < iters; i++) step();
+  CUDA_CHECK(cudaEventRecord(b, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (ms_out) *ms_out = ms / iters;
+  if (bytes_out) *bytes_out = 2.0 * (e->world - 1) / e->world * (double)e->L.total * 4.0;
+  GUARD_END(e)
+  return AZ_OK;
+}
+
 int az_profile(az_engine* e, int32_t enable, double out[8]) {
   GUARD_BEGIN
   CUDA_CHECK(cudaSetDevice(e->device));

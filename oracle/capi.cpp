@@ -446,6 +446,7 @@ int az_train_apply(az_engine* e, int32_t net, const float* grads, float lr) {
 int az_comm_unique_id(uint8_t id[128]) { memset(id, 0, 128); return AZ_ERR_UNSUPPORTED; }
 int az_comm_init(az_engine*, int32_t, int32_t, const uint8_t*) { return AZ_ERR_UNSUPPORTED; }
 
+int az_comm_bench(az_engine*, int32_t, int32_t, double*, double*) { return AZ_ERR_UNSUPPORTED; }
 int az_profile(az_engine*, int32_t, double out[8]) { if (out) for (int i = 0; i < 8; i++) out[i] = 0; return AZ_OK; }
 
 int az_counters_get(const az_engine* e, az_counters* out) {
