@@ -383,15 +383,32 @@ __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float
   const size_t lo = (size_t)rank * shard;
   const size_t hi = lo + shard < n ? lo + shard : ((n + 3) & ~(size_t)3);  // buffers are padded to a multiple of 4
   float* mine = peer_params[rank];
-  for (size_t i = lo + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < hi; i += (size_t)gridDim.x * blockDim.x * 4) {
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < world; r++) {
-      const float4 v = *reinterpret_cast<const float4*>(peer_grads[r] + i);
-      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+  // peer loads cost ~2 us each: keep U x world 16-byte loads in flight per thread before touching the data
+  constexpr int U = 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i0 = lo + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < hi; i0 += stride * U) {
+    float4 g[U], p[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * stride;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < hi) {
+        p[u] = *reinterpret_cast<const float4*>(mine + i);
+        for (int r = 0; r < world; r++) {
+          const float4 v = *reinterpret_cast<const float4*>(peer_grads[r] + i);
+          g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+        }
+      }
     }
-    float4 p = *reinterpret_cast<const float4*>(mine + i);
-    p.x -= lr_over_world * g.x; p.y -= lr_over_world * g.y; p.z -= lr_over_world * g.z; p.w -= lr_over_world * g.w;
-    for (int r = 0; r < world; r++) *reinterpret_cast<float4*>(peer_params[r] + i) = p;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * stride;
+      if (i < hi) {
+        float4 q = p[u];
+        q.x -= lr_over_world * g[u].x; q.y -= lr_over_world * g[u].y; q.z -= lr_over_world * g[u].z; q.w -= lr_over_world * g[u].w;
+        for (int r = 0; r < world; r++) *reinterpret_cast<float4*>(peer_params[r] + i) = q;
+      }
+    }
   }
   // (B) the last block of this rank publishes "slice written" and waits for everybody's
   __threadfence_system();
@@ -411,7 +428,7 @@ void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params
                              int rank, int world, size_t n, float lr, int epoch, unsigned int* done_counter, int num_sms,
                              cudaStream_t st, unsigned long long* launches) {
   const size_t shard = (((n + world - 1) / world) + 3) & ~(size_t)3;
-  int blocks = (int)std::min<size_t>((shard / 4 + 255) / 256, (size_t)num_sms * 2);
+  int blocks = (int)std::min<size_t>((shard / 4 + 255) / 256, (size_t)num_sms * 8);
   if (blocks < 1) blocks = 1;
   k_allreduce_sgd_p2p<<<blocks, 256, 0, st>>>(peer_grads, peer_params, peer_flags, my_flags, rank, world, n, lr / (float)world, epoch,
                                              done_counter);
