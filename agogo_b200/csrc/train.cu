@@ -365,9 +365,11 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
 // w -= lr * g / world to its slice and writes the updated slice into every rank's parameter buffer.
 // Cross-GPU ordering uses epoch flags in peer memory: (A) "my gradients are complete" before anyone
 // reads them, (B) "my slice is written everywhere" before anyone's next kernel may start.
+template <int WORLD>  // compile-time world size (0 = runtime): lets every peer load of a thread be issued up front
 __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float* const* __restrict__ peer_params,
-                                    int* const* __restrict__ peer_flags, int* my_flags, int rank, int world, size_t n,
+                                    int* const* __restrict__ peer_flags, int* my_flags, int rank, int world_rt, size_t n,
                                     float lr_over_world, int epoch, unsigned int* done_counter) {
+  const int world = WORLD ? WORLD : world_rt;
   __shared__ int s_last;
   // (A) publish "gradients ready", then wait for everybody's
   if (blockIdx.x == 0 && threadIdx.x < world) {
@@ -383,6 +385,10 @@ __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float
   const size_t lo = (size_t)rank * shard;
   const size_t hi = lo + shard < n ? lo + shard : ((n + 3) & ~(size_t)3);  // buffers are padded to a multiple of 4
   float* mine = peer_params[rank];
+  float* pg[WORLD ? WORLD : 16];
+  float* pp[WORLD ? WORLD : 16];
+#pragma unroll
+  for (int r = 0; r < (WORLD ? WORLD : 16); r++) { pg[r] = r < world ? peer_grads[r] : nullptr; pp[r] = r < world ? peer_params[r] : nullptr; }
   // peer loads cost ~2 us each: keep U x world 16-byte loads in flight per thread before touching the data
   constexpr int U = 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -394,9 +400,12 @@ __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float
       g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < hi) {
         p[u] = *reinterpret_cast<const float4*>(mine + i);
-        for (int r = 0; r < world; r++) {
-          const float4 v = *reinterpret_cast<const float4*>(peer_grads[r] + i);
-          g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+#pragma unroll
+        for (int r = 0; r < (WORLD ? WORLD : 16); r++) {
+          if (r < world) {
+            const float4 v = *reinterpret_cast<const float4*>(pg[r] + i);
+            g[u].x += v.x; g[u].y += v.y; g[u].z += v.z; g[u].w += v.w;
+          }
         }
       }
     }
@@ -406,7 +415,9 @@ __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float
       if (i < hi) {
         float4 q = p[u];
         q.x -= lr_over_world * g[u].x; q.y -= lr_over_world * g[u].y; q.z -= lr_over_world * g[u].z; q.w -= lr_over_world * g[u].w;
-        for (int r = 0; r < world; r++) *reinterpret_cast<float4*>(peer_params[r] + i) = q;
+#pragma unroll
+        for (int r = 0; r < (WORLD ? WORLD : 16); r++)
+          if (r < world) *reinterpret_cast<float4*>(pp[r] + i) = q;
       }
     }
   }
@@ -430,8 +441,14 @@ void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params
   const size_t shard = (((n + world - 1) / world) + 3) & ~(size_t)3;
   int blocks = (int)std::min<size_t>((shard / 4 + 255) / 256, (size_t)num_sms * 8);
   if (blocks < 1) blocks = 1;
-  k_allreduce_sgd_p2p<<<blocks, 256, 0, st>>>(peer_grads, peer_params, peer_flags, my_flags, rank, world, n, lr / (float)world, epoch,
-                                             done_counter);
+  if (world > 16) throw std::runtime_error("k_allreduce_sgd_p2p: world > 16");
+#define AZ_LAUNCH_K8(W) k_allreduce_sgd_p2p<W><<<blocks, 256, 0, st>>>(peer_grads, peer_params, peer_flags, my_flags, rank, world, n, \
+                                                                       lr / (float)world, epoch, done_counter)
+  if (world == 2) AZ_LAUNCH_K8(2);
+  else if (world == 4) AZ_LAUNCH_K8(4);
+  else if (world == 8) AZ_LAUNCH_K8(8);
+  else AZ_LAUNCH_K8(0);
+#undef AZ_LAUNCH_K8
   if (launches) (*launches)++;
 }
 
