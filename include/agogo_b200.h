@@ -217,7 +217,8 @@ int az_comm_unique_id(uint8_t id[128]);
 int az_comm_init(az_engine* e, int32_t rank, int32_t world, const uint8_t id[128]);
 /* Times the gradient exchange + solver step alone (lr = 0: parameters unchanged), `iters` back-to-back
  * launches with CUDA events on the engine's stream; every rank must call it.  ms_out = average per step,
- * bytes_out = bytes this rank moves over NVLink per step (2*(R-1)/R*|theta|*4).  For the K8 roofline. */
+ * bytes_out = bytes entering (= leaving) this rank over NVLink per step: (R-1)/R*|theta|*4 of gradient
+ * reads plus the same amount of parameter writes = 2*(R-1)/R*|theta|*4 PER DIRECTION.  For the K8 roofline. */
 int az_comm_bench(az_engine* e, int32_t net, int32_t iters, double* ms_out, double* bytes_out);
 
 /* ---- counters (per engine, since create or az_counters_reset) -------------------------------- */

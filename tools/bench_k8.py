@@ -37,9 +37,9 @@ ms, nbytes = e.comm_bench(1, args.iters)
 out = torch.tensor([ms], dtype=torch.float64).cuda()
 dist.all_reduce(out, op=dist.ReduceOp.MAX)
 if rank == 0:
-    gbs = nbytes / 2 / (out.item() / 1e3) / 1e9  # per direction
+    gbs = nbytes / (out.item() / 1e3) / 1e9  # nbytes is already per direction (gradient reads in + parameter writes in)
     print(json.dumps({"kernel": "k_allreduce_sgd_p2p" if args.collective == "p2p" else "ncclAllReduce+k_sgd", "world": world,
-                      "params": e.param_count()[1], "ms": out.item(), "nvlink_bytes_per_rank": nbytes,
+                      "params": e.param_count()[1], "ms": out.item(), "nvlink_bytes_per_rank_per_direction": nbytes,
                       "gbs_per_direction": gbs, "peak_gbs_per_direction_measured": 770.0, "frac": gbs / 770.0}))
 dist.barrier()
 dist.destroy_process_group()
