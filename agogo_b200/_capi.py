@@ -330,7 +330,7 @@ class Engine:
     def profile(self, enable):
         out = (C.c_double * 8)()
         self._ck(self.lib.dll.az_profile(self.h, int(enable), out))
-        return dict(conv_ms=out[0], conv_launches=out[1], forward_ms=out[2], forward_calls=out[3])
+        return dict(conv_ms=out[0], conv_launches=out[1], forward_ms=out[2], forward_calls=out[3], region_ms=out[4])
 
     def comm_bench(self, net=1, iters=10):
         ms, nbytes = C.c_double(), C.c_double()

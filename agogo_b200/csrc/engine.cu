@@ -88,6 +88,7 @@ struct az_engine {
   uint64_t wave_graph_version = 0, cfg_version = 1;
   unsigned long long wave_graph_launches = 0;
   bool graphs_enabled = true, profiling = false;
+  cudaEvent_t prof_start = nullptr, prof_stop = nullptr;  // region timing between az_profile(1) and az_profile(0)
   TrainWS train;
   void* comm = nullptr;  // ncclComm_t (bootstrap of the peer-memory path; plain all-reduce as the checked alternative)
   int rank = 0, world = 1;
@@ -178,6 +179,7 @@ void az_engine_destroy(az_engine* e) {
   for (int a = 0; a < 2; a++) { tc_tower_free(e->tc[a]); }
   train_ws_free(e->train);
   if (e->wave_graph) cudaGraphExecDestroy(e->wave_graph);
+  if (e->prof_start) { cudaEventDestroy(e->prof_start); cudaEventDestroy(e->prof_stop); }
   for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
   if (e->comm) { try { nccl_api().CommDestroy((ncclComm_t)e->comm); } catch (...) {} }
   fp32_scratch_free(e->fp32);
@@ -1057,10 +1059,19 @@ int az_comm_bench(az_engine* e, int32_t net, int32_t iters, double* ms_out, doub
 int az_profile(az_engine* e, int32_t enable, double out[8]) {
   GUARD_BEGIN
   CUDA_CHECK(cudaSetDevice(e->device));
+  if (!e->prof_start) { CUDA_CHECK(cudaEventCreate(&e->prof_start)); CUDA_CHECK(cudaEventCreate(&e->prof_stop)); }
   if (out) {
     for (int i = 0; i < 8; i++) out[i] = 0;
     if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile_collect(e->tc[a], e->stream, &out[0], &out[1], &out[2], &out[3]);
+    if (e->profiling && !enable) {  // whole region on the engine's stream, device-timed
+      CUDA_CHECK(cudaEventRecord(e->prof_stop, e->stream));
+      CUDA_CHECK(cudaEventSynchronize(e->prof_stop));
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e->prof_start, e->prof_stop));
+      out[4] = ms;
+    }
   }
+  if (enable) { CUDA_CHECK(cudaStreamSynchronize(e->stream)); CUDA_CHECK(cudaEventRecord(e->prof_start, e->stream)); }
   if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile(e->tc[a], enable != 0);
   e->profiling = enable != 0;  // event records inside the wave: replay the plain launch sequence instead of the graph
   GUARD_END(e)

@@ -233,19 +233,28 @@ def main():
 
     for _ in range(warmup):
         one_step()
-    e.counters_reset()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e.profile(True)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_step()
-    prof = e.profile(False)  # synchronises the engine stream, collects event timings
-    barrier()
-    dt = time.perf_counter() - t0
-    sampler.stop_flag = True
-    cnt = e.counters()
+
+    def timed_region():
+        e.counters_reset()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e.profile(True)                      # records the start event on the engine's stream
+        for _ in range(args.steps):
+            one_step()
+        prof = e.profile(False)              # stop event + synchronise: device time of exactly `steps` steps
+        barrier()
+        sampler.stop_flag = True
+        return prof, sampler.summary(), e.counters()
+
+    prof, clocks, cnt = timed_region()
+    bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if bad & set(clocks.get("reasons", [])) and world == 1:  # rejected: re-measure once (timing rules)
+        clocks["rejected_first_run"] = True
+        prof, clocks2, cnt = timed_region()
+        clocks2["rejected_first_run"] = True
+        clocks = clocks2
+    dt = prof["region_ms"] / 1e3
     sims = cnt["sims"]
     evals = cnt["evals"]
     tot = [dt, float(sims), float(evals), float(cnt["kernel_launches"])]
@@ -336,7 +345,7 @@ def main():
             "data": "synthetic", "config": config, "moves_per_sec": value / (w["sims"] + 1),
             "evals_per_sec": tot_evals / dt_max, "tflops_algorithmic": tot_evals / dt_max * fpe / 1e12,
             "e2e": e2e, "gpu_launches": int(tot_launch), "roofline": roofline, "tree": tree, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary()}
+            "clocks": clocks, "timing": "CUDA events on the engine's stream around exactly `steps` steps, barrier+synchronize both sides, max over ranks"}
     print(json.dumps(line))
     return 0
 

@@ -234,7 +234,8 @@ int az_counters_reset(az_engine* e);
 /* Kernel timing for bench.py's roofline line: CUDA events on the engine's own stream around every
  * launch of the dominant kernel (the fused 3x3 conv of a residual block).  enable=1 starts a fresh
  * measurement, enable=0 stops; out (may be NULL) receives {conv_ms_total, conv_launches,
- * forward_ms_total, forward_calls, 0...} accumulated since the last enable=1. */
+ * forward_ms_total, forward_calls, region_ms, 0...} accumulated since the last enable=1; region_ms is the device
+ * time between the enable=1 and the enable=0 call on the engine's stream. */
 int az_profile(az_engine* e, int32_t enable, double out[8]);
 
 const char* az_build_info(void); /* "agogo_b200 <ver> sm_100a ..." or "oracle ..." */
