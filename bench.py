@@ -200,6 +200,7 @@ def main():
 
     dist = torch = None
     if world > 1:  # plumbing only: process group for barrier / max-over-ranks
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
