@@ -324,7 +324,7 @@ class AZ:
         return Xs, Pi, V, batches
 
     # ---- AZ.Learn (agogo.go:100-172) ----------------------------------------------------------
-    def Learn(self, iters, episodes, nniters, arenaGames):
+    def Learn(self, iters, episodes, nniters, arenaGames, on_epoch=None):
         e = self.engine
         for self.epoch in range(iters):
             ep = self.epoch
@@ -350,6 +350,8 @@ class AZ:
             e.net_init(1, derive_seed(self.seed, 200 + ep))  # newB (arena.go:205-224)
             self.log.append(dict(a=(float(aw), float(al), float(ad)), b=(float(bw), float(bl), float(bd)), n_examples=len(ex), batches=batches, promoted=promoted,
                                  first_cost=float(costs[0]), last_cost=float(costs[-1])))
+            if on_epoch is not None:
+                on_epoch(ep, self.log[-1])
         return None
 
     # ---- checkpoint: Model()-ordered flat payload (the gob container stays on the Go side) ---------
