@@ -200,6 +200,8 @@ def main():
 
     dist = torch = None
     if world > 1:  # plumbing only: process group for barrier / max-over-ranks
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the VERSION banner goes to stdout; stdout carries exactly one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         import torch
         import torch.distributed as dist

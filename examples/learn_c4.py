@@ -32,6 +32,8 @@ rank = int(os.environ.get("RANK", "0"))
 lrank = int(os.environ.get("LOCAL_RANK", "0"))
 dist = None
 if world > 1:
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
