@@ -344,7 +344,9 @@ def main():
                     "pointer chase, not bandwidth-bound"}
     line = {"metric": "mcts_sims_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split on tcgen05, fp32 accumulate; outputs within 1e-4 of fp32)",
+            "vs_baseline": None, "dtype": "f32",
+            "precision": "fp32 semantics on fp16 tensor cores: hi/lo operand split, 3 tcgen05 passes, fp32 TMEM accumulate; "
+                         "policy/value within 1.4e-5 of the fp32 oracle (tolerance 1e-4)",
             "data": "synthetic", "config": config, "moves_per_sec": value / (w["sims"] + 1),
             "evals_per_sec": tot_evals / dt_max, "tflops_algorithmic": tot_evals / dt_max * fpe / 1e12,
             "e2e": e2e, "gpu_launches": int(tot_launch), "roofline": roofline, "tree": tree, "cpu_baseline": cpu_baseline,
