@@ -498,3 +498,23 @@ def test_parity_temperature_sampling(oracle, engine_lib, kind, m, n, k, temp, mi
     a, b = H.play_and_collect(eo, 8), H.play_and_collect(eg, 8)
     H.assert_same_run(a, b, "temperature")
     assert len({tuple(r["moves"][:4]) for r in a["records"]}) >= 1
+
+
+def test_arena_play_chunking_and_single_slot(oracle, engine_lib):
+    """az_arena_play with more games than device slots runs them in chunks that continue the same coin
+    stream; one-slot engines work: records, examples (game order) and statistics equal an all-at-once run."""
+    def desc(g):
+        return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=15, nn=H.tiny_nn(3, 3, 10), n_games=g, seed=19)
+    runs = []
+    for lib, slots in ((oracle, 16), (engine_lib, 4), (engine_lib, 1)):
+        e = lib.create(desc(slots))
+        e.set_inferer(0, K.INF_DUMMY, 0); e.set_inferer(1, K.INF_DUMMY, 0)
+        e.arena_play(10, True)
+        recs = [e.game_record(g) for g in range(10)]
+        runs.append((recs, e.examples(clear=True), e.stats(0), e.stats(1)))
+    for other in runs[1:]:
+        for ra, rb in zip(runs[0][0], other[0]):
+            assert list(ra["moves"]) == list(rb["moves"]) and ra["winner"] == rb["winner"] and ra["a_player"] == rb["a_player"]
+        for xa, xb in zip(runs[0][1], other[1]):
+            assert xa.shape == xb.shape and (xa.view(np.uint32) == xb.view(np.uint32)).all()
+        assert runs[0][2:] == other[2:]
