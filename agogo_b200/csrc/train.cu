@@ -2,9 +2,9 @@
 // One step = forward in BatchNorm train mode on a batch of exactly BatchSize samples, the
 // reference's loss (dual.go:105-126: "xent" on raw logits, ermahagerdmonards.go:106-147, + MSE on
 // the pre-tanh value), reverse-mode gradients for every Model() tensor (batch-shaped BN affines
-// and biases included), vanilla SGD (meta.go:20,39).  Correctness-first kernels (one thread per
-// output, block reductions, no atomics => deterministic); the tensor-core version of the conv
-// passes is the next optimisation row.  Semantics are pinned against oracle/dual.hpp
+// and biases included), vanilla SGD (meta.go:20,39).  fp32 throughout: shared-memory tiled implicit
+// GEMMs for the three conv passes (4x4 register tiles), block reductions for BatchNorm, no atomics
+// => deterministic; the tensor-core version of the conv passes is the next optimisation row.  Semantics are pinned against oracle/dual.hpp
 // (dual_train_step), whose backward is itself pinned by a finite-difference check.
 #include <algorithm>
 #include <stdexcept>
@@ -15,27 +15,141 @@
 
 namespace {
 
-__global__ void k_conv_fwd(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z, int B, int Ci,
-                           int Co, int H, int W, int k) {
-  const int HW = H * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * Co * HW) return;
-  const int hw = (int)(idx % HW), co = (int)((idx / HW) % Co), b = (int)(idx / ((size_t)HW * Co));
-  const int y = hw / W, xx = hw - y * W, pad = (k - 1) / 2;
-  const float* xb = x + (size_t)b * Ci * HW;
-  const float* wk = w + (size_t)co * Ci * k * k;
-  float acc = 0.0f;
-  for (int ci = 0; ci < Ci; ci++)
-    for (int ky = 0; ky < k; ky++) {
-      int yy = y + ky - pad;
-      if (yy < 0 || yy >= H) continue;
-      for (int kx = 0; kx < k; kx++) {
-        int xc = xx + kx - pad;
-        if (xc < 0 || xc >= W) continue;
-        acc += wk[(ci * k + ky) * k + kx] * xb[(size_t)ci * HW + yy * W + xc];
-      }
+// ---- shared-memory tiled fp32 convolutions (used for every layer of the training pass) -------------
+// Implicit GEMM  out[co, p] (+)= sum_q Wm[co, q] * im2col(x)[q, p],  q = (ci, ky, kx), p = (b, y, x):
+// 64 output channels x 64 positions per block, 16x16 threads with a 4x4 register tile each, the
+// reduction dimension streamed through shared memory in chunks of 8 input channels.
+constexpr int TT = 64;   // tile edge (channels / positions)
+constexpr int CKC = 8;   // input channels per chunk
+template <bool ACC>
+__global__ void __launch_bounds__(256) k_conv_fwd_tiled(const float* __restrict__ x, const float* __restrict__ w, float* out,
+                                                        int B, int Ci, int Co, int H, int W, int k) {
+  __shared__ float sW[CKC * 9][TT + 1];  // [q][co]
+  __shared__ float sX[CKC * 9][TT];      // [q][p]
+  const int HW = H * W, kk = k * k, pad = (k - 1) / 2;
+  const int P = B * HW;
+  const int p0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+  for (int ci0 = 0; ci0 < Ci; ci0 += CKC) {
+    const int nq = min(CKC, Ci - ci0) * kk;
+    for (int e = threadIdx.x; e < nq * TT; e += 256) {
+      const int q = e / TT, c = e - q * TT;
+      const int ci = ci0 + q / kk, t = q - (q / kk) * kk;
+      sW[q][c] = (c0 + c < Co) ? w[((size_t)(c0 + c) * Ci + ci) * kk + t] : 0.0f;
     }
-  z[idx] = acc;
+    for (int e = threadIdx.x; e < nq * TT; e += 256) {
+      const int q = e / TT, pp = e - q * TT;
+      const int ci = ci0 + q / kk, t = q - (q / kk) * kk;
+      const int p = p0 + pp;
+      float v = 0.0f;
+      if (p < P) {
+        const int b = p / HW, hw = p - b * HW;
+        const int yy = hw / W + t / k - pad, xx = hw % W + t % k - pad;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((size_t)b * Ci + ci) * HW + yy * W + xx];
+      }
+      sX[q][pp] = v;
+    }
+    __syncthreads();
+    for (int q = 0; q < nq; q++) {
+      float wv[4], xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) wv[i] = sW[q][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) xv[j] = sX[q][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int co = c0 + ty * 4 + i;
+    if (co >= Co) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int p = p0 + tx * 4 + j;
+      if (p >= P) continue;
+      const int b = p / HW, hw = p - b * HW;
+      float* o = out + ((size_t)b * Co + co) * HW + hw;
+      if (ACC) *o += acc[i][j]; else *o = acc[i][j];
+    }
+  }
+}
+// wt[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx]: backward-data is the forward kernel on the mirrored, transposed filter
+__global__ void k_flip_filter(const float* __restrict__ w, float* wt, int Ci, int Co, int k) {
+  const int kk = k * k;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ci * Co * kk) return;
+  const int t = idx % kk, co = (idx / kk) % Co, ci = idx / (kk * Co);
+  wt[idx] = w[((size_t)co * Ci + ci) * kk + (kk - 1 - t)];
+}
+// dW[co, (ci,t)] = sum_p dz[co, p] * x[ci, p + shift(t)]: 64 x 64 outputs per block, positions streamed in chunks of 32
+__global__ void __launch_bounds__(256) k_conv_bwd_w_tiled(const float* __restrict__ x, const float* __restrict__ dz, float* dW,
+                                                          int B, int Ci, int Co, int H, int W, int k) {
+  constexpr int PK = 32;
+  __shared__ float sD[PK][TT + 1];  // [p][co]
+  __shared__ float sXs[PK][TT + 1]; // [p][(ci,t)]
+  const int HW = H * W, kk = k * k, pad = (k - 1) / 2;
+  const int P = B * HW, Q = Ci * kk;
+  const int q0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+  for (int pb = 0; pb < P; pb += PK) {
+    for (int e = threadIdx.x; e < PK * TT; e += 256) {
+      const int c = e / PK, pp = e - c * PK;  // consecutive threads walk positions: coalesced in hw
+      const int p = pb + pp;
+      float v = 0.0f;
+      if (p < P && c0 + c < Co) { const int b = p / HW, hw = p - b * HW; v = dz[((size_t)b * Co + c0 + c) * HW + hw]; }
+      sD[pp][c] = v;
+    }
+    for (int e = threadIdx.x; e < PK * TT; e += 256) {
+      const int qq = e / PK, pp = e - qq * PK;
+      const int q = q0 + qq, p = pb + pp;
+      float v = 0.0f;
+      if (p < P && q < Q) {
+        const int ci = q / kk, t = q - ci * kk;
+        const int b = p / HW, hw = p - b * HW;
+        const int yy = hw / W + t / k - pad, xx = hw % W + t % k - pad;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((size_t)b * Ci + ci) * HW + yy * W + xx];
+      }
+      sXs[pp][qq] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < PK; pp++) {
+      float dv[4], xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) dv[i] = sD[pp][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) xv[j] = sXs[pp][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int co = c0 + ty * 4 + i;
+    if (co >= Co) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int q = q0 + tx * 4 + j;
+      if (q < Q) dW[(size_t)co * Q + q] = acc[i][j];
+    }
+  }
 }
 
 __device__ inline float block_sum(float v, float* sh) {
@@ -173,50 +287,6 @@ __global__ void k_bn_bwd_apply(float* dxn, const float* __restrict__ xn, const f
     dxn[idx] = (dxn[idx] - m1 - xn[idx] * m2) / sd;
   }
 }
-// dW[co,ci,ky,kx] = sum_{b,y,x} x[b,ci,y+dy,x+dx] dz[b,co,y,x]; one block per (co,ci)
-__global__ void k_conv_bwd_w(const float* __restrict__ x, const float* __restrict__ dz, float* dW, int B, int Ci, int Co,
-                             int H, int W, int k) {
-  __shared__ float sh[32];
-  const int co = blockIdx.x / Ci, ci = blockIdx.x - co * Ci;
-  const int HW = H * W, pad = (k - 1) / 2, m = B * HW;
-  for (int t = 0; t < k * k; t++) {
-    const int ddy = t / k - pad, ddx = t % k - pad;
-    float acc = 0.0f;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      int b = i / HW, hw = i - b * HW;
-      int y = hw / W, xx = hw - y * W;
-      int yy = y + ddy, xc = xx + ddx;
-      if (yy < 0 || yy >= H || xc < 0 || xc >= W) continue;
-      acc += x[((size_t)b * Ci + ci) * HW + yy * W + xc] * dz[((size_t)b * Co + co) * HW + hw];
-    }
-    const float r = block_sum(acc, sh);
-    if (threadIdx.x == 0) dW[((size_t)co * Ci + ci) * k * k + t] = r;
-  }
-}
-// dx[b,ci,y,x] += sum_{co,ky,kx} w[co,ci,ky,kx] dz[b,co,y-dy,x-dx]
-__global__ void k_conv_bwd_in(const float* __restrict__ w, const float* __restrict__ dz, float* dx, int B, int Ci, int Co,
-                              int H, int W, int k) {
-  const int HW = H * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * Ci * HW) return;
-  const int hw = (int)(idx % HW), ci = (int)((idx / HW) % Ci), b = (int)(idx / ((size_t)HW * Ci));
-  const int y = hw / W, xx = hw - y * W, pad = (k - 1) / 2;
-  float acc = 0.0f;
-  for (int co = 0; co < Co; co++) {
-    const float* wk = w + ((size_t)co * Ci + ci) * k * k;
-    const float* dzb = dz + ((size_t)b * Co + co) * HW;
-    for (int ky = 0; ky < k; ky++) {
-      int yy = y - (ky - pad);
-      if (yy < 0 || yy >= H) continue;
-      for (int kx = 0; kx < k; kx++) {
-        int xc = xx - (kx - pad);
-        if (xc < 0 || xc >= W) continue;
-        acc += wk[ky * k + kx] * dzb[yy * W + xc];
-      }
-    }
-  }
-  dx[idx] += acc;
-}
 __global__ void k_sgd(float* p, const float* __restrict__ g, float lr, float gscale, size_t n) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) p[idx] = p[idx] - lr * (g[idx] * gscale);
@@ -236,6 +306,7 @@ struct TrainImpl {
   float *dph = nullptr, *dvh = nullptr, *dcur = nullptr, *dprev = nullptr, *tmp = nullptr, *dl = nullptr;
   float* cost = nullptr;
   float* grads = nullptr;
+  float* wflip = nullptr;  // mirrored/transposed filter of the unit being back-propagated
   std::vector<void*> allocs;
   float* alloc(size_t n) {
     float* p;
@@ -265,6 +336,7 @@ void train_ws_alloc(TrainWS& ws, const NetLayout& L) {
   T->dph = T->alloc(B * 2 * HW); T->dvh = T->alloc(B * HW);
   T->dcur = T->alloc(act); T->dprev = T->alloc(act); T->tmp = T->alloc(act); T->dl = T->alloc(act);
   T->cost = T->alloc(1);
+  { size_t mx = 1; for (const UnitH& u : L.units) mx = std::max(mx, (size_t)u.Ci * u.Co * u.k * u.k); T->wflip = T->alloc(mx); }
   T->grads = T->alloc(L.total + 4);  // +4: the fused collective moves float4s
   CUDA_CHECK(cudaMemset(T->grads, 0, (L.total + 4) * 4));
 }
@@ -294,7 +366,7 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   auto unit_fwd = [&](int ui, const float* x) {
     const UnitH& u = L.units[ui];
     size_t n = (size_t)B * u.Co * HW;
-    k_conv_fwd<<<nblk(n), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
+    k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
     k_bn_stats<<<u.Co, 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
     k_bn_apply<<<nblk(n), 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], Pp(u.gamma), Pp(u.beta), T->xn[ui], T->y[ui], n, u.Co, HW);
     nl += 3;
@@ -335,9 +407,13 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
     size_t n = (size_t)B * u.Co * HW;
     k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n);
     k_bn_bwd_apply<<<u.Co, 256, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
-    k_conv_bwd_w<<<u.Co * u.Ci, 256, 0, st>>>(x, T->tmp, Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
+    k_conv_bwd_w_tiled<<<dim3((u.Ci * u.k * u.k + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, T->tmp, Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
     nl += 3;
-    if (dx) { k_conv_bwd_in<<<nblk((size_t)B * u.Ci * HW), 256, 0, st>>>(Pp(u.filter), T->tmp, dx, B, u.Ci, u.Co, H, W, u.k); nl++; }
+    if (dx) {  // dx += conv(dz, mirrored transposed filter)
+      k_flip_filter<<<nblk((size_t)u.Ci * u.Co * u.k * u.k), 256, 0, st>>>(Pp(u.filter), T->wflip, u.Ci, u.Co, u.k);
+      k_conv_fwd_tiled<true><<<dim3((B * HW + TT - 1) / TT, (u.Ci + TT - 1) / TT), 256, 0, st>>>(T->tmp, T->wflip, dx, B, u.Co, u.Ci, H, W, u.k);
+      nl += 2;
+    }
   };
   CUDA_CHECK(cudaMemsetAsync(T->dcur, 0, act * 4, st));
   unit_bwd(pu, cur, T->dph, T->dcur);
