@@ -35,13 +35,12 @@
 namespace {
 
 constexpr int BM = 128;        // M tile (TMEM lanes)
-constexpr int BK = 64;         // K block: 64 fp16 = 128 B = one SWIZZLE_128B row
+// K block per pipeline stage: 64 fp16 = 128 B rows (SWIZZLE_128B) or 32 fp16 = 64 B rows (SWIZZLE_64B, twice the
+// stages in the same shared memory).  Template parameter BKT of the kernel; chosen at tower allocation.
 constexpr int NTHREADS = 192;  // 6 warps
-constexpr int A_TILE_BYTES = BM * BK * 2;
-
-__host__ __device__ constexpr int stage_bytes(int BN) { return 2 * A_TILE_BYTES + 2 * BN * BK * 2; }
-__host__ __device__ constexpr int num_stages(int BN) { return BN == 256 ? 2 : (BN == 128 ? 3 : 4); }
-__host__ __device__ constexpr int smem_bytes(int BN) { return num_stages(BN) * stage_bytes(BN) + 1024 + 256; }
+__host__ __device__ constexpr int stage_bytes(int BN, int BKT) { return 2 * BM * BKT * 2 + 2 * BN * BKT * 2; }
+__host__ __device__ constexpr int num_stages(int BN, int BKT) { return 196608 / stage_bytes(BN, BKT) > 8 ? 8 : 196608 / stage_bytes(BN, BKT); }
+__host__ __device__ constexpr int smem_bytes(int BN, int BKT) { return num_stages(BN, BKT) * stage_bytes(BN, BKT) + 1024 + 256; }
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -93,15 +92,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, SWIZZLE_128B operand descriptor: start>>4 | LBO (ignored for swizzled K-major) |
-// SBO = 1024 B (8 rows x 128 B) | version 1 (bits 46-47) | layout type 2 (bits 61-63)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+// K-major swizzled operand descriptor: start>>4 | LBO (ignored for swizzled K-major) | SBO = 8 rows x row bytes
+// (1024 B for SWIZZLE_128B, 512 B for SWIZZLE_64B) | version 1 (bits 46-47) | layout type (bits 61-63: 2 = 128B, 4 = 64B)
+template <int BKT>
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * BKT * 2) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(BKT == 64 ? 2 : 4) << 61;
   return d;
 }
 // instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
@@ -138,12 +138,14 @@ struct ConvArgs {
   int passes;         // 3: hi*hi + hi*lo + lo*hi (fp32-faithful, default); 2: drops lo*hi; 1: hi*hi only
 };
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int BKT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ConvArgs a) {
-  constexpr int STAGES = num_stages(BN);
-  constexpr int STAGE_BYTES = stage_bytes(BN);
+  constexpr int BK = BKT;
+  constexpr int A_TILE_BYTES = BM * BK * 2;
+  constexpr int STAGES = num_stages(BN, BKT);
+  constexpr int STAGE_BYTES = stage_bytes(BN, BKT);
   constexpr int B_TILE_BYTES = BN * BK * 2;
   constexpr int OUTC = PAIR ? BN / 2 : BN;  // output channels per N tile
   constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : 128);
@@ -226,8 +228,8 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + s * STAGE_BYTES;
-          const uint64_t dAh = make_desc_sw128(sa), dAl = make_desc_sw128(sa + A_TILE_BYTES);
-          const uint64_t dBh = make_desc_sw128(sa + 2 * A_TILE_BYTES), dBl = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          const uint64_t dAh = make_desc_sw<BKT>(sa), dAl = make_desc_sw<BKT>(sa + A_TILE_BYTES);
+          const uint64_t dBh = make_desc_sw<BKT>(sa + 2 * A_TILE_BYTES), dBl = make_desc_sw<BKT>(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
           for (int ks = 0; ks < BK / 16; ks++) {
             const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 fp16 = 32 B along K inside the swizzle atom
@@ -394,28 +396,28 @@ EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// 2-D fp16 row-major [rows][cols] tensor, box {64 cols, box_rows}, 128B swizzle
-CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D fp16 row-major [rows][cols] tensor, box {bk cols, box_rows}, swizzle = row bytes of the box
+CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bk) {
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {BK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
   return m;
 }
 
 // per-sample layout: 3-D fp16 tensor [n][S][cols], box {64 cols, BM positions, 1 sample}
-CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols) {
+CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk) {
   CUtensorMap m;
   cuuint64_t dims[3] = {cols, S, n};
   cuuint64_t strides[2] = {cols * 2, S * cols * 2};
-  cuuint32_t box[3] = {BK, BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, BM, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(3d) failed: " + std::to_string((int)r));
   return m;
 }
@@ -429,7 +431,7 @@ struct Layer {
 };
 struct Impl {
   NetDims d;
-  int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1;
+  int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1, bk = 64;
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
   __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
@@ -446,12 +448,12 @@ struct Impl {
   }
 };
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, int BKT>
 void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                  const int* n_dev, int* err, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
+    CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN, BKT)));
     attr_set = true;
   }
   ConvArgs a;
@@ -461,16 +463,22 @@ void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUt
   a.act_scale = ldexpf(1.0f, I.ea); a.err = err; a.passes = I.passes;
   const int max_tiles = (I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
   const int grid = std::min(I.num_sms, max_tiles);
-  k_conv3x3_tc<BN, PAIR><<<grid, NTHREADS, smem_bytes(BN), st>>>(ah, al, L.mB_hi, L.mB_lo, a);
+  k_conv3x3_tc<BN, PAIR, BKT><<<grid, NTHREADS, smem_bytes(BN, BKT), st>>>(ah, al, L.mB_hi, L.mB_lo, a);
+}
+template <int BKT>
+void dispatch_conv_bk(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
+                      const int* n_dev, int* err, cudaStream_t st) {
+  if (L.pair && L.bn == 256) launch_conv<256, true, BKT>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (L.pair && L.bn == 128) launch_conv<128, true, BKT>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (!L.pair && L.bn == 256) launch_conv<256, false, BKT>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (!L.pair && L.bn == 128) launch_conv<128, false, BKT>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (!L.pair && L.bn == 64) launch_conv<64, false, BKT>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else throw std::runtime_error("tc tower: unsupported tile");
 }
 void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                    const int* n_dev, int* err, cudaStream_t st) {
-  if (L.pair && L.bn == 256) launch_conv<256, true>(I, L, ah, al, ohi, olo, n_dev, err, st);
-  else if (L.pair && L.bn == 128) launch_conv<128, true>(I, L, ah, al, ohi, olo, n_dev, err, st);
-  else if (!L.pair && L.bn == 256) launch_conv<256, false>(I, L, ah, al, ohi, olo, n_dev, err, st);
-  else if (!L.pair && L.bn == 128) launch_conv<128, false>(I, L, ah, al, ohi, olo, n_dev, err, st);
-  else if (!L.pair && L.bn == 64) launch_conv<64, false>(I, L, ah, al, ohi, olo, n_dev, err, st);
-  else throw std::runtime_error("tc tower: unsupported tile");
+  if (I.bk == 64) dispatch_conv_bk<64>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else dispatch_conv_bk<32>(I, L, ah, al, ohi, olo, n_dev, err, st);
 }
 
 }  // namespace
@@ -483,6 +491,7 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
   Impl* I = new Impl;
   t.impl = I;
   I->d = d; I->n_max = n_max; I->ea = act_scale_log2;
+  if (const char* bs = getenv("AZ_TC_BK")) { if (atoi(bs) == 32) I->bk = 32; }  // experiments: 32 = SWIZZLE_64B, deeper ring
   if (const char* ps = getenv("AZ_TC_PASSES")) { int v = atoi(ps); if (v >= 1 && v <= 3) I->passes = v; }  // experiments only
   // layout choice by padded-row overhead (rows computed per real board point)
   const int S_flat = (d.H + 1) * (d.W + 1), S_ps = d.H * (d.W + 1), tps = (S_ps + BM - 1) / BM;
@@ -497,11 +506,11 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
   I->xin_hi = alloc_h((size_t)I->rows_alloc * 64); I->xin_lo = alloc_h((size_t)I->rows_alloc * 64);
   for (int i = 0; i < 2; i++) { I->x_hi[i] = alloc_h((size_t)I->rows_alloc * d.K); I->x_lo[i] = alloc_h((size_t)I->rows_alloc * d.K); }
   if (I->mode3d) {
-    I->mIn_hi = make_map3d(I->xin_hi, n_max, I->S, 64); I->mIn_lo = make_map3d(I->xin_lo, n_max, I->S, 64);
-    for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map3d(I->x_hi[i], n_max, I->S, d.K); I->mX_lo[i] = make_map3d(I->x_lo[i], n_max, I->S, d.K); }
+    I->mIn_hi = make_map3d(I->xin_hi, n_max, I->S, 64, I->bk); I->mIn_lo = make_map3d(I->xin_lo, n_max, I->S, 64, I->bk);
+    for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map3d(I->x_hi[i], n_max, I->S, d.K, I->bk); I->mX_lo[i] = make_map3d(I->x_lo[i], n_max, I->S, d.K, I->bk); }
   } else {
-    I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM);
-    for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM); }
+    I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM, I->bk); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM, I->bk);
+    for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM, I->bk); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM, I->bk); }
   }
   // layers: init (single), then SharedLayers fused pairs
   const int K = d.K, HW = d.HW();
@@ -514,7 +523,7 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
     const size_t ktot = (size_t)9 * L.cin;
     L.w_hi = alloc_h((size_t)L.n_total * ktot); L.w_lo = alloc_h((size_t)L.n_total * ktot);
     CUDA_CHECK(cudaMalloc(&L.aff, (size_t)HW * L.n_total * sizeof(float2)));
-    L.mB_hi = make_map(L.w_hi, L.n_total, ktot, L.bn); L.mB_lo = make_map(L.w_lo, L.n_total, ktot, L.bn);
+    L.mB_hi = make_map(L.w_hi, L.n_total, ktot, L.bn, I->bk); L.mB_lo = make_map(L.w_lo, L.n_total, ktot, L.bn, I->bk);
     I->layers.push_back(L);
   }
   CUDA_CHECK(cudaDeviceSynchronize());
