@@ -20,3 +20,14 @@ void tc_tower_profile_collect(TcTower& t, cudaStream_t st, double* conv_ms, doub
 void tc_tower_forward(TcTower& t, const NetLayout& L, const Snapshot& s, Fp32Scratch& sc, const float* planes,
                       const int* n_dev, int n_max, float* policy, int ldp, float* value, int* err_flag, cudaStream_t st,
                       unsigned long long* launches);
+
+// K7: the 3x3 convolutions of the training pass (forward, backward-data) on the same tcgen05 kernel (raw epilogue)
+struct TcGemm { void* impl = nullptr; };
+bool tc_gemm_supported(const NetDims& d);
+void tc_gemm_create(TcGemm& g, const NetDims& d, int B);
+void tc_gemm_destroy(TcGemm& g);
+// out[B][Cout][HW] (+)= conv3x3(x[B][Cin][HW], filter[fCo][fCi][3][3]); flip = backward-data (x = dz, Cin = fCo, Cout = fCi)
+void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int fCo, int fCi, bool flip, float* out, int Cout,
+                  bool accumulate, cudaStream_t st, unsigned long long* launches);
+// dW[K][K][3][3] = sum over batch and positions of dz (x) shifted x  (backward-filter of a K->K 3x3 layer)
+void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStream_t st, unsigned long long* launches);

@@ -12,6 +12,7 @@
 
 #include "nn.cuh"
 #include "train.cuh"
+#include "tower_tc.cuh"
 
 namespace {
 
@@ -307,6 +308,7 @@ struct TrainImpl {
   float* cost = nullptr;
   float* grads = nullptr;
   float* wflip = nullptr;  // mirrored/transposed filter of the unit being back-propagated
+  TcGemm tc;               // 3x3 forward / backward-data convs on tcgen05 (K in {64,128,256}); impl == nullptr -> fp32 tiled
   std::vector<void*> allocs;
   float* alloc(size_t n) {
     float* p;
@@ -337,6 +339,10 @@ void train_ws_alloc(TrainWS& ws, const NetLayout& L) {
   T->dcur = T->alloc(act); T->dprev = T->alloc(act); T->tmp = T->alloc(act); T->dl = T->alloc(act);
   T->cost = T->alloc(1);
   { size_t mx = 1; for (const UnitH& u : L.units) mx = std::max(mx, (size_t)u.Ci * u.Co * u.k * u.k); T->wflip = T->alloc(mx); }
+  {
+    const char* e = getenv("AZ_TRAIN_TC");
+    if (tc_gemm_supported(d) && !(e && e[0] == '0')) tc_gemm_create(T->tc, d, d.B);
+  }
   T->grads = T->alloc(L.total + 4);  // +4: the fused collective moves float4s
   CUDA_CHECK(cudaMemset(T->grads, 0, (L.total + 4) * 4));
 }
@@ -344,6 +350,7 @@ void train_ws_free(TrainWS& ws) {
   TrainImpl* T = (TrainImpl*)ws.impl;
   if (!T) return;
   for (void* p : T->allocs) cudaFree(p);
+  tc_gemm_destroy(T->tc);
   delete T;
   ws.impl = nullptr;
 }
@@ -366,7 +373,10 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   auto unit_fwd = [&](int ui, const float* x) {
     const UnitH& u = L.units[ui];
     size_t n = (size_t)B * u.Co * HW;
-    k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
+    if (T->tc.impl && u.k == 3 && u.Co % 64 == 0)
+      tc_gemm_conv(T->tc, x, u.Ci, Pp(u.filter), u.Co, u.Ci, false, T->z[ui], u.Co, false, st, &nl);
+    else
+      k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
     k_bn_stats<<<u.Co, 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
     k_bn_apply<<<nblk(n), 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], Pp(u.gamma), Pp(u.beta), T->xn[ui], T->y[ui], n, u.Co, HW);
     nl += 3;
@@ -407,9 +417,14 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
     size_t n = (size_t)B * u.Co * HW;
     k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n);
     k_bn_bwd_apply<<<u.Co, 256, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
-    k_conv_bwd_w_tiled<<<dim3((u.Ci * u.k * u.k + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, T->tmp, Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
+    if (T->tc.impl && u.k == 3 && u.Ci == K && u.Co == K)
+      tc_gemm_dw(T->tc, x, T->tmp, Gp(u.filter), st, &nl);
+    else
+      k_conv_bwd_w_tiled<<<dim3((u.Ci * u.k * u.k + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, T->tmp, Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
     nl += 3;
-    if (dx) {  // dx += conv(dz, mirrored transposed filter)
+    if (dx && T->tc.impl && u.k == 3 && u.Ci % 64 == 0 && u.Co % 64 == 0) {
+      tc_gemm_conv(T->tc, T->tmp, u.Co, Pp(u.filter), u.Co, u.Ci, true, dx, u.Ci, true, st, &nl);
+    } else if (dx) {  // dx += conv(dz, mirrored transposed filter)
       k_flip_filter<<<nblk((size_t)u.Ci * u.Co * u.k * u.k), 256, 0, st>>>(Pp(u.filter), T->wflip, u.Ci, u.Co, u.k);
       k_conv_fwd_tiled<true><<<dim3((B * HW + TT - 1) / TT, (u.Ci + TT - 1) / TT), 256, 0, st>>>(T->tmp, T->wflip, dx, B, u.Co, u.Ci, H, W, u.k);
       nl += 2;

@@ -217,6 +217,8 @@ def _train_data(rng, B, plane, A1):
 @pytest.mark.parametrize("kind,m,n,k,nn", [
     (K.GAME_MNK, 3, 3, 3, dict(k=3, shared_layers=3, fc=8, batch_size=20, features=2, action_space=10)),   # cmd/tictactoe
     (K.GAME_C4, 6, 7, 4, dict(k=16, shared_layers=2, fc=32, batch_size=16, features=2, action_space=8)),   # C4 shapes
+    # K = 64: the 3x3 convs (forward and backward-data) run on the tcgen05 kernel (hi/lo split, raw epilogue)
+    (K.GAME_MNK, 9, 9, 5, dict(k=64, shared_layers=2, fc=32, batch_size=4, features=2, action_space=82)),
 ])
 def test_train_grads_vs_oracle(oracle, engine_lib, kind, m, n, k, nn):
     """One Train step (BN train mode, xent-on-logits + MSE, reverse mode): CUDA gradients of every
@@ -235,6 +237,29 @@ def test_train_grads_vs_oracle(oracle, engine_lib, kind, m, n, k, nn):
     # and the solver step
     eo.train_apply(1, go, 0.1); eg.train_apply(1, gg, 0.1)
     assert np.abs(eo.net_get(1) - eg.net_get(1)).max() <= 1e-4 * max(1.0, scale)
+
+
+def test_train_tensor_core_vs_fp32_full_width(engine_lib, monkeypatch):
+    """K7 at the C3 width (19x19, K=256): the tcgen05 training convs (forward, backward-data, backward-filter with
+    split-K) against the engine's own fp32 CUDA-core kernels on the same batch — size-independent A/B, the fp32 path
+    being the one pinned against the oracle above."""
+    nn = dict(k=256, shared_layers=2, fc=64, batch_size=8, features=18, action_space=362)
+    def desc():
+        return K.make_desc(K.GAME_WQ, 19, 19, 0, komi=7.5, sims=2, n_games=2, seed=1, nn=nn, max_moves=4, flags=K.FLAG_FP32_TOWER)
+    rng = np.random.default_rng(5)
+    X, Pi, V = _train_data(rng, 8, 18 * 361, 362)
+    out = []
+    for tc in ("0", "1"):
+        monkeypatch.setenv("AZ_TRAIN_TC", tc)
+        e = engine_lib.create(desc())
+        H.tame_gammas([e], 1, 23, target=0.05)
+        out.append(e.train_grads(1, X, Pi, V))
+        e.close()
+    (g0, c0), (g1, c1) = out
+    assert np.isfinite(g1).all()
+    assert abs(c0 - c1) <= 1e-5 * max(1, abs(c0))
+    scale = np.abs(g0).max()
+    assert np.abs(g0 - g1).max() <= 1e-4 * scale, (np.abs(g0 - g1).max(), scale)
 
 
 def test_train_loop_vs_oracle(oracle, engine_lib):

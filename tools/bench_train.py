@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""dual.Train step (K7) timing: forward (BN train mode) + loss + backward + SGD on one batch, fp32 CUDA-core
-kernels of train.cu.  Prints one JSON line per shape with the algorithmic FLOPs (3 x forward) and the achieved rate."""
+"""dual.Train step (K7) timing: forward (BN train mode) + loss + backward + SGD on one batch.  3x3 layers with
+K in {64,128,256} run forward / backward-data / backward-filter on the tcgen05 kernels (AZ_TRAIN_TC=0 forces the fp32
+CUDA-core kernels of train.cu, which every other layer uses).  Prints one JSON line per shape with the algorithmic FLOPs (3 x forward) and the achieved rate."""
 import json
 import os
 import sys
@@ -36,5 +37,5 @@ for name, kind, m, n, k, nn in SHAPES:
     dt = (time.perf_counter() - t0) / iters
     print(json.dumps({"shape": name, "ms_per_step": dt * 1e3, "algorithmic_gflop_per_step": 3 * fwd / 1e9,
                       "tflops": 3 * fwd / dt / 1e12, "cost": float(costs[-1]),
-                      "note": "fp32 CUDA-core kernels (one thread per output); tensor-core backward is the next optimisation row"}), flush=True)
+                      "train_tc": os.environ.get("AZ_TRAIN_TC", "1")}), flush=True)
     e.close()
