@@ -132,6 +132,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// training operands carry a data-dependent power-of-two scale: the device word is ilogb(absmax) - 13 (or the
+// 0x80808080 fill when the tensor is all zero); scale exponent e = -word
+__device__ __forceinline__ int exp_decode(const int* e) { const int v = *e; return v < -100000 ? 0 : -v; }
+
 struct ConvArgs {
   const int* n_dev;   // batch size (device)
   int n_max;
@@ -296,7 +300,7 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         tmem_ld_wait();
         if (a.out_raw) {
           if (valid) {
-            const float sc = exp2f(-(float)(*a.exp_a + *a.exp_b));
+            const float sc = exp2f(-(float)(exp_decode(a.exp_a) + exp_decode(a.exp_b)));
             float4* o = reinterpret_cast<float4*>(a.out_raw + (size_t)(a.guard + r) * a.n_total + n0 + c0);
 #pragma unroll
             for (int q = 0; q < 8; q++)
@@ -488,7 +492,7 @@ __global__ void k_dw_reduce(const float* __restrict__ partial, int splits, int C
                             const int* __restrict__ eb, float* __restrict__ dW) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Co * Ci) return;
-  const float sc = exp2f(-(float)(*ea + *eb));
+  const float sc = exp2f(-(float)(exp_decode(ea) + exp_decode(eb)));
   const size_t tap_stride = (size_t)Co * Ci;
   for (int tap = 0; tap < 9; tap++) {
     float acc = 0.0f;
@@ -504,7 +508,7 @@ __global__ void k_pack_cmajor(const float* __restrict__ x, int B, int C, int H, 
   if (idx >= (size_t)B * C * HW) return;
   const int hw = (int)(idx % HW), c = (int)((idx / HW) % C), b = (int)(idx / ((size_t)HW * C));
   const int y = hw / W, xx = hw - y * W;
-  const float v = x[idx] * exp2f((float)*exp_in);
+  const float v = x[idx] * exp2f((float)exp_decode(exp_in));
   const __half h = __float2half_rn(v);
   const size_t o = (size_t)c * ld + guard + (size_t)b * S + y * Wp + xx;
   hi[o] = h;
@@ -868,32 +872,58 @@ __global__ void k_absmax_exp(const float* __restrict__ x, size_t n, int* exp_out
     if (threadIdx.x == 0) atomicMax(exp_out, (m > 0.0f && isfinite(m)) ? ilogbf(m) - 13 : -0x7fffffff);  // stores -e (max over blocks)
   }
 }
-__global__ void k_exp_finish(int* e) { int v = *e; *e = v < -100000 ? 0 : -v; }  // e = 13 - ilogb(absmax)
 
-// NCHW fp32 [B][C][HW] -> flat zero-bordered NHWC hi/lo [guard + B*S][cpad], scaled by 2^(*exp)
-__global__ void k_pack_nchw(const float* __restrict__ x, int B, int C, int H, int W, int cpad, int guard, int S,
-                            const int* __restrict__ exp_in, __half* hi, __half* lo) {
+
+// NCHW fp32 [B][C][HW] -> flat zero-bordered NHWC hi/lo [guard + B*S][cpad], scaled by 2^e.  Tile = 64 channels x
+// 32 board points through shared memory: reads coalesced along hw, writes 128-byte runs along the channels.
+__global__ void __launch_bounds__(256) k_pack_nchw(const float* __restrict__ x, int B, int C, int H, int W, int cpad, int guard, int S,
+                                                   const int* __restrict__ exp_in, __half* hi, __half* lo) {
+  __shared__ float t[64][33];
   const int HW = H * W, Wp = W + 1;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * HW * cpad) return;
-  const int c = (int)(idx % cpad), hw = (int)((idx / cpad) % HW), b = (int)(idx / ((size_t)cpad * HW));
-  const int y = hw / W, xx = hw - y * W;
-  const float v = c < C ? x[((size_t)b * C + c) * HW + hw] * exp2f((float)*exp_in) : 0.0f;
-  const __half h = __float2half_rn(v);
-  const size_t o = ((size_t)guard + (size_t)b * S + y * Wp + xx) * cpad + c;
-  hi[o] = h;
-  lo[o] = __float2half_rn(v - __half2float(h));
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float sc = exp2f((float)exp_decode(exp_in));
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int c = c0 + ty + 8 * i, hw = hw0 + tx;
+    t[ty + 8 * i][tx] = (c < C && hw < HW) ? x[((size_t)b * C + c) * HW + hw] * sc : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int hw = hw0 + ty + 8 * i;
+    if (hw >= HW) continue;
+    const int y = hw / W, xx = hw - y * W;
+    const size_t o = ((size_t)guard + (size_t)b * S + y * Wp + xx) * cpad + c0 + 2 * tx;
+    const float v0 = t[2 * tx][ty + 8 * i], v1 = t[2 * tx + 1][ty + 8 * i];
+    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+    *reinterpret_cast<__half2*>(hi + o) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(lo + o) = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+  }
 }
-// flat NHWC fp32 [guard + B*S][ld] -> NCHW [B][C][HW] (assign or accumulate)
-__global__ void k_unpack_nchw(const float* __restrict__ raw, int B, int C, int H, int W, int ld, int guard, int S, float* out,
-                              int accumulate) {
+// flat NHWC fp32 [guard + B*S][ld] -> NCHW [B][C][HW] (assign or accumulate); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) k_unpack_nchw(const float* __restrict__ raw, int B, int C, int H, int W, int ld, int guard, int S,
+                                                     float* out, int accumulate) {
+  __shared__ float t[32][33];
   const int HW = H * W, Wp = W + 1;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * C * HW) return;
-  const int hw = (int)(idx % HW), c = (int)((idx / HW) % C), b = (int)(idx / ((size_t)HW * C));
-  const int y = hw / W, xx = hw - y * W;
-  const float v = raw[((size_t)guard + (size_t)b * S + y * Wp + xx) * ld + c];
-  if (accumulate) out[idx] += v; else out[idx] = v;
+  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int hw = hw0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.0f;
+    if (hw < HW && c < C) { const int y = hw / W, xx = hw - y * W; v = raw[((size_t)guard + (size_t)b * S + y * Wp + xx) * ld + c]; }
+    t[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int c = c0 + ty + 8 * i, hw = hw0 + tx;
+    if (c < C && hw < HW) {
+      const size_t o = ((size_t)b * C + c) * HW + hw;
+      if (accumulate) out[o] += t[tx][ty + 8 * i]; else out[o] = t[tx][ty + 8 * i];
+    }
+  }
 }
 // filter [Co][Ci][3][3] -> Bm hi/lo [rows][9*cpad]; flip = backward-data operand (rows = Ci, K = tap*Co + co, mirrored taps)
 __global__ void k_prep_filter(const float* __restrict__ w, int Co, int Ci, int cpad, int flip, const int* __restrict__ exp_in,
@@ -904,7 +934,7 @@ __global__ void k_prep_filter(const float* __restrict__ w, int Co, int Ci, int c
   const int kc = (int)(idx % cpad), tap = (int)((idx / cpad) % 9), row = (int)(idx / ((size_t)9 * cpad));
   float v = 0.0f;
   if (kc < kin) v = flip ? w[((size_t)kc * Ci + row) * 9 + (8 - tap)] : w[((size_t)row * Ci + kc) * 9 + tap];
-  v *= exp2f((float)*exp_in);
+  v *= exp2f((float)exp_decode(exp_in));
   const __half h = __float2half_rn(v);
   hi[idx] = h;
   lo[idx] = __float2half_rn(v - __half2float(h));
@@ -973,7 +1003,6 @@ static void absmax_exp(const float* x, size_t n, int* e, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(e, 0x80, 4, st));  // 0x80808080: below every real exponent
   unsigned blocks = (unsigned)std::min<size_t>((n + 1023) / 1024, 1024);
   k_absmax_exp<<<blocks, 256, 0, st>>>(x, n, e);
-  k_exp_finish<<<1, 1, 0, st>>>(e);
 }
 
 // out (NCHW [B][Cout][HW]) (+)= conv3x3(x (NCHW [B][Cin][HW]), filter [Co][Ci][3][3]) or its backward-data twin
@@ -992,8 +1021,7 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   absmax_exp(x, (size_t)I->B * Cin * HW, I->exp_a, st);
   absmax_exp(filter, (size_t)fCo * fCi * 9, I->exp_b, st);
   {
-    size_t total = (size_t)I->B * HW * cpad;
-    k_pack_nchw<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, I->B, Cin, d.H, d.W, cpad, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
+    k_pack_nchw<<<dim3((HW + 31) / 32, cpad / 64, I->B), 256, 0, st>>>(x, I->B, Cin, d.H, d.W, cpad, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
     size_t wt = (size_t)Cout * 9 * cpad;
     k_prep_filter<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(filter, fCo, fCi, cpad, flip ? 1 : 0, I->exp_b, I->w_hi, I->w_lo);
   }
@@ -1017,10 +1045,9 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   else if (bn == 128) launch(k_conv3x3_tc<128, false, 64>, 128);
   else launch(k_conv3x3_tc<64, false, 64>, 64);
   {
-    size_t total = (size_t)I->B * Cout * HW;
-    k_unpack_nchw<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0);
+    k_unpack_nchw<<<dim3((HW + 31) / 32, (Cout + 31) / 32, I->B), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0);
   }
-  if (launches) *launches += 8;
+  if (launches) *launches += 6;
 }
 
 // dW[Co][Ci][3][3] = backward-filter of conv3x3 for x (NCHW [B][Ci][HW]) and dz (NCHW [B][Co][HW]); Ci == Co == K
@@ -1037,7 +1064,7 @@ void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStrea
   absmax_exp(dz, n, I->exp_t, st);
   absmax_exp(x, n, I->exp_a, st);
   k_pack_cmajor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, I->B, C, d.H, d.W, I->ld, I->guard, I->S, I->exp_t, I->t_hi, I->t_lo);
-  k_pack_nchw<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, I->B, C, d.H, d.W, C, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
+  k_pack_nchw<<<dim3((HW + 31) / 32, C / 64, I->B), 256, 0, st>>>(x, I->B, C, d.H, d.W, C, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
   const int bn = std::min(256, C);
   CUtensorMap mAh = make_map(I->t_hi, I->crow, I->ld, BM, 64), mAl = make_map(I->t_lo, I->crow, I->ld, BM, 64);
   CUtensorMap mBh = make_map(I->a_hi, I->rows_alloc, C, 64, 64), mBl = make_map(I->a_lo, I->rows_alloc, C, 64, 64);
@@ -1056,5 +1083,5 @@ void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStrea
   else if (bn == 128) launch(k_dw_tc<128>, 128);
   else launch(k_dw_tc<64>, 64);
   k_dw_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(I->partial, I->splits, C, C, I->exp_t, I->exp_a, dW);
-  if (launches) *launches += 8;
+  if (launches) *launches += 6;
 }

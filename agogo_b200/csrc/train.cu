@@ -101,24 +101,29 @@ __global__ void __launch_bounds__(256) k_conv_bwd_w_tiled(const float* __restric
   const int P = B * HW, Q = Ci * kk;
   const int q0 = blockIdx.x * TT, c0 = blockIdx.y * TT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // blockIdx.z = slice of the position range (few-output layers would otherwise run on a handful of blocks);
+  // slice z writes its partial to dW + z * Co * Q, k_sum_slices adds them in slice order
+  const int chunk = ((P + gridDim.z - 1) / gridDim.z + PK - 1) / PK * PK;
+  const int p_begin = blockIdx.z * chunk, p_end = min(P, p_begin + chunk);
+  dW += (size_t)blockIdx.z * Co * Q;
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
-  for (int pb = 0; pb < P; pb += PK) {
+  for (int pb = p_begin; pb < p_end; pb += PK) {
     for (int e = threadIdx.x; e < PK * TT; e += 256) {
       const int c = e / PK, pp = e - c * PK;  // consecutive threads walk positions: coalesced in hw
       const int p = pb + pp;
       float v = 0.0f;
-      if (p < P && c0 + c < Co) { const int b = p / HW, hw = p - b * HW; v = dz[((size_t)b * Co + c0 + c) * HW + hw]; }
+      if (p < p_end && c0 + c < Co) { const int b = p / HW, hw = p - b * HW; v = dz[((size_t)b * Co + c0 + c) * HW + hw]; }
       sD[pp][c] = v;
     }
     for (int e = threadIdx.x; e < PK * TT; e += 256) {
       const int qq = e / PK, pp = e - qq * PK;
       const int q = q0 + qq, p = pb + pp;
       float v = 0.0f;
-      if (p < P && q < Q) {
+      if (p < p_end && q < Q) {
         const int ci = q / kk, t = q - ci * kk;
         const int b = p / HW, hw = p - b * HW;
         const int yy = hw / W + t / k - pad, xx = hw % W + t % k - pad;
@@ -151,6 +156,14 @@ __global__ void __launch_bounds__(256) k_conv_bwd_w_tiled(const float* __restric
       if (q < Q) dW[(size_t)co * Q + q] = acc[i][j];
     }
   }
+}
+
+__global__ void k_sum_slices(const float* __restrict__ part, int slices, size_t n, float* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float acc = 0.0f;
+  for (int z = 0; z < slices; z++) acc += part[(size_t)z * n + idx];
+  out[idx] = acc;
 }
 
 __device__ inline float block_sum(float v, float* sh) {
@@ -289,13 +302,27 @@ __global__ void k_bn_bwd_apply(float* dxn, const float* __restrict__ xn, const f
   }
 }
 __global__ void k_sgd(float* p, const float* __restrict__ g, float lr, float gscale, size_t n) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < n) p[idx] = p[idx] - lr * (g[idx] * gscale);
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    pv.x = pv.x - lr * (gv.x * gscale); pv.y = pv.y - lr * (gv.y * gscale);
+    pv.z = pv.z - lr * (gv.z * gscale); pv.w = pv.w - lr * (gv.w * gscale);
+    reinterpret_cast<float4*>(p)[i] = pv;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const size_t i = (n4 << 2) + threadIdx.x; p[i] = p[i] - lr * (g[i] * gscale); }
 }
 
 inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 }  // namespace
+
+// how many position slices the fp32 backward-filter kernel of a unit is launched with (1 = write dW directly)
+static int dw_slices(const UnitH& u, int P) {
+  const int blocks = ((u.Ci * u.k * u.k + TT - 1) / TT) * ((u.Co + TT - 1) / TT);
+  if (blocks >= 148) return 1;
+  return std::max(1, std::min({(296 + blocks - 1) / blocks, 64, (P + 255) / 256}));
+}
 
 struct TrainImpl {
   NetDims d;
@@ -308,6 +335,8 @@ struct TrainImpl {
   float* cost = nullptr;
   float* grads = nullptr;
   float* wflip = nullptr;  // mirrored/transposed filter of the unit being back-propagated
+  float* dwpart = nullptr; // position-sliced partial filter gradients of the few-output layers
+  size_t dwpart_n = 0;
   TcGemm tc;               // 3x3 forward / backward-data convs on tcgen05 (K in {64,128,256}); impl == nullptr -> fp32 tiled
   std::vector<void*> allocs;
   float* alloc(size_t n) {
@@ -339,6 +368,11 @@ void train_ws_alloc(TrainWS& ws, const NetLayout& L) {
   T->dcur = T->alloc(act); T->dprev = T->alloc(act); T->tmp = T->alloc(act); T->dl = T->alloc(act);
   T->cost = T->alloc(1);
   { size_t mx = 1; for (const UnitH& u : L.units) mx = std::max(mx, (size_t)u.Ci * u.Co * u.k * u.k); T->wflip = T->alloc(mx); }
+  for (const UnitH& u : L.units) {
+    int slices = dw_slices(u, (int)(B * HW));
+    if (slices > 1) T->dwpart_n = std::max(T->dwpart_n, (size_t)slices * u.Co * u.Ci * u.k * u.k);
+  }
+  if (T->dwpart_n) T->dwpart = T->alloc(T->dwpart_n);
   {
     const char* e = getenv("AZ_TRAIN_TC");
     if (tc_gemm_supported(d) && !(e && e[0] == '0')) tc_gemm_create(T->tc, d, d.B);
@@ -377,7 +411,7 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
       tc_gemm_conv(T->tc, x, u.Ci, Pp(u.filter), u.Co, u.Ci, false, T->z[ui], u.Co, false, st, &nl);
     else
       k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
-    k_bn_stats<<<u.Co, 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
+    k_bn_stats<<<u.Co, 1024, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
     k_bn_apply<<<nblk(n), 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], Pp(u.gamma), Pp(u.beta), T->xn[ui], T->y[ui], n, u.Co, HW);
     nl += 3;
   };
@@ -416,11 +450,16 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
     const UnitH& u = L.units[ui];
     size_t n = (size_t)B * u.Co * HW;
     k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n);
-    k_bn_bwd_apply<<<u.Co, 256, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
+    k_bn_bwd_apply<<<u.Co, 1024, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
     if (T->tc.impl && u.k == 3 && u.Ci == K && u.Co == K)
       tc_gemm_dw(T->tc, x, T->tmp, Gp(u.filter), st, &nl);
-    else
-      k_conv_bwd_w_tiled<<<dim3((u.Ci * u.k * u.k + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, T->tmp, Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
+    else {
+      const int slices = dw_slices(u, B * HW);
+      const size_t nw = (size_t)u.Co * u.Ci * u.k * u.k;
+      k_conv_bwd_w_tiled<<<dim3((u.Ci * u.k * u.k + TT - 1) / TT, (u.Co + TT - 1) / TT, slices), 256, 0, st>>>(
+          x, T->tmp, slices > 1 ? T->dwpart : Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
+      if (slices > 1) { k_sum_slices<<<nblk(nw), 256, 0, st>>>(T->dwpart, slices, nw, Gp(u.filter)); nl++; }
+    }
     nl += 3;
     if (dx && T->tc.impl && u.k == 3 && u.Ci % 64 == 0 && u.Co % 64 == 0) {
       tc_gemm_conv(T->tc, T->tmp, u.Co, Pp(u.filter), u.Co, u.Ci, true, dx, u.Ci, true, st, &nl);
@@ -545,6 +584,6 @@ void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params
 
 void train_sgd(TrainWS& ws, const NetLayout& L, float* P, float lr, float gscale, cudaStream_t st, unsigned long long* launches) {
   TrainImpl* T = (TrainImpl*)ws.impl;
-  k_sgd<<<nblk(L.total), 256, 0, st>>>(P, T->grads, lr, gscale, L.total);
+  k_sgd<<<(unsigned)std::min<size_t>((L.total / 4 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(P, T->grads, lr, gscale, L.total);
   if (launches) (*launches)++;
 }

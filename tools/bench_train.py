@@ -20,7 +20,10 @@ SHAPES = [
     ("C3/C5 19x19 Go (K=256, 20 blocks, batch 32)", K.GAME_WQ, 19, 19, 0, dict(k=256, shared_layers=20, fc=512, batch_size=32, features=18, action_space=362)),
 ]
 lib = K.load()
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""   # substring filter on the shape name (e.g. C3)
 for name, kind, m, n, k, nn in SHAPES:
+    if ONLY not in name:
+        continue
     d = K.make_desc(kind, m, n, k, komi=7.5, sims=2, n_games=2, seed=1, nn=nn, max_moves=4, flags=K.FLAG_FP32_TOWER)
     e = lib.create(d)
     e.net_init(1, 3)
