@@ -30,7 +30,7 @@ class MCTSConfig(C.Structure):
     _fields_ = [("puct", C.c_float), ("timeout_ns", C.c_int64), ("m", C.c_int32), ("n", C.c_int32),
                 ("random_count", C.c_int32), ("budget", C.c_int32), ("random_min_visits", C.c_uint32),
                 ("random_temperature", C.c_float), ("dumb_pass", C.c_int32), ("resign_percentage", C.c_float),
-                ("pass_preference", C.c_int32), ("sims", C.c_int32)]
+                ("pass_preference", C.c_int32), ("sims", C.c_int32), ("workers", C.c_int32)]
 
 
 class DualConfig(C.Structure):
@@ -356,12 +356,12 @@ def comm_unique_id(lib):
 
 def make_desc(kind, m, n, k=0, komi=0.0, sims=50, puct=1.0, nn=None, encoder=None, n_games=1, seed=1, flags=0,
               max_moves=0, device=0, zobrist_seed=12345, pass_preference=DONT_PREFER_PASS, dumb_pass=1,
-              mcts_m=None, mcts_n=None):
+              mcts_m=None, mcts_n=None, workers=0):
     """Build an EngineDesc the way the reference's programs build their Configs."""
     d = EngineDesc()
     d.game = GameDesc(kind, m, n, k, komi, max_moves, zobrist_seed)
     d.mcts = MCTSConfig(puct, 0, mcts_m if mcts_m is not None else m, mcts_n if mcts_n is not None else n, 0, 10000, 0,
-                        0.0, dumb_pass, 0.0, pass_preference, sims)
+                        0.0, dumb_pass, 0.0, pass_preference, sims, workers)
     cells = m * n
     A = n if kind == GAME_C4 else cells
     if nn is None:

@@ -88,6 +88,8 @@ struct az_engine {
   uint64_t wave_graph_version = 0, cfg_version = 1;
   unsigned long long wave_graph_launches = 0;
   bool graphs_enabled = true, profiling = false;
+  int32_t* round_workers_dev = nullptr;  // mcts.Config workers: how many the current round starts
+  int round_workers_host = -1;
   cudaEvent_t prof_start = nullptr, prof_stop = nullptr;  // region timing between az_profile(1) and az_profile(0)
   TrainWS train;
   void* comm = nullptr;  // ncclComm_t (bootstrap of the peer-memory path; plain all-reduce as the checked alternative)
@@ -240,6 +242,10 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     EngineDev& E = e->E;
     const int G = desc->n_games;
     E.G = G; E.T = P.shared_tree ? 1 : 2; E.cellsP = (P.cells + 15) & ~15;
+    const int V = desc->mcts.workers > 1 ? desc->mcts.workers : 1;
+    if (V > 4096 || (long long)G * V > (1LL << 24)) throw std::runtime_error("mcts.Config workers out of range");
+    E.V = V; E.GS = G * V;
+    const size_t GV = (size_t)G * V;
     E.Lmax = std::max(n.action_space, P.A + 1);
     E.tree_seed = derive_seed(desc->seed, 1);
     E.board = e->dalloc<uint8_t>((size_t)G * E.cellsP);
@@ -254,13 +260,16 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     const size_t NN = GT * (size_t)P.max_nodes;
     E.N = e->dalloc<uint32_t>(NN, false); E.W = e->dalloc<float>(NN, false); E.Pr = e->dalloc<float>(NN, false);
     E.meta = e->dalloc<uint32_t>(NN, false); E.first = e->dalloc<int32_t>(NN, false);
-    E.wv = e->dalloc<int32_t>((size_t)G * WV_COUNT);
-    E.path = e->dalloc<int32_t>((size_t)G * (P.maxDepth + 1));
-    E.leaf_board = e->dalloc<uint8_t>((size_t)G * E.cellsP);
-    E.batch_count = e->dalloc<int32_t>(2);
-    E.nn_in = e->dalloc<float>((size_t)2 * G * P.plane);
-    E.policy = e->dalloc<float>((size_t)2 * G * E.Lmax);
-    E.value = e->dalloc<float>((size_t)2 * G);
+    E.wv = e->dalloc<int32_t>(GV * WV_COUNT);
+    E.path = e->dalloc<int32_t>(GV * (P.maxDepth + 1));
+    E.leaf_board = e->dalloc<uint8_t>(GV * E.cellsP);
+    E.batch_count = e->dalloc<int32_t>(4);
+    E.nn_in = e->dalloc<float>((size_t)2 * GV * P.plane);
+    E.policy = e->dalloc<float>((size_t)2 * GV * E.Lmax);
+    E.value = e->dalloc<float>((size_t)2 * GV);
+    E.vl = V > 1 ? e->dalloc<uint8_t>(NN) : nullptr;
+    e->round_workers_dev = e->dalloc<int32_t>(1);
+    E.round_workers = e->round_workers_dev;
     E.ex_board = e->dalloc<float>((size_t)G * P.plane);
     E.ex_policy = e->dalloc<float>((size_t)G * (P.A + 1));
     E.ex_value = e->dalloc<float>(G);
@@ -291,10 +300,10 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
       e->snap[a] = make_snapshot_layout(e->L);
       e->snap[a].d = e->dalloc<float>(e->snap[a].total);
     }
-    fp32_scratch_alloc(e->fp32, nd, G);
+    fp32_scratch_alloc(e->fp32, nd, E.GS);
     e->use_tc = !(desc->flags & AZ_FLAG_FP32_TOWER) && tc_tower_supported(nd);
     if (e->use_tc)
-      for (int a = 0; a < 2; a++) tc_tower_alloc(e->tc[a], nd, G, desc->act_scale_log2 ? desc->act_scale_log2 : 5);
+      for (int a = 0; a < 2; a++) tc_tower_alloc(e->tc[a], nd, E.GS, desc->act_scale_log2 ? desc->act_scale_log2 : 5);
 
     CUDA_CHECK(cudaMallocHost(&e->h_ex_board, (size_t)G * P.plane * 4));
     CUDA_CHECK(cudaMallocHost(&e->h_ex_policy, (size_t)G * (P.A + 1) * 4));
@@ -412,12 +421,12 @@ int az_agent_set_table(az_engine* e, int32_t agent, int32_t n_rows, int32_t row_
 static void run_forward(az_engine* e, int agent) {
   const EngineDev& E = e->E;
   if (E.inf[agent].kind != INF_DUAL) return;
-  const float* in = E.nn_in + (size_t)agent * E.G * e->P.plane;
-  float* pol = E.policy + (size_t)agent * E.G * E.Lmax;
-  float* val = E.value + (size_t)agent * E.G;
+  const float* in = E.nn_in + (size_t)agent * E.GS * e->P.plane;
+  float* pol = E.policy + (size_t)agent * E.GS * E.Lmax;
+  float* val = E.value + (size_t)agent * E.GS;
   const int* cnt = E.batch_count + agent;
-  if (e->use_tc) tc_tower_forward(e->tc[agent], e->L, e->snap[agent], e->fp32, in, cnt, E.G, pol, E.Lmax, val, E.err, e->stream, &e->launches);
-  else forward_fp32(e->L, e->snap[agent], e->fp32, in, cnt, E.G, pol, E.Lmax, val, e->stream, &e->launches);
+  if (e->use_tc) tc_tower_forward(e->tc[agent], e->L, e->snap[agent], e->fp32, in, cnt, E.GS, pol, E.Lmax, val, E.err, e->stream, &e->launches);
+  else forward_fp32(e->L, e->snap[agent], e->fp32, in, cnt, E.GS, pol, E.Lmax, val, e->stream, &e->launches);
 }
 
 int az_infer(az_engine* e, int32_t agent, const float* planes, int32_t n, float* policy, float* value) {
@@ -428,15 +437,15 @@ int az_infer(az_engine* e, int32_t agent, const float* planes, int32_t n, float*
   CUDA_CHECK(cudaSetDevice(e->device));
   const EngineDev& E = e->E;
   const int A1 = e->d.nn.action_space;
-  for (int done = 0; done < n; done += E.G) {
-    int chunk = std::min(E.G, n - done);
-    CUDA_CHECK(cudaMemcpyAsync(E.nn_in + (size_t)agent * E.G * e->P.plane, planes + (size_t)done * e->P.plane,
+  for (int done = 0; done < n; done += E.GS) {
+    int chunk = std::min(E.GS, n - done);
+    CUDA_CHECK(cudaMemcpyAsync(E.nn_in + (size_t)agent * E.GS * e->P.plane, planes + (size_t)done * e->P.plane,
                                (size_t)chunk * e->P.plane * 4, cudaMemcpyHostToDevice, e->stream));
     CUDA_CHECK(cudaMemcpyAsync(E.batch_count + agent, &chunk, 4, cudaMemcpyHostToDevice, e->stream));
     run_forward(e, agent);
-    CUDA_CHECK(cudaMemcpy2DAsync(policy + (size_t)done * A1, (size_t)A1 * 4, E.policy + (size_t)agent * E.G * E.Lmax,
+    CUDA_CHECK(cudaMemcpy2DAsync(policy + (size_t)done * A1, (size_t)A1 * 4, E.policy + (size_t)agent * E.GS * E.Lmax,
                                  (size_t)E.Lmax * 4, (size_t)A1 * 4, chunk, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_CHECK(cudaMemcpyAsync(value + done, E.value + (size_t)agent * E.G, (size_t)chunk * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(value + done, E.value + (size_t)agent * E.GS, (size_t)chunk * 4, cudaMemcpyDeviceToHost, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
   }
   int bits = 0;
@@ -505,6 +514,12 @@ int az_search_begin(az_engine* e) {
   GUARD_END(e)
   return AZ_OK;
 }
+// n pipeline iterations = ceil(n / workers) rounds; the device reads how many workers the round starts
+static void set_round_workers(az_engine* e, int w) {
+  if (e->E.V == 1 || e->round_workers_host == w) return;
+  e->round_workers_host = w;
+  CUDA_CHECK(cudaMemcpyAsync(e->round_workers_dev, &e->round_workers_host, 4, cudaMemcpyHostToDevice, e->stream));
+}
 static void run_wave(az_engine* e) {
   launch_select(e->P, e->E, e->n_play, e->stream); e->launches++;
   eval_pending(e);
@@ -527,9 +542,12 @@ int az_search_run(az_engine* e, int32_t n) {
       e->launches = l0;
       e->wave_graph_n = e->n_play; e->wave_graph_version = e->cfg_version;
     }
-    for (int i = 0; i < n; i++) { CUDA_CHECK(cudaGraphLaunch(e->wave_graph, e->stream)); e->launches += e->wave_graph_launches; }
+    for (int left = n; left > 0; left -= e->E.V) {
+      set_round_workers(e, std::min(left, e->E.V));
+      CUDA_CHECK(cudaGraphLaunch(e->wave_graph, e->stream)); e->launches += e->wave_graph_launches;
+    }
   } else {
-    for (int i = 0; i < n; i++) run_wave(e);
+    for (int left = n; left > 0; left -= e->E.V) { set_round_workers(e, std::min(left, e->E.V)); run_wave(e); }
   }
   GUARD_END(e)
   return AZ_OK;

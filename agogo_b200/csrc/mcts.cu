@@ -185,7 +185,7 @@ __global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __re
     if (lane < TI_COUNT)
       ti[lane] = lane == TI_ROOT ? -1 : (lane == TI_RNG_LO ? (int)(unsigned)(E.tree_seed & 0xffffffffu) : (lane == TI_RNG_HI ? (int)(unsigned)(E.tree_seed >> 32) : 0));
   }
-  if (lane < WV_COUNT) E.wv[(size_t)g * WV_COUNT + lane] = 0;
+  for (int i = lane; i < E.V * WV_COUNT; i += 32) WV_OF(E, g, 0)[i] = 0;
   __syncwarp();
   if (lane == 0) {
     for (int i = 0; i < GI_COUNT; i++) gi[i] = 0;
@@ -222,13 +222,16 @@ __global__ void k_assign_slots(EngineDev E, int n_games, int shared_tree) {
     for (int a = 0; a < 2; a++) {
       unsigned m = __ballot_sync(FULL, active && agent == a);
       if (active && agent == a) {
-        E.wv[(size_t)g * WV_COUNT + WV_SLOT] = cnt[a] + __popc(m & ((1u << lane) - 1));
-        E.wv[(size_t)g * WV_COUNT + WV_AGENT] = a;
+        WV_OF(E, g, 0)[WV_SLOT] = cnt[a] + __popc(m & ((1u << lane) - 1));
+        WV_OF(E, g, 0)[WV_AGENT] = a;
       }
       cnt[a] += __popc(m);
     }
   }
-  if (lane == 0) { E.batch_count[0] = cnt[0]; E.batch_count[1] = cnt[1]; *E.n_active = cnt[0] + cnt[1]; }
+  if (lane == 0) {
+    E.batch_count[0] = cnt[0]; E.batch_count[1] = cnt[1]; E.batch_count[2] = cnt[0]; E.batch_count[3] = cnt[1];
+    *E.n_active = cnt[0] + cnt[1];
+  }
 }
 
 // findChild (node.go:288-298): first child with the wanted move, or -1
@@ -252,7 +255,8 @@ __global__ void k_search_begin(GameP P, EngineDev E, int n_games) {
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
   if (g >= n_games) return;
   int* gi = E.gi + (size_t)g * GI_COUNT;
-  int* wv = E.wv + (size_t)g * WV_COUNT;
+  int* wv = WV_OF(E, g, 0);
+  for (int l = 1 + lane; l < E.V; l += 32) WV_OF(E, g, l)[WV_STATUS] = ST_IDLE;  // the root preparation is worker 0's
   if (!gi[GI_ACTIVE]) { if (lane == 0) wv[WV_STATUS] = ST_IDLE; return; }
   WS w = make_ws(P, E.cellsP, smem + (size_t)wib * ws_bytes(P, E.cellsP));
   const uint8_t* gb = E.board + (size_t)g * E.cellsP;
@@ -322,7 +326,7 @@ __global__ void k_search_begin(GameP P, EngineDev E, int n_games) {
     wv[WV_TREE] = t; wv[WV_PLAYER] = player; wv[WV_HASH] = (int)hash;
     wv[WV_FLAGS] = 1;  // root preparation wave
     wv[WV_PATHLEN] = 1;
-    E.path[(size_t)g * (P.maxDepth + 1)] = root;
+    E.path[(size_t)g * E.V * (P.maxDepth + 1)] = root;
   }
   // ---- prepareRoot (search.go:392-408)
   const bool hadChildren = META_NCHILD(rmeta) > 0;
@@ -330,7 +334,7 @@ __global__ void k_search_begin(GameP P, EngineDev E, int n_games) {
   const int passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
   if (expandable && passes < 2) {
     // leaf request on the root state
-    uint8_t* lb = E.leaf_board + (size_t)g * E.cellsP;
+    uint8_t* lb = E.leaf_board + (size_t)g * E.V * E.cellsP;
     for (int i = lane; i < P.cells; i += 32) lb[i] = w.board[i];
     if (lane == 0) {
       wv[WV_STATUS] = ST_LEAF; wv[WV_TO_MOVE] = player; wv[WV_MOVE_NUMBER] = mn; wv[WV_PASSES] = passes;
@@ -351,137 +355,163 @@ __global__ void k_encode_roots(GameP P, EngineDev E, int n_games) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
   if (g >= n_games) return;
-  const int* wv = E.wv + (size_t)g * WV_COUNT;
+  const int* wv = WV_OF(E, g, 0);
   if (wv[WV_STATUS] != ST_LEAF) return;
   const int agent = wv[WV_AGENT];
   if (E.inf[agent].kind != INF_DUAL) return;
-  float* out = E.nn_in + ((size_t)agent * E.G + wv[WV_SLOT]) * P.plane;
+  float* out = E.nn_in + ((size_t)agent * E.GS + wv[WV_SLOT]) * P.plane;
   encode_planes(P, E.board + (size_t)g * E.cellsP, E.hist + (size_t)g * 8 * E.cellsP, E.cellsP, wv[WV_TO_MOVE],
                 wv[WV_MOVE_NUMBER], out, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: one pipeline() descent per game (search.go:209-248).
+// K1: the descent part of pipeline() (search.go:209-248), one warp per game.  With mcts.Config workers = V > 1 the
+// warp starts V pipeline calls one after the other (the fixed interleaving of the reference's concurrent
+// searchStates, include/agogo_b200.h): each sets the virtual-loss flag on its path (search.go:222, node.go:248-253)
+// and stops at the leaf it wants evaluated; null results and two-pass terminals complete at once and clear their flags.
 __global__ void k_select(GameP P, EngineDev E, int n_games) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
+  const int workers = E.V > 1 ? min(*E.round_workers, E.V) : 1;
+  if (E.V > 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+    E.batch_count[0] = E.batch_count[2] * workers;
+    E.batch_count[1] = E.batch_count[3] * workers;
+  }
   if (g >= n_games) return;
   int* gi = E.gi + (size_t)g * GI_COUNT;
-  int* wv = E.wv + (size_t)g * WV_COUNT;
-  if (!gi[GI_ACTIVE]) { if (lane == 0) wv[WV_STATUS] = ST_IDLE; return; }
+  int* wv0 = WV_OF(E, g, 0);
+  if (!gi[GI_ACTIVE]) { for (int l = lane; l < E.V; l += 32) WV_OF(E, g, l)[WV_STATUS] = ST_IDLE; return; }
+  for (int l = workers + lane; l < E.V; l += 32) WV_OF(E, g, l)[WV_STATUS] = ST_IDLE;
   WS w = make_ws(P, E.cellsP, smem + (size_t)wib * ws_bytes(P, E.cellsP));
   const uint8_t* gb = E.board + (size_t)g * E.cellsP;
-  for (int i = lane; i < P.cells; i += 32) w.board[i] = gb[i];
-  if (P.hist_len) {
-    const uint8_t* gh = E.hist + (size_t)g * 8 * E.cellsP;
-    for (int i = lane; i < 8 * E.cellsP; i += 32) w.hist[i] = gh[i];
-  }
-  __syncwarp();
-  const int t = wv[WV_TREE];
+  const int t = wv0[WV_TREE];
+  const int agent = wv0[WV_AGENT];
+  const int slot0 = wv0[WV_SLOT], slot_stride = E.batch_count[2 + agent];
   const size_t tb = ((size_t)g * E.T + t) * (size_t)P.max_nodes;
   const int* ti = E.ti + ((size_t)g * E.T + t) * TI_COUNT;
-  int* path = E.path + (size_t)g * (P.maxDepth + 1);
-  St s;
-  s.to_move = gi[GI_TO_MOVE];
-  s.move_number = gi[GI_MOVE_NUMBER];
-  s.passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
-  int node = ti[TI_ROOT];
-  int depth = 0, path_len = 0;
-  int status = ST_DONE;
-  bool is_null = true;
-  bool analyzed = false;
-  unsigned long long sel_children = 0, sel_levels = 0;
-  if (lane == 0) wv[WV_FLAGS] = 0;
+  uint8_t* vl = E.vl ? E.vl + tb : nullptr;
+  if (lane == 0) wv0[WV_FLAGS] = 0;
 
-  while (true) {
-    depth++;
-    if (depth > P.maxDepth) break;  // search.go:211-215: null result, nothing on the path is updated
-    const int player = s.to_move;
-    if (lane == 0) path[path_len] = node;
-    path_len++;
-    const uint32_t meta = E.meta[tb + node];
-    if (!META_EXPANDED(meta)) {
-      if (s.passes >= 2) {  // search.go:226-228: terminal by passes -> combinedScore (utils.go:62-67)
-        float ws_ = game_score(P, w.board, C_WHITE, lane);
-        float bs_ = game_score(P, w.board, C_BLACK, lane);
-        float v = __fsub_rn(__fsub_rn(bs_, ws_), P.komi);
-        __syncwarp();
-        backup(E, tb, path, path_len, v, lane);
-        is_null = false;
-      } else {
-        // leaf: hand the state to the evaluator
-        uint8_t* lb = E.leaf_board + (size_t)g * E.cellsP;
-        for (int i = lane; i < P.cells; i += 32) lb[i] = w.board[i];
-        const int agent = wv[WV_AGENT];
-        if (E.inf[agent].kind == INF_DUAL) {
-          float* out = E.nn_in + ((size_t)agent * E.G + wv[WV_SLOT]) * P.plane;
-          encode_planes(P, w.board, w.hist, E.cellsP, s.to_move, s.move_number, out, lane);
+  for (int wk = 0; wk < workers; wk++) {
+    int* wv = WV_OF(E, g, wk);
+    __syncwarp();
+    for (int i = lane; i < P.cells; i += 32) w.board[i] = gb[i];
+    if (P.hist_len) {
+      const uint8_t* gh = E.hist + (size_t)g * 8 * E.cellsP;
+      for (int i = lane; i < 8 * E.cellsP; i += 32) w.hist[i] = gh[i];
+    }
+    __syncwarp();
+    int* path = E.path + ((size_t)g * E.V + wk) * (P.maxDepth + 1);
+    St s;
+    s.to_move = gi[GI_TO_MOVE];
+    s.move_number = gi[GI_MOVE_NUMBER];
+    s.passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
+    int node = ti[TI_ROOT];
+    int depth = 0, path_len = 0;
+    int status = ST_DONE;
+    bool is_null = true;
+    bool analyzed = false;
+    unsigned long long sel_children = 0, sel_levels = 0;
+
+    while (true) {
+      depth++;
+      if (depth > P.maxDepth) break;  // search.go:211-215: null result, nothing on the path is updated
+      const int player = s.to_move;
+      if (lane == 0) { path[path_len] = node; if (vl) vl[node] = 1; }
+      path_len++;
+      const uint32_t meta = E.meta[tb + node];
+      if (!META_EXPANDED(meta)) {
+        if (s.passes >= 2) {  // search.go:226-228: terminal by passes -> combinedScore (utils.go:62-67)
+          float ws_ = game_score(P, w.board, C_WHITE, lane);
+          float bs_ = game_score(P, w.board, C_BLACK, lane);
+          float v = __fsub_rn(__fsub_rn(bs_, ws_), P.komi);
+          __syncwarp();
+          backup(E, tb, path, path_len, v, lane);
+          is_null = false;
+        } else {
+          // leaf: hand the state to the evaluator
+          uint8_t* lb = E.leaf_board + ((size_t)g * E.V + wk) * E.cellsP;
+          for (int i = lane; i < P.cells; i += 32) lb[i] = w.board[i];
+          if (E.inf[agent].kind == INF_DUAL) {
+            float* out = E.nn_in + ((size_t)agent * E.GS + slot0 + (size_t)wk * slot_stride) * P.plane;
+            encode_planes(P, w.board, w.hist, E.cellsP, s.to_move, s.move_number, out, lane);
+          }
+          if (lane == 0) { wv[WV_TO_MOVE] = s.to_move; wv[WV_MOVE_NUMBER] = s.move_number; wv[WV_PASSES] = s.passes; }
+          status = ST_LEAF;
+          is_null = false;
         }
-        if (lane == 0) { wv[WV_TO_MOVE] = s.to_move; wv[WV_MOVE_NUMBER] = s.move_number; wv[WV_PASSES] = s.passes; }
-        status = ST_LEAF;
-        is_null = false;
+        break;
       }
-      break;
-    }
-    // ---- Node.Select (node.go:170-237).  Child blocks start on a 4-node boundary, so each lane pulls
-    // four consecutive children's N / W / P with one 128-bit load per array (coalesced 512 B per warp).
-    const int nc = META_NCHILD(meta), first = E.first[tb + node];
-    const uint32_t* Nb = E.N + tb + first;
-    const float* Wb = E.W + tb + first;
-    const float* Pb = E.Pr + tb + first;
-    uint32_t pv = 0;
-    for (int j0 = lane * 4; j0 < nc; j0 += 128) {
-      const uint4 n4 = *reinterpret_cast<const uint4*>(Nb + j0);
-      pv += n4.x;
-      if (j0 + 1 < nc) pv += n4.y;
-      if (j0 + 2 < nc) pv += n4.z;
-      if (j0 + 3 < nc) pv += n4.w;
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) pv += __shfl_xor_sync(FULL, pv, off);
-    const float numerator = __fsqrt_rn(__uint2float_rn(pv));
-    float bestv = -INFINITY;
-    int besti = 0x7fffffff;
-    for (int j0 = lane * 4; j0 < nc; j0 += 128) {
-      const uint4 n4 = *reinterpret_cast<const uint4*>(Nb + j0);
-      const float4 w4 = *reinterpret_cast<const float4*>(Wb + j0);
-      const float4 p4 = *reinterpret_cast<const float4*>(Pb + j0);
-      const uint32_t nn[4] = {n4.x, n4.y, n4.z, n4.w};
-      const float ww[4] = {w4.x, w4.y, w4.z, w4.w};
-      const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (j0 + i >= nc) break;
-        const uint32_t visits = nn[i];
-        const float qsa = evaluate(ww[i], visits, player);  // visits >= 1 always (tree.go:110): fpu is dead
-        const float denominator = __fadd_rn(1.0f, __uint2float_rn(visits));
-        const float lastTerm = __fdiv_rn(numerator, denominator);
-        const float puct = __fmul_rn(__fmul_rn(P.puct, pp[i]), lastTerm);
-        const float usa = __fadd_rn(qsa, puct);
-        if (usa > bestv) { bestv = usa; besti = j0 + i; }  // strict >: earliest child wins ties
+      // ---- Node.Select (node.go:170-237).  Child blocks start on a 4-node boundary, so each lane pulls
+      // four consecutive children's N / W / P with one 128-bit load per array (coalesced 512 B per warp).
+      const int nc = META_NCHILD(meta), first = E.first[tb + node];
+      const uint32_t* Nb = E.N + tb + first;
+      const float* Wb = E.W + tb + first;
+      const float* Pb = E.Pr + tb + first;
+      uint32_t pv = 0;
+      for (int j0 = lane * 4; j0 < nc; j0 += 128) {
+        const uint4 n4 = *reinterpret_cast<const uint4*>(Nb + j0);
+        pv += n4.x;
+        if (j0 + 1 < nc) pv += n4.y;
+        if (j0 + 2 < nc) pv += n4.z;
+        if (j0 + 3 < nc) pv += n4.w;
       }
-    }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) {
-      float ov = __shfl_xor_sync(FULL, bestv, off);
-      int oi = __shfl_xor_sync(FULL, besti, off);
-      if (oi != 0x7fffffff && (besti == 0x7fffffff || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+      for (int off = 16; off; off >>= 1) pv += __shfl_xor_sync(FULL, pv, off);
+      const float numerator = __fsqrt_rn(__uint2float_rn(pv));
+      float bestv = -INFINITY;
+      int besti = 0x7fffffff;
+      for (int j0 = lane * 4; j0 < nc; j0 += 128) {
+        const uint4 n4 = *reinterpret_cast<const uint4*>(Nb + j0);
+        const float4 w4 = *reinterpret_cast<const float4*>(Wb + j0);
+        const float4 p4 = *reinterpret_cast<const float4*>(Pb + j0);
+        const uint32_t nn[4] = {n4.x, n4.y, n4.z, n4.w};
+        float ww[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float pp[4] = {p4.x, p4.y, p4.z, p4.w};
+        if (vl && player == C_WHITE) {  // Node.Evaluate: blackScores += VirtualLoss() for White only (node.go:150-152)
+          const uint32_t f4 = *reinterpret_cast<const uint32_t*>(vl + first + j0);
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if ((f4 >> (8 * i)) & 0xffu) ww[i] = __fadd_rn(ww[i], 3.0f);  // virtualLoss1, mcts.go:27
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (j0 + i >= nc) break;
+          const uint32_t visits = nn[i];
+          const float qsa = evaluate(ww[i], visits, player);  // visits >= 1 always (tree.go:110): fpu is dead
+          const float denominator = __fadd_rn(1.0f, __uint2float_rn(visits));
+          const float lastTerm = __fdiv_rn(numerator, denominator);
+          const float puct = __fmul_rn(__fmul_rn(P.puct, pp[i]), lastTerm);
+          const float usa = __fadd_rn(qsa, puct);
+          if (usa > bestv) { bestv = usa; besti = j0 + i; }  // strict >: earliest child wins ties
+        }
+      }
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        float ov = __shfl_xor_sync(FULL, bestv, off);
+        int oi = __shfl_xor_sync(FULL, besti, off);
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || ov > bestv || (ov == bestv && oi < besti))) { bestv = ov; besti = oi; }
+      }
+      sel_children += nc;
+      sel_levels++;
+      if (besti == 0x7fffffff) { raise(E, ERR_NO_ACTIVE_CHILD, lane); break; }
+      const int next = first + besti;
+      const int move = META_MOVE(E.meta[tb + next]);
+      if (!state_check(P, w, player, move, lane, &analyzed)) break;  // illegal: null result, no retry
+      state_apply(P, w, E.cellsP, s, player, move, lane, &analyzed, nullptr, nullptr);
+      node = next;
     }
-    sel_children += nc;
-    sel_levels++;
-    if (besti == 0x7fffffff) { raise(E, ERR_NO_ACTIVE_CHILD, lane); break; }
-    const int next = first + besti;
-    const int move = META_MOVE(E.meta[tb + next]);
-    if (!state_check(P, w, player, move, lane, &analyzed)) break;  // illegal: null result, no retry
-    state_apply(P, w, E.cellsP, s, player, move, lane, &analyzed, nullptr, nullptr);
-    node = next;
+    if (vl && status != ST_LEAF) {  // the call returned: undoVirtualLoss on every node it entered (search.go:254)
+      __syncwarp();
+      for (int i = lane; i < path_len; i += 32) vl[path[i]] = 0;
+    }
+    count(E, CNT_SIMS, 1, lane);
+    count(E, CNT_NULL, is_null ? 1 : 0, lane);
+    count(E, CNT_SEL_CHILDREN, sel_children, lane);
+    count(E, CNT_SEL_LEVELS, sel_levels, lane);
+    if (lane == 0) { wv[WV_STATUS] = status; wv[WV_PATHLEN] = path_len; }
   }
-  count(E, CNT_SIMS, 1, lane);
-  count(E, CNT_NULL, is_null ? 1 : 0, lane);
-  count(E, CNT_SEL_CHILDREN, sel_children, lane);
-  count(E, CNT_SEL_LEVELS, sel_levels, lane);
-  if (lane == 0) { wv[WV_STATUS] = status; wv[WV_PATHLEN] = path_len; }
 }
 
 // dummy.go / scripted-table evaluators, run on device for every pending leaf
@@ -489,22 +519,26 @@ __global__ void k_infer_simple(GameP P, EngineDev E, int n_games) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
   if (g >= n_games) return;
-  const int* wv = E.wv + (size_t)g * WV_COUNT;
-  if (wv[WV_STATUS] != ST_LEAF) return;
-  const int agent = wv[WV_AGENT];
+  const int* wv0 = WV_OF(E, g, 0);
+  const int agent = wv0[WV_AGENT];
   const InfererDev inf = E.inf[agent];
   if (inf.kind == INF_DUAL) return;
-  float* pol = E.policy + ((size_t)agent * E.G + wv[WV_SLOT]) * E.Lmax;
-  float* val = E.value + (size_t)agent * E.G + wv[WV_SLOT];
-  if (inf.kind == INF_DUMMY) {
-    float p = __fdiv_rn(1.0f, (float)inf.L);
-    for (int i = lane; i < inf.L; i += 32) pol[i] = p;
-    if (lane == 0) *val = inf.dummy_value;
-  } else {
-    int mn = wv[WV_MOVE_NUMBER];
-    bool ok = mn >= 0 && mn < inf.table_rows;
-    for (int i = lane; i < inf.L; i += 32) pol[i] = ok ? inf.table[(size_t)mn * inf.L + i] : 0.0f;
-    if (lane == 0) *val = ok ? inf.table_values[mn] : 0.0f;
+  for (int wk = 0; wk < E.V; wk++) {
+    const int* wv = WV_OF(E, g, wk);
+    if (wv[WV_STATUS] != ST_LEAF) continue;
+    const size_t slot = (size_t)agent * E.GS + wv0[WV_SLOT] + (size_t)wk * E.batch_count[2 + agent];
+    float* pol = E.policy + slot * E.Lmax;
+    float* val = E.value + slot;
+    if (inf.kind == INF_DUMMY) {
+      float p = __fdiv_rn(1.0f, (float)inf.L);
+      for (int i = lane; i < inf.L; i += 32) pol[i] = p;
+      if (lane == 0) *val = inf.dummy_value;
+    } else {
+      int mn = P.kind == KIND_C4 ? 1 : wv[WV_MOVE_NUMBER];  // c4/game.go:51: MoveNumber() is moveCount + 1, never advanced
+      bool ok = mn >= 0 && mn < inf.table_rows;
+      for (int i = lane; i < inf.L; i += 32) pol[i] = ok ? inf.table[(size_t)mn * inf.L + i] : 0.0f;
+      if (lane == 0) *val = ok ? inf.table_values[mn] : 0.0f;
+    }
   }
 }
 
@@ -515,29 +549,37 @@ __global__ void k_expand_backup(GameP P, EngineDev E, int n_games) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
   if (g >= n_games) return;
-  int* wv = E.wv + (size_t)g * WV_COUNT;
-  if (wv[WV_STATUS] != ST_LEAF) return;
+  const int* wv0 = WV_OF(E, g, 0);
   WS w = make_ws(P, E.cellsP, smem + (size_t)wib * ws_bytes(P, E.cellsP));
-  const uint8_t* lb = E.leaf_board + (size_t)g * E.cellsP;
-  for (int i = lane; i < P.cells; i += 32) w.board[i] = lb[i];
-  __syncwarp();
-  const int agent = wv[WV_AGENT], slot = wv[WV_SLOT], t = wv[WV_TREE];
+  const int agent = wv0[WV_AGENT], t = wv0[WV_TREE];
   const int L = E.inf[agent].L;
-  const float* pol = E.policy + ((size_t)agent * E.G + slot) * E.Lmax;
-  float value = E.value[(size_t)agent * E.G + slot];
-  const int player = wv[WV_TO_MOVE];
-  if (player == C_WHITE) value = __fsub_rn(1.0f, value);  // search.go:278-280
   const size_t tb = ((size_t)g * E.T + t) * (size_t)P.max_nodes;
   int* ti = E.ti + ((size_t)g * E.T + t) * TI_COUNT;
-  const int* path = E.path + (size_t)g * (P.maxDepth + 1);
+  // pending workers finish in start order (with V == 1: the one descent of this wave)
+  for (int wk = 0; wk < E.V; wk++) {
+  int* wv = WV_OF(E, g, wk);
+  __syncwarp();
+  if (wv[WV_STATUS] != ST_LEAF) continue;
+  const uint8_t* lb = E.leaf_board + ((size_t)g * E.V + wk) * E.cellsP;
+  for (int i = lane; i < P.cells; i += 32) w.board[i] = lb[i];
+  __syncwarp();
+  const size_t slot = (size_t)agent * E.GS + wv0[WV_SLOT] + (size_t)wk * E.batch_count[2 + agent];
+  const float* pol = E.policy + slot * E.Lmax;
+  float value = E.value[slot];
+  const int player = wv[WV_TO_MOVE];
+  if (player == C_WHITE) value = __fsub_rn(1.0f, value);  // search.go:278-280
+  const int* path = E.path + ((size_t)g * E.V + wk) * (P.maxDepth + 1);
   const int path_len = wv[WV_PATHLEN];
   const int leaf = path[path_len - 1];
   count(E, CNT_EVALS, 1, lane);
+  // a worker that reached a leaf an earlier worker of this round has expanded meanwhile: every candidate is found
+  // by findChild / oldMinPsa is 0 (search.go:316-325) — nothing is created, the value is still backed up
+  const bool already = META_EXPANDED(E.meta[tb + leaf]) != 0;
 
   // legal list in index order, then Pass (search.go:285-296)
-  if (P.kind == KIND_WQ) wq_analyze(P, w.board, w.wq, lane);
+  if (P.kind == KIND_WQ && !already) wq_analyze(P, w.board, w.wq, lane);
   int nleg = 0;
-  for (int base = 0; base < P.A; base += 32) {
+  for (int base = 0; base < (already ? 0 : P.A); base += 32) {
     int i = base + lane;
     bool legal = false;
     if (i < P.A) {
@@ -552,7 +594,7 @@ __global__ void k_expand_backup(GameP P, EngineDev E, int n_games) {
     }
     nleg += __popc(m);
   }
-  if (P.kind != KIND_MNK) {  // Check(Pass): c4/game.go:53 and wq/game.go:69 accept, mnk.go:102 rejects
+  if (P.kind != KIND_MNK && !already) {  // Check(Pass): c4/game.go:53 and wq/game.go:69 accept, mnk.go:102 rejects
     if (lane == 0) { w.fa[nleg] = pol[L - 1]; w.ia[nleg] = MV_PASS; }
     nleg++;
   }
@@ -616,7 +658,9 @@ __global__ void k_expand_backup(GameP P, EngineDev E, int n_games) {
   }
   __syncwarp();
   backup(E, tb, path, path_len, value, lane);
+  if (E.vl) for (int i = lane; i < path_len; i += 32) E.vl[tb + path[i]] = 0;  // undoVirtualLoss (search.go:254)
   if (lane == 0) wv[WV_STATUS] = ST_DONE;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -627,7 +671,7 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
   if (g >= n_games) return;
   int* gi = E.gi + (size_t)g * GI_COUNT;
-  int* wv = E.wv + (size_t)g * WV_COUNT;
+  int* wv = WV_OF(E, g, 0);
   if (lane == 0) E.ex_valid[g] = 0;
   if (!gi[GI_ACTIVE]) return;
   WS w = make_ws(P, E.cellsP, smem + (size_t)wib * ws_bytes(P, E.cellsP));

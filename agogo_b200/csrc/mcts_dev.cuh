@@ -24,6 +24,7 @@ enum { INF_DUAL = 0, INF_DUMMY = 1, INF_TABLE = 2 };
 enum { CNT_SEARCHES, CNT_SIMS, CNT_NULL, CNT_EVALS, CNT_SEL_CHILDREN, CNT_SEL_LEVELS, CNT_CREATED, CNT_BACKUP,
        CNT_COUNT = 16 };
 
+#define WV_OF(E, g, l) ((E).wv + ((size_t)(g) * (E).V + (l)) * WV_COUNT)
 #define META_MOVE(m) ((int)((m) & 0xFFFFu) - 2)
 #define META_NCHILD(m) ((int)(((m) >> 16) & 0x7FFFu))
 #define META_EXPANDED(m) (((m) >> 31) & 1u)
@@ -56,7 +57,7 @@ struct EngineDev {
   int32_t* path;        // [G][maxDepth+1]
   uint8_t* leaf_board;  // [G][cellsP]
   // evaluation batches, one per agent
-  int32_t* batch_count;  // [2]
+  int32_t* batch_count;  // [4]: [0..1] evaluation batch sizes, [2..3] active games per agent
   float* nn_in;          // [2][G][plane]   fp32 planes, NCHW
   float* policy;         // [2][G][Lmax]
   float* value;          // [2][G]
@@ -71,6 +72,11 @@ struct EngineDev {
   unsigned long long* counters;  // [CNT_COUNT]
   int32_t* n_active;      // [1]
   int cellsP, T, Lmax, G;
+  // concurrent pipeline calls per tree (mcts.Config workers, search.go:112-130): every per-wave record exists V
+  // times per game, evaluation batches hold GS = G*V slots per agent (slot = rank + worker * active games of the agent)
+  int V, GS;
+  uint8_t* vl;                 // [G*T][max_nodes] virtual-loss flags (node.go:41), nullptr when V == 1
+  const int32_t* round_workers;  // [1] workers started in the current round (the last round of a search may be short)
   unsigned long long tree_seed;  // MCTS.rand seed (tree.go:84), injected
   InfererDev inf[2];
 };

@@ -86,6 +86,7 @@ class MCTSConfig:
     ResignPercentage: float = 0.0
     PassPreference: int = K.DONT_PREFER_PASS
     Sims: int = 100
+    Workers: int = 0  # concurrent pipeline calls per tree (the reference: runtime.NumCPU()); 0/1 = canonical single worker
 
     def IsValid(self):  # tree.go:43-45
         return 0 < self.PUCT <= 1
@@ -190,7 +191,7 @@ class AZ:
         d.game = K.GameDesc(game.kind, game.m, game.n, game.k, game.komi, game.max_moves, game.zobrist_seed)
         m, n = conf.MCTSConf, conf.NNConf
         d.mcts = K.MCTSConfig(m.PUCT, m.Timeout, m.M, m.N, m.RandomCount, m.Budget, m.RandomMinVisits,
-                              m.RandomTemperature, int(m.DumbPass), m.ResignPercentage, m.PassPreference, m.Sims)
+                              m.RandomTemperature, int(m.DumbPass), m.ResignPercentage, m.PassPreference, m.Sims, m.Workers)
         d.nn = K.DualConfig(n.K, n.SharedLayers, n.FC, n.L2, n.BatchSize, n.Width, n.Height, n.Features, n.ActionSpace,
                             int(n.FwdOnly))
         d.encoder, d.n_games, d.device, d.flags = conf.Encoder, self.n_games, device, flags

@@ -31,6 +31,7 @@ type Desc struct {
 	NN            dual.Config
 	MCTS          mcts.Config
 	Sims          int
+	Workers       int // concurrent pipeline calls per tree (0/1 = canonical single worker)
 	Encoder       int
 	Games, Device int
 	Seed          uint64
@@ -64,6 +65,7 @@ func New(d Desc) *Engine {
 		cd.mcts.dumb_pass = 1
 	}
 	cd.mcts.resign_percentage, cd.mcts.pass_preference, cd.mcts.sims = C.float(m.ResignPercentage), C.int32_t(m.PassPreference), C.int32_t(d.Sims)
+	cd.mcts.workers = C.int32_t(d.Workers)
 	n := d.NN
 	cd.nn.k, cd.nn.shared_layers, cd.nn.fc, cd.nn.l2 = C.int32_t(n.K), C.int32_t(n.SharedLayers), C.int32_t(n.FC), C.double(n.L2)
 	cd.nn.batch_size, cd.nn.width, cd.nn.height, cd.nn.features = C.int32_t(n.BatchSize), C.int32_t(n.Width), C.int32_t(n.Height), C.int32_t(n.Features)

@@ -63,7 +63,14 @@ typedef struct az_game_desc {
 } az_game_desc;
 
 /* mcts.Config, mcts/tree.go:15-29, field for field; `sims` is new: the fixed number of
- * pipeline iterations per Search (the reference stops on Timeout only, search.go:133). */
+ * pipeline iterations per Search (the reference stops on Timeout only, search.go:133).
+ * `workers` is the number of concurrent pipeline calls per tree — the reference starts
+ * runtime.NumCPU() searchStates (search.go:112-130) whose interleaving Go leaves unspecified;
+ * here they run under one fixed schedule: rounds of `workers` descents that each set the
+ * virtual-loss flag on their path (search.go:222) and stop at the leaf they want evaluated, ONE
+ * batched inference for the round, then expansion + Update + undoVirtualLoss in start order.
+ * 0 or 1 = the canonical single worker (bit-exact tree for a given seed); > 1 multiplies the
+ * evaluation batch of a single position by `workers` (Agent.Search on one state, GTP play). */
 typedef struct az_mcts_config {
   float puct;
   int64_t timeout_ns;
@@ -76,6 +83,7 @@ typedef struct az_mcts_config {
   float resign_percentage;
   int32_t pass_preference; /* mcts/mcts.go:31-38 */
   int32_t sims;
+  int32_t workers;
 } az_mcts_config;
 
 /* dual.Config, dualnet/config.go:4-16, field for field. */

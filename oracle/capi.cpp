@@ -61,7 +61,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     e->mc.PUCT = m.puct; e->mc.Timeout = m.timeout_ns; e->mc.M = m.m; e->mc.N = m.n;
     e->mc.RandomCount = m.random_count; e->mc.Budget = m.budget; e->mc.RandomMinVisits = m.random_min_visits;
     e->mc.RandomTemperature = m.random_temperature; e->mc.DumbPass = m.dumb_pass != 0;
-    e->mc.ResignPercentage = m.resign_percentage; e->mc.PassPref = m.pass_preference; e->mc.Sims = m.sims;
+    e->mc.ResignPercentage = m.resign_percentage; e->mc.PassPref = m.pass_preference; e->mc.Sims = m.sims; e->mc.Workers = m.workers > 1 ? m.workers : 1;
     const az_dual_config& n = desc->nn;
     e->dc.K = n.k; e->dc.SharedLayers = n.shared_layers; e->dc.FC = n.fc; e->dc.L2 = n.l2;
     e->dc.BatchSize = n.batch_size; e->dc.Width = n.width; e->dc.Height = n.height; e->dc.Features = n.features;

@@ -39,6 +39,7 @@ struct MCTSConfig {  // mcts/tree.go:15-29 (+ Sims: the fixed-iteration mode the
   float ResignPercentage = 0;
   int PassPref = DontPreferPass;
   int Sims = 0;
+  int Workers = 1;  // concurrent pipeline calls per tree (the reference starts runtime.NumCPU(), search.go:112-130)
   bool IsValid() const { return PUCT > 0 && PUCT <= 1; }  // tree.go:43-45
 };
 
@@ -276,7 +277,68 @@ struct MCTS {
     prepareRoot(player, *current);
     depth = 0;
   }
+  // Workers > 1: the reference's concurrent searchStates under ONE fixed interleaving (its goroutine schedule is
+  // otherwise unspecified).  A round starts `Workers` pipeline calls one after the other; each descends, setting the
+  // virtual-loss flag on its path (search.go:222), until it needs an inference — the slow step during which the
+  // next worker runs.  Null results and two-pass terminals complete (and clear their flags) on the spot.  Then the
+  // pending workers finish in start order: expansion (children already present are found by findChild /
+  // oldMinPsa = 0, search.go:318-325), Update along the path, undoVirtualLoss (a store of 0, node.go:255-260).
+  struct Pending { std::vector<int> path; std::unique_ptr<State> st; bool hadChildren; };
+  void finishPath(const std::vector<int>& path, float ret) {
+    for (size_t i = path.size(); i-- > 0;) {
+      if (!isNullResult(ret)) Update(path[i], ret);
+      nodes[path[i]].virtualLoss = 0;
+    }
+  }
+  void SearchRunWorkers(int iterations, int workers) {
+    int left = iterations;
+    while (left > 0) {
+      const int v = std::min(workers, left);
+      left -= v;
+      std::vector<Pending> pend;
+      for (int l = 0; l < v; l++) {
+        std::unique_ptr<State> cur(current->Clone());
+        std::vector<int> path;
+        int node = root, d = 0;
+        float ret = noResult();
+        bool pending = false;
+        while (true) {
+          d++;
+          if (d > maxDepth) break;  // search.go:211-215
+          Player player = cur->ToMove();
+          nodes[node].virtualLoss = 3.0f;
+          path.push_back(node);
+          bool isExpandable = IsExpandable(nodes[node], 0);
+          if (isExpandable && cur->Passes() >= 2) { ret = combinedScore(*cur); break; }
+          if (isExpandable && nc < MAXTREESIZE && IsExpandable(nodes[node], minPsaRatio())) {  // search.go:229, 264, 269
+            Pending p; p.path = path; p.hadChildren = HasChildren(nodes[node]); p.st = std::move(cur);
+            if (p.hadChildren) throw std::runtime_error("partially expanded node under concurrent search");
+            pend.push_back(std::move(p));
+            pending = true;
+            break;
+          }
+          if (!HasChildren(nodes[node])) break;
+          int next = Select(node, player);
+          PlayerMove pm{player, nodes[next].move};
+          if (!cur->Check(pm)) break;
+          State* n = cur->Apply(pm);
+          if (n != cur.get()) cur.reset(n);
+          node = next;
+        }
+        cnt.sims++;
+        if (pending) { playouts++; continue; }
+        if (!isNullResult(ret)) playouts++; else cnt.null_results++;
+        finishPath(path, ret);
+      }
+      for (Pending& p : pend) {
+        float value; bool ok;
+        expandBody(p.path.back(), *p.st, minPsaRatio(), &value, &ok);
+        finishPath(p.path, ok ? value : noResult());
+      }
+    }
+  }
   void SearchRun(int iterations) {  // canonical doSearch (search.go:166-202): 1 worker, fixed count
+    if (conf.Workers > 1) { SearchRunWorkers(iterations, conf.Workers); return; }
     for (int it = 0; it < iterations; it++) {
       std::unique_ptr<State> cl(current->Clone());
       float res = pipeline(cl, root);
@@ -349,6 +411,10 @@ struct MCTS {
     *value = 0; *ok = false;
     if (!IsExpandable(nodes[parent], minPsaRatio_)) return;
     if (state.Passes() >= 2) return;
+    expandBody(parent, state, minPsaRatio_, value, ok);
+  }
+  // search.go:274-338: everything after the two early returns (a concurrent worker passed them at descent time)
+  void expandBody(int parent, const State& state, float minPsaRatio_, float* value, bool* ok) {
     std::vector<float> policy;
     nn->Infer(state, &policy, value);
     cnt.evals++;

@@ -89,6 +89,54 @@ def test_parity_wq_arena_dummy(oracle, engine_lib, size, sims, plies):
     H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "wq")
 
 
+@pytest.mark.parametrize("game,workers,sims", [
+    ("ttt", 2, 40), ("ttt", 8, 50), ("ttt", 64, 50), ("gomoku", 3, 25), ("c4", 4, 30), ("c4shared", 4, 30), ("wq5", 4, 26), ("wq9", 16, 40),
+])
+def test_parity_concurrent_workers(oracle, engine_lib, game, workers, sims):
+    """mcts.Config workers > 1 (the reference's concurrent searchStates, search.go:112-130, under the fixed schedule
+    of include/agogo_b200.h): rounds of `workers` descents with virtual-loss flags, one evaluation batch per round.
+    Trees after every ply, moves, examples and counters bit-identical to the oracle's restatement of the same
+    schedule; sims not a multiple of workers leaves a short last round; workers > sims runs a single round."""
+    def desc():
+        if game == "ttt":
+            return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=sims, nn=H.tiny_nn(3, 3, 10), n_games=8, seed=11, workers=workers)
+        if game == "gomoku":
+            return K.make_desc(K.GAME_MNK, 5, 5, 4, sims=sims, nn=H.tiny_nn(5, 5, 26), n_games=6, seed=3, workers=workers)
+        if game in ("c4", "c4shared"):
+            return K.make_desc(K.GAME_C4, 6, 7, 4, sims=sims, nn=H.tiny_nn(6, 7, 8), n_games=8, seed=5, workers=workers,
+                               flags=K.FLAG_SHARED_TREE if game == "c4shared" else 0)
+        size = 5 if game == "wq5" else 9
+        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=sims, n_games=4, seed=9, max_moves=30, workers=workers,
+                           nn=H.tiny_nn(size, size, size * size + 1, features=18))
+    eo, eg = _pair(oracle, engine_lib, desc)
+    n = eo.desc.n_games
+    rng = np.random.default_rng(7)
+    A1 = eo.desc.nn.action_space
+    table = rng.random((64, A1)).astype(np.float32)
+    table /= table.sum(axis=1, keepdims=True)
+    values = rng.uniform(0.05, 0.95, 64).astype(np.float32)
+    for e in (eo, eg):
+        if game in ("ttt", "wq9"):
+            e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+        else:  # scripted evaluator: policy and value depend on the leaf's move number -> distinct priors per depth
+            e.set_table(0, table, values); e.set_table(1, table[::-1].copy(), values[::-1].copy())
+    a, b = H.play_and_collect(eo, n), H.play_and_collect(eg, n)
+    H.assert_same_run(a, b, "workers-%s-%d" % (game, workers))
+    ca, cb = dict(a["counters"]), dict(b["counters"])
+    ca.pop("kernel_launches", None); cb.pop("kernel_launches", None)
+    assert ca == cb
+    assert ca["sims"] == ca["searches"] * sims
+
+
+def test_concurrent_workers_dual_net(oracle, engine_lib):
+    """The same schedule with the dual network in the loop (fp32 tower): batch = games x workers per round."""
+    def desc():
+        return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=24, nn=H.tiny_nn(3, 3, 10, k=4, layers=2, fc=8), n_games=4, seed=2,
+                           workers=6, flags=K.FLAG_FP32_TOWER)
+    eo, eg = _dual_pair(oracle, engine_lib, desc)
+    H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "workers-dual", float_ulps=64)
+
+
 def test_wq_random_rules_vs_oracle(oracle, engine_lib):
     """Board.check / Board.Apply on random (also inconsistent) 7x7 positions, every point, both colours."""
     rng = np.random.default_rng(1)
