@@ -290,6 +290,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     if (const char* ng = getenv("AZ_NO_GRAPH")) e->graphs_enabled = !(ng[0] == '1');
     e->coin_state = derive_seed(desc->seed, 0);
     mcts_set_smem_limits(P, E.cellsP);
+    heads_tiled_configure();
 
     NetDims nd;
     nd.K = n.k; nd.SharedLayers = n.shared_layers; nd.FC = n.fc; nd.B = n.batch_size; nd.W = n.width; nd.H = n.height;

@@ -5,6 +5,8 @@
 //   k_search_end     bestMove, cachedPolicies, Example, Apply, Ended         (search.go:341-390,152-161; arena.go:98-137)
 // Compiled with -fmad=false: the PUCT arithmetic must match Go/amd64 bit for bit (no FMA), and
 // every rounding-sensitive operation is additionally spelled with an explicit _rn intrinsic.
+#include <stdexcept>
+
 #include "mcts_dev.cuh"
 #include "rules.cuh"
 
@@ -963,15 +965,20 @@ __global__ void k_rules_status(GameP P, int cellsP, int n, const int* __restrict
 static inline dim3 grid_for(int n, int wpb) { return dim3((n + wpb - 1) / wpb); }
 static const int WPB = 4;
 
+// Raised to the device's opt-in maximum (not to this engine's need): the attribute is per function and per device,
+// and engines of different board sizes share both.
 void mcts_set_smem_limits(const GameP& P, int cellsP) {
-  int bytes = (int)(ws_bytes(P, cellsP) * WPB);
-  CUDA_CHECK(cudaFuncSetAttribute(k_arena_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(k_search_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(k_expand_backup, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(k_search_end, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(k_rules_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  CUDA_CHECK(cudaFuncSetAttribute(k_rules_status, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  int dev = 0, optin = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if ((int)(ws_bytes(P, cellsP) * WPB) > optin) throw std::runtime_error("board too large for the per-warp shared-memory workspace");
+  CUDA_CHECK(cudaFuncSetAttribute(k_arena_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_search_begin, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_expand_backup, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_search_end, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_rules_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_rules_status, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
 #define SMEM(P, E) (ws_bytes(P, (E).cellsP) * WPB)
 void launch_arena_begin(const GameP& P, const EngineDev& E, int n_games, const int* coins, cudaStream_t s) {

@@ -62,5 +62,6 @@ void forward_fp32(const NetLayout& L, const Snapshot& s, Fp32Scratch& sc, const 
 void heads_fp32(const NetLayout& L, const Snapshot& s, Fp32Scratch& sc, const float* tower, const int* n_dev, int n_max,
                 float* policy, int ldp, float* value, cudaStream_t st, unsigned long long* launches);
 // heads from the post-1x1-unit activations ph [n,2*HW], vh [n,HW]: throughput version (SB samples per block)
+void heads_tiled_configure();
 void heads_tiled(const NetLayout& L, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
                  float* policy, int ldp, float* value, cudaStream_t st, unsigned long long* launches);

@@ -288,16 +288,18 @@ __global__ void k_heads_tiled(const float* __restrict__ ph, const float* __restr
   }
 }
 
+// per device, once per engine: opt-in maximum (engines of different head sizes share the function attribute)
+void heads_tiled_configure() {
+  int dev = 0, optin = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+}
 void heads_tiled(const NetLayout& L, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
                  float* policy, int ldp, float* value, cudaStream_t st, unsigned long long* launches) {
   const NetDims& d = L.d;
   constexpr int SB = 8;
   const size_t sm = (size_t)SB * (3 * d.HW() + d.A1 + d.FC) * 4;
-  static size_t configured = 0;
-  if (sm > configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    configured = sm;
-  }
   k_heads_tiled<SB><<<(n_max + SB - 1) / SB, 256, sm, st>>>(ph, vh, s.d + s.pW, s.d + s.pB, s.d + s.vW, s.d + s.vB, s.d + s.voW,
                                                           s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC);
   if (launches) (*launches)++;

@@ -620,6 +620,22 @@ CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk
   return m;
 }
 
+// dynamic shared memory opt-in of every instantiation, on the current device (the attribute is per function and per
+// device; called from the allocators, which run with the engine's device current)
+template <int BN, bool PAIR, int BKT>
+void set_conv_attr() {
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN, BKT)));
+}
+void tc_configure_device() {
+  set_conv_attr<256, true, 64>(); set_conv_attr<128, true, 64>(); set_conv_attr<256, false, 64>(); set_conv_attr<128, false, 64>();
+  set_conv_attr<64, false, 64>();
+  set_conv_attr<256, true, 32>(); set_conv_attr<128, true, 32>(); set_conv_attr<256, false, 32>(); set_conv_attr<128, false, 32>();
+  set_conv_attr<64, false, 32>();
+  CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256, 64)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128, 64)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64, 64)));
+}
+
 struct Layer {
   int cin, n_total, bn;
   bool pair;
@@ -649,11 +665,6 @@ struct Impl {
 template <int BN, bool PAIR, int BKT>
 void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                  const int* n_dev, int* err, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN, BKT)));
-    attr_set = true;
-  }
   ConvArgs a;
   a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
   a.mode3d = I.mode3d; a.tps = I.tps;
@@ -687,6 +698,7 @@ bool tc_tower_supported(const NetDims& d) {
 }
 
 void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2) {
+  tc_configure_device();
   Impl* I = new Impl;
   t.impl = I;
   I->d = d; I->n_max = n_max; I->ea = act_scale_log2;
@@ -960,6 +972,7 @@ struct TcGemmImpl {
 bool tc_gemm_supported(const NetDims& d) { return d.K == 64 || d.K == 128 || d.K == 256; }
 
 void tc_gemm_create(TcGemm& g, const NetDims& d, int B) {
+  tc_configure_device();
   TcGemmImpl* I = new TcGemmImpl;
   g.impl = I;
   I->d = d; I->B = B;
@@ -1036,9 +1049,6 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   const int max_tiles = ((I->B * I->S + BM - 1) / BM) * (Cout / bn);
   const int grid = std::min(I->num_sms, max_tiles);
   auto launch = [&](auto kern, int BNv) {
-    static bool set256 = false, set128 = false, set64 = false;
-    bool& flag = BNv == 256 ? set256 : (BNv == 128 ? set128 : set64);
-    if (!flag) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BNv, 64))); flag = true; }
     kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, a);
   };
   if (bn == 256) launch(k_conv3x3_tc<256, false, 64>, 256);
@@ -1074,9 +1084,6 @@ void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStrea
   const int items = 9 * a.co_tiles * a.ci_tiles * a.splits;
   const int grid = std::min(I->num_sms, items);
   auto launch = [&](auto kern, int BNv) {
-    static bool set256 = false, set128 = false, set64 = false;
-    bool& flag = BNv == 256 ? set256 : (BNv == 128 ? set128 : set64);
-    if (!flag) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BNv, 64))); flag = true; }
     kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, a);
   };
   if (bn == 256) launch(k_dw_tc<256>, 256);

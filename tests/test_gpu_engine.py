@@ -137,6 +137,21 @@ def test_concurrent_workers_dual_net(oracle, engine_lib):
     H.assert_same_run(H.play_and_collect(eo, 4), H.play_and_collect(eg, 4), "workers-dual", float_ulps=64)
 
 
+def test_engines_of_different_sizes_coexist(oracle, engine_lib):
+    """Kernel attributes (dynamic shared memory opt-in) are per function and per device, not per engine: a small-board
+    engine created after a large-board one must not shrink what the large one needs."""
+    def big():
+        return K.make_desc(K.GAME_WQ, 9, 9, 0, komi=7.5, sims=8, n_games=2, seed=9, max_moves=12, nn=H.tiny_nn(9, 9, 82, features=18))
+    def small():
+        return K.make_desc(K.GAME_MNK, 3, 3, 3, sims=8, nn=H.tiny_nn(3, 3, 10), n_games=2, seed=1)
+    eo, eg = _pair(oracle, engine_lib, big)
+    so, sg = _pair(oracle, engine_lib, small)          # created while the 9x9 engines are alive
+    for e in (eo, eg, so, sg):
+        _setup_dummy(e)
+    H.assert_same_run(H.play_and_collect(so, 2), H.play_and_collect(sg, 2), "small")
+    H.assert_same_run(H.play_and_collect(eo, 2), H.play_and_collect(eg, 2), "big-after-small")
+
+
 def test_wq_random_rules_vs_oracle(oracle, engine_lib):
     """Board.check / Board.Apply on random (also inconsistent) 7x7 positions, every point, both colours."""
     rng = np.random.default_rng(1)
