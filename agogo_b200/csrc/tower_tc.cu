@@ -40,7 +40,10 @@ constexpr int BM = 128;        // M tile (TMEM lanes)
 constexpr int NTHREADS = 192;  // 6 warps
 __host__ __device__ constexpr int stage_bytes(int BN, int BKT) { return 2 * BM * BKT * 2 + 2 * BN * BKT * 2; }
 __host__ __device__ constexpr int num_stages(int BN, int BKT) { return 196608 / stage_bytes(BN, BKT) > 8 ? 8 : 196608 / stage_bytes(BN, BKT); }
-__host__ __device__ constexpr int smem_bytes(int BN, int BKT) { return num_stages(BN, BKT) * stage_bytes(BN, BKT) + 1024 + 256; }
+constexpr int AFF_BYTES = 4 * 2 * 4096;  // fused-pair epilogue: per epilogue warp two 32-row x 128-byte affine boxes (TMA, SWIZZLE_128B)
+__host__ __device__ constexpr int smem_bytes(int BN, int BKT, bool pair = false) {
+  return num_stages(BN, BKT) * stage_bytes(BN, BKT) + (pair ? AFF_BYTES : 0) + 1024 + 256;
+}
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -160,7 +163,8 @@ struct ConvArgs {
 template <int BN, bool PAIR, int BKT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, ConvArgs a) {
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+             const __grid_constant__ CUtensorMap tmAff, ConvArgs a) {
   constexpr int BK = BKT;
   constexpr int A_TILE_BYTES = BM * BK * 2;
   constexpr int STAGES = num_stages(BN, BKT);
@@ -171,17 +175,21 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;  // full[S], empty[S], tfull[2], tempty[2]
-  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES * STAGE_BYTES + 128);
+  constexpr int AFF = PAIR ? AFF_BYTES : 0;
+  const uint32_t aff_smem = smem_base + STAGES * STAGE_BYTES;  // PAIR: 4 warps x 2 x 4 KB affine boxes (1024-aligned)
+  const uint32_t bars = aff_smem + AFF;  // full[S], empty[S], tfull[2], tempty[2], afull[4][2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES * STAGE_BYTES + AFF + 240);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
   auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
+  auto afull_bar = [&](int quad, int buf) { return bars + 8u * (2 * STAGES + 4 + quad * 2 + buf); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int i = 0; i < 8; i++) mbar_init(afull_bar(i >> 1, i & 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -265,6 +273,27 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     uint32_t tcount = 0;
+    // Fused-pair layers: the per-(channel, point) affine of both branches ({A'a, Ba, A'b, Bb} per channel, rows = board
+    // positions in layout order) is staged through shared memory by TMA, 8 channels (= one 128-byte row) x this warp's
+    // 32 rows per box, double buffered and prefetched two boxes ahead across tiles.  (Reading it with per-thread global
+    // loads touches 32 cache lines per warp instruction: lane = row, 4 KB row pitch.)
+    constexpr int CH = OUTC / 8;  // boxes per tile
+    const uint32_t aff_buf = aff_smem + quad * 8192;
+    auto aff_issue = [&](uint32_t qq) {
+      if (!PAIR) return;
+      const int tile = blockIdx.x + (int)(qq / CH) * gridDim.x;
+      if (tile >= total_tiles) return;
+      const int j = qq % CH;
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int prow = a.mode3d ? (mt % a.tps) * BM + quad * 32 : (mt * BM + quad * 32) % a.S;
+      if (lane == 0) {
+        const uint32_t bar = afull_bar(quad, qq & 1);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(aff_buf + (qq & 1) * 4096, &tmAff, bar, (nt * OUTC + j * 8) * 4, prow);
+      }
+    };
+    aff_issue(0);
+    aff_issue(1);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
       const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
       const int m0 = mt * BM, n0 = nt * BN;
@@ -306,6 +335,33 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             for (int q = 0; q < 8; q++)
               o[q] = make_float4(__uint_as_float(ra[4 * q]) * sc, __uint_as_float(ra[4 * q + 1]) * sc,
                                  __uint_as_float(ra[4 * q + 2]) * sc, __uint_as_float(ra[4 * q + 3]) * sc);
+          }
+        } else if (PAIR) {
+#pragma unroll
+          for (int sub = 0; sub < 4; sub++) {
+            const uint32_t qq = tcount * CH + (c0 >> 3) + sub;
+            mbar_wait(afull_bar(quad, qq & 1), (qq >> 1) & 1);
+            const uint8_t* box = smem_al + (aff_buf - smem_base) + (qq & 1) * 4096 + lane * 128;
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const float4 f = *reinterpret_cast<const float4*>(box + ((k ^ (lane & 7)) << 4));  // SWIZZLE_128B
+              const int i = sub * 8 + k;
+              float v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+              v *= a.act_scale;
+              const __half h = __float2half_rn(v);
+              const float hf = __half2float(h);
+              overflow |= valid && !(fabsf(hf) <= 65504.0f);
+              hi[k] = h;
+              lo[k] = __float2half_rn(v - hf);
+            }
+            if (valid) {
+              *(uint4*)(ohi + c0 + sub * 8) = *(const uint4*)hi;
+              *(uint4*)(olo + c0 + sub * 8) = *(const uint4*)lo;
+            }
+            __syncwarp();
+            aff_issue(qq + 2);
           }
         } else if (valid) {
           __align__(16) __half hi[32];
@@ -607,6 +663,19 @@ CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows
   return m;
 }
 
+// fused-pair affine: fp32 [rows = board positions][cols = 4 floats per channel], box {32 floats = 128 B, 32 rows}
+CUtensorMap make_map_aff(void* base, uint64_t rows, uint64_t cols) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(affine) failed: " + std::to_string((int)r));
+  return m;
+}
+
 // per-sample layout: 3-D fp16 tensor [n][S][cols], box {64 cols, BM positions, 1 sample}
 CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk) {
   CUtensorMap m;
@@ -624,7 +693,7 @@ CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk
 // device; called from the allocators, which run with the engine's device current)
 template <int BN, bool PAIR, int BKT>
 void set_conv_attr() {
-  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN, BKT)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN, BKT, PAIR)));
 }
 void tc_configure_device() {
   set_conv_attr<256, true, 64>(); set_conv_attr<128, true, 64>(); set_conv_attr<256, false, 64>(); set_conv_attr<128, false, 64>();
@@ -640,8 +709,10 @@ struct Layer {
   int cin, n_total, bn;
   bool pair;
   __half *w_hi = nullptr, *w_lo = nullptr;  // [n_total][9*cin]
-  float2* aff = nullptr;                    // [HW][n_total]
-  CUtensorMap mB_hi, mB_lo;
+  float2* aff = nullptr;                    // [HW][n_total]  (single layers: read by the epilogue with global loads)
+  float* affq = nullptr;                    // fused pairs: [aff_rows][K] x {A'a, Ba, A'b, Bb}, rows = positions in layout order
+  int aff_rows = 0;
+  CUtensorMap mB_hi, mB_lo, mAff;
 };
 struct Impl {
   NetDims d;
@@ -673,7 +744,7 @@ void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUt
   a.out_raw = nullptr; a.exp_a = nullptr; a.exp_b = nullptr;
   const int max_tiles = (I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
   const int grid = std::min(I.num_sms, max_tiles);
-  k_conv3x3_tc<BN, PAIR, BKT><<<grid, NTHREADS, smem_bytes(BN, BKT), st>>>(ah, al, L.mB_hi, L.mB_lo, a);
+  k_conv3x3_tc<BN, PAIR, BKT><<<grid, NTHREADS, smem_bytes(BN, BKT, PAIR), st>>>(ah, al, L.mB_hi, L.mB_lo, PAIR ? L.mAff : L.mB_hi, a);
 }
 template <int BKT>
 void dispatch_conv_bk(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
@@ -734,6 +805,13 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
     const size_t ktot = (size_t)9 * L.cin;
     L.w_hi = alloc_h((size_t)L.n_total * ktot); L.w_lo = alloc_h((size_t)L.n_total * ktot);
     CUDA_CHECK(cudaMalloc(&L.aff, (size_t)HW * L.n_total * sizeof(float2)));
+    if (L.pair) {
+      // flat layout: an M tile runs across samples, so a warp's 32 rows start at (row % S) and may wrap: the first 32
+      // positions are repeated after the last one
+      L.aff_rows = I->mode3d ? I->S : I->S + 32;
+      CUDA_CHECK(cudaMalloc(&L.affq, (size_t)L.aff_rows * K * 16));
+      L.mAff = make_map_aff(L.affq, L.aff_rows, (uint64_t)K * 4);
+    }
     L.mB_hi = make_map(L.w_hi, L.n_total, ktot, L.bn, I->bk); L.mB_lo = make_map(L.w_lo, L.n_total, ktot, L.bn, I->bk);
     I->layers.push_back(L);
   }
@@ -745,7 +823,7 @@ void tc_tower_free(TcTower& t) {
   if (!I) return;
   cudaFree(I->xin_hi); cudaFree(I->xin_lo);
   for (int i = 0; i < 2; i++) { cudaFree(I->x_hi[i]); cudaFree(I->x_lo[i]); }
-  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); }
+  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); cudaFree(L.affq); }
   for (cudaEvent_t e : I->ev_pool) cudaEventDestroy(e);
   delete I;
   t.impl = nullptr;
@@ -800,6 +878,23 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
     CUDA_CHECK(cudaMemcpy(L.w_hi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(L.w_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(L.aff, aff.data(), aff.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    if (L.pair) {
+      std::vector<float> q((size_t)L.aff_rows * K * 4, 0.0f);
+      const int Wp = d.W + 1;
+      for (int r = 0; r < L.aff_rows; r++) {
+        const int p = r % I->S, y = p / Wp, x = p - y * Wp;
+        if (y >= d.H || x >= d.W) continue;  // zero-border positions
+        const int hw = y * d.W + x;
+        for (int ch = 0; ch < K; ch++) {
+          float* o = q.data() + ((size_t)r * K + ch) * 4;
+          for (int br = 0; br < 2; br++) {
+            o[2 * br] = h[u[br]->gamma + (size_t)ch * HW + hw] * fold;
+            o[2 * br + 1] = h[u[br]->beta + (size_t)ch * HW + hw];
+          }
+        }
+      }
+      CUDA_CHECK(cudaMemcpy(L.affq, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
   (void)NL;
   t.ready = true;
@@ -1049,7 +1144,7 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   const int max_tiles = ((I->B * I->S + BM - 1) / BM) * (Cout / bn);
   const int grid = std::min(I->num_sms, max_tiles);
   auto launch = [&](auto kern, int BNv) {
-    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, a);
+    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, mBh, a);
   };
   if (bn == 256) launch(k_conv3x3_tc<256, false, 64>, 256);
   else if (bn == 128) launch(k_conv3x3_tc<128, false, 64>, 128);
