@@ -401,6 +401,258 @@ k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// CTA-pair version of the fused residual-block layer (cta_group::2): two CTAs of a cluster compute a 256 x 256 tile,
+// each owning 128 rows of A (its own M tile) and HALF of the B tile (rank 0: the 128 branch-a filter rows, rank 1:
+// the 128 branch-b rows); the pair's tensor cores read each B half once for both SMs.  Per SM and K-step that is
+// 4 KB (A) + 4 KB (B half) of shared-memory reads instead of 4 + 8, and 64 KB instead of 96 KB of TMA fill per
+// stage — the 1-CTA kernel is bound by exactly that shared-memory traffic (MMA operand reads ~91 B/clk + fill
+// ~60 B/clk against 128 B/clk; profiles/r01_summary.md).  3 stages of 64 KB.
+//   * both producers signal the LEADER's full barrier (count 2, tx = 2 x 64 KB); the leader's single MMA thread issues
+//     tcgen05.mma.cta_group::2 (M = 256) and commits with multicast to both CTAs' empty / tmem-full barriers;
+//   * each CTA's epilogue warps read their own TMEM lanes and arrive on the leader's tmem-empty barrier (count 8).
+constexpr int STAGES2 = 3;
+constexpr int STAGE2_BYTES = 4 * BM * 64 * 2;  // A hi/lo (128 x 64) + B-half hi/lo (128 x 64) = 64 KB
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address -> the pair's even CTA
+__host__ __device__ constexpr int smem_bytes2() { return STAGES2 * STAGE2_BYTES + AFF_BYTES + 1024 + 256; }
+
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+              const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+              const __grid_constant__ CUtensorMap tmAff, ConvArgs a) {
+  constexpr int BK = 64, BN = 256, OUTC = 128;
+  constexpr int TILE_BYTES = BM * BK * 2;  // 16 KB: one 128 x 64 fp16 operand tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t aff_smem = smem_base + STAGES2 * STAGE2_BYTES;
+  const uint32_t bars = aff_smem + AFF_BYTES;  // full[3], empty[3], tfull[2], tempty[2], afull[4][2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES2 * STAGE2_BYTES + AFF_BYTES + 240);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES2 + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES2 + 2 + i); };
+  auto afull_bar = [&](int quad, int buf) { return bars + 8u * (2 * STAGES2 + 4 + quad * 2 + buf); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; s++) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+    for (int i = 0; i < 8; i++) mbar_init(afull_bar(i >> 1, i & 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n = min(*a.n_dev, a.n_max);
+  const int rows = n * a.S;
+  const int m_tiles = a.mode3d ? n * a.tps : (rows + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int n_tiles = a.n_total / BN;
+  const int total_tiles = m_pairs * n_tiles;  // pair tiles (256 x 256)
+  const int kc_per_tap = a.cin / BK;
+  const int kblocks = 9 * kc_per_tap;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A tile + own half of B, all bytes counted on the leader's barrier =====
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+        const int mt = 2 * mp + (int)rank;
+        const int m0 = mt * BM, n0 = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES2;
+          const uint32_t ph = (it / STAGES2) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const uint32_t sa = smem_base + s * STAGE2_BYTES;
+          const uint32_t lbar = full_bar(s) & PEER_MASK;
+          mbar_expect_tx_cluster(lbar, STAGE2_BYTES);
+          if (a.mode3d) {
+            const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM + dy * a.Wp + dx;
+            tma2_load_3d(sa, &tmA_hi, lbar, kc * BK, p0, b);
+            tma2_load_3d(sa + TILE_BYTES, &tmA_lo, lbar, kc * BK, p0, b);
+          } else {
+            const int arow = a.guard + m0 + dy * a.Wp + dx;
+            tma2_load_2d(sa, &tmA_hi, lbar, kc * BK, arow);
+            tma2_load_2d(sa + TILE_BYTES, &tmA_lo, lbar, kc * BK, arow);
+          }
+          tma2_load_2d(sa + 2 * TILE_BYTES, &tmB_hi, lbar, tap * a.cin + kc * BK, n0);
+          tma2_load_2d(sa + 3 * TILE_BYTES, &tmB_lo, lbar, tap * a.cin + kc * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer: the leader CTA's single thread drives both SMs =====
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
+        const int acc = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES2;
+          const uint32_t ph = (it / STAGES2) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE2_BYTES;
+          const uint64_t dAh = make_desc_sw<64>(sa), dAl = make_desc_sw<64>(sa + TILE_BYTES);
+          const uint64_t dBh = make_desc_sw<64>(sa + 2 * TILE_BYTES), dBl = make_desc_sw<64>(sa + 3 * TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ks++) {
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+            umma2_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | ks) ? 1u : 0u);
+            if (a.passes >= 2) umma2_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            if (a.passes >= 3) umma2_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma2_commit_mc(empty_bar(s));  // frees the stage in both CTAs
+        }
+        umma2_commit_mc(tfull_bar(acc));  // accumulators complete in both CTAs
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5 of either CTA: own 128 TMEM lanes =====
+    const int quad = warp & 3;
+    uint32_t tcount = 0;
+    constexpr int CH = OUTC / 8;
+    const uint32_t aff_buf = aff_smem + quad * 8192;
+    auto aff_issue = [&](uint32_t qq) {
+      const int tile = cluster_id + (int)(qq / CH) * n_clusters;
+      if (tile >= total_tiles) return;
+      const int j = qq % CH;
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int prow = a.mode3d ? (mt % a.tps) * BM + quad * 32 : (mt * BM + quad * 32) % a.S;
+      if (lane == 0) {
+        const uint32_t bar = afull_bar(quad, qq & 1);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(aff_buf + (qq & 1) * 4096, &tmAff, bar, (nt * OUTC + j * 8) * 4, prow);
+      }
+    };
+    aff_issue(0);
+    aff_issue(1);
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int m0 = mt * BM;
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      int r, p;
+      bool inb;
+      if (a.mode3d) {
+        const int b = mt / a.tps;
+        p = (mt - b * a.tps) * BM + quad * 32 + lane;
+        r = b * a.S + p;
+        inb = p < a.S && mt < m_tiles;
+      } else {
+        r = m0 + quad * 32 + lane;
+        p = r % a.S;
+        inb = r < rows;
+      }
+      const int y = p / a.Wp, x = p - y * a.Wp;
+      const bool valid = inb && y < a.H && x < a.W;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      __half* ohi = a.out_hi + (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      __half* olo = a.out_lo + (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      bool overflow = false;
+#pragma unroll 1
+      for (int c0 = 0; c0 < OUTC; c0 += 32) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row + c0, ra);
+        tmem_ld32(t_row + BN / 2 + c0, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < 4; sub++) {
+          const uint32_t qq = tcount * CH + (c0 >> 3) + sub;
+          mbar_wait(afull_bar(quad, qq & 1), (qq >> 1) & 1);
+          const uint8_t* box = smem_al + (aff_buf - smem_base) + (qq & 1) * 4096 + lane * 128;
+          __align__(16) __half hi[8];
+          __align__(16) __half lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const float4 f = *reinterpret_cast<const float4*>(box + ((k ^ (lane & 7)) << 4));
+            const int i = sub * 8 + k;
+            float v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+            v *= a.act_scale;
+            const __half h = __float2half_rn(v);
+            const float hf = __half2float(h);
+            overflow |= valid && !(fabsf(hf) <= 65504.0f);
+            hi[k] = h;
+            lo[k] = __float2half_rn(v - hf);
+          }
+          if (valid) {
+            *(uint4*)(ohi + c0 + sub * 8) = *(const uint4*)hi;
+            *(uint4*)(olo + c0 + sub * 8) = *(const uint4*)lo;
+          }
+          __syncwarp();
+          aff_issue(qq + 2);
+        }
+      }
+      if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & PEER_MASK);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still signal its barriers / read its B half
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // K7 backward-filter on the same pipeline: dW[co][ci][tap] = sum_p dz[p, co] * x[p + shift(tap), ci].
 // GEMM view: M = co, N = ci, K = board positions of the whole batch.  A = dz channel-major ([co][guard + positions],
 // K-major).  B = x in the forward's position-major NHWC buffer, fed to the tensor core as an MN-major operand: the tap
@@ -700,6 +952,7 @@ void tc_configure_device() {
   set_conv_attr<64, false, 64>();
   set_conv_attr<256, true, 32>(); set_conv_attr<128, true, 32>(); set_conv_attr<256, false, 32>(); set_conv_attr<128, false, 32>();
   set_conv_attr<64, false, 32>();
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
   CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256, 64)));
   CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128, 64)));
   CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64, 64)));
@@ -713,10 +966,12 @@ struct Layer {
   float* affq = nullptr;                    // fused pairs: [aff_rows][K] x {A'a, Ba, A'b, Bb}, rows = positions in layout order
   int aff_rows = 0;
   CUtensorMap mB_hi, mB_lo, mAff;
+  CUtensorMap mB2_hi, mB2_lo;               // CTA-pair kernel: 128-row boxes (each CTA of the pair loads half of the N tile)
 };
 struct Impl {
   NetDims d;
   int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1, bk = 64;
+  int pair_clusters = 0;  // > 0: fused layers run on k_conv3x3_tc2 with this many co-resident CTA pairs
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
   __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
@@ -756,9 +1011,23 @@ void dispatch_conv_bk(const Impl& I, const Layer& L, const CUtensorMap& ah, cons
   else if (!L.pair && L.bn == 64) launch_conv<64, false, BKT>(I, L, ah, al, ohi, olo, n_dev, err, st);
   else throw std::runtime_error("tc tower: unsupported tile");
 }
+void launch_conv_pair2(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
+                       const int* n_dev, int* err, cudaStream_t st) {
+  ConvArgs a;
+  a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
+  a.mode3d = I.mode3d; a.tps = I.tps;
+  a.cin = L.cin; a.n_total = L.n_total; a.cout = I.d.K; a.aff = L.aff; a.out_hi = ohi; a.out_lo = olo;
+  a.act_scale = ldexpf(1.0f, I.ea); a.err = err; a.passes = I.passes;
+  a.out_raw = nullptr; a.exp_a = nullptr; a.exp_b = nullptr;
+  const int m_tiles = I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM;
+  const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
+  const int clusters = std::min(I.pair_clusters, pair_tiles);
+  k_conv3x3_tc2<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(ah, al, L.mB2_hi, L.mB2_lo, L.mAff, a);
+}
 void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                    const int* n_dev, int* err, cudaStream_t st) {
-  if (I.bk == 64) dispatch_conv_bk<64>(I, L, ah, al, ohi, olo, n_dev, err, st);
+  if (I.pair_clusters > 0 && L.pair && L.bn == 256) launch_conv_pair2(I, L, ah, al, ohi, olo, n_dev, err, st);
+  else if (I.bk == 64) dispatch_conv_bk<64>(I, L, ah, al, ohi, olo, n_dev, err, st);
   else dispatch_conv_bk<32>(I, L, ah, al, ohi, olo, n_dev, err, st);
 }
 
@@ -794,6 +1063,21 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
     I->mIn_hi = make_map(I->xin_hi, I->rows_alloc, 64, BM, I->bk); I->mIn_lo = make_map(I->xin_lo, I->rows_alloc, 64, BM, I->bk);
     for (int i = 0; i < 2; i++) { I->mX_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, BM, I->bk); I->mX_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, BM, I->bk); }
   }
+  {
+    // CTA-pair kernel for the fused layers (N tile 256, K block 64): as many clusters as can be co-resident
+    const char* e2 = getenv("AZ_TC_2CTA");
+    const bool want = e2 ? e2[0] != '0' : true;  // AZ_TC_2CTA=0: the single-CTA kernel (A/B experiments)
+    if (want && I->bk == 64 && 2 * d.K >= 256) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(I->num_sms & ~1); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem_bytes2();
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nc = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveClusters(&nc, k_conv3x3_tc2, &cfg));
+      I->pair_clusters = std::min(nc, I->num_sms / 2);
+    }
+  }
   // layers: init (single), then SharedLayers fused pairs
   const int K = d.K, HW = d.HW();
   for (int l = 0; l <= d.SharedLayers; l++) {
@@ -813,6 +1097,7 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
       L.mAff = make_map_aff(L.affq, L.aff_rows, (uint64_t)K * 4);
     }
     L.mB_hi = make_map(L.w_hi, L.n_total, ktot, L.bn, I->bk); L.mB_lo = make_map(L.w_lo, L.n_total, ktot, L.bn, I->bk);
+    if (L.pair && L.bn == 256) { L.mB2_hi = make_map(L.w_hi, L.n_total, ktot, 128, 64); L.mB2_lo = make_map(L.w_lo, L.n_total, ktot, 128, 64); }
     I->layers.push_back(L);
   }
   CUDA_CHECK(cudaDeviceSynchronize());

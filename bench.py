@@ -313,20 +313,22 @@ def main():
     achieved = conv_flops / conv_s / 1e12 if conv_s > 0 else None
     peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r01_conv2_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "tensor", "kernel": "k_conv3x3_tc<256,true> (fused residual-block conv, fp16 hi/lo 3-pass tcgen05)",
+    roofline = {"bound": "tensor", "kernel": "k_conv3x3_tc2 (fused residual-block conv, CTA pair / cta_group::2, fp16 hi/lo 3-pass tcgen05)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peak_src,
                 "traffic": traffic, "launches_timed": prof["conv_launches"],
                 "avg_launch_ms": prof["conv_ms"] / max(prof["conv_launches"], 1),
                 "algorithmic_flops_per_launch": conv_flops / max(prof["conv_launches"], 1),
                 "share_of_step": conv_s / dt, "note": "3 tensor-core passes per algorithmic MAC (fp32-faithful split): "
-                "frac of the bf16 peak tops out at 1/3 x 361/400 (zero-border padding) = 0.30"}
+                "frac of the bf16 peak tops out at 1/3 x 361/384 (M-tile padding per sample) = 0.31"}
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         os.environ.setdefault("OMP_WAIT_POLICY", "passive")
