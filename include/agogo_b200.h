@@ -107,7 +107,8 @@ typedef struct az_engine_desc {
   int32_t device;   /* CUDA device ordinal */
   uint32_t flags;
   uint64_t seed;    /* replaces the reference's time.Now() seeds (arena.go:61, tree.go:84) */
-  int32_t act_scale_log2;     /* tcgen05 tower: activations are stored as fp16 hi/lo of x*2^this (0 = default 5) */
+  int32_t act_scale_log2;     /* tcgen05 tower: activations are stored as fp16 hi/lo of x*2^this; 0 = default (-2: |x| up to 2.6e5
+                               * before AZ_ERR_PANIC "activation overflow"; outputs are insensitive to it between -5 and 5) */
   int32_t max_nodes_per_tree; /* 0 = derive from sims and action space */
 } az_engine_desc;
 
