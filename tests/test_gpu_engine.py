@@ -365,6 +365,24 @@ def test_c1_learn_on_device(oracle, engine_lib):
         assert sum(l["a"]) == 10 and sum(l["b"]) == 10
 
 
+def test_learn_loop_go_on_tensor_cores(engine_lib):
+    """AZ.Learn end to end on a Go net wide enough for every tensor-core path (9x9, K = 64: tcgen05 tower in self-play
+    and arena, tcgen05 forward / backward-data / backward-filter in Train) from the reference's own random init: two
+    epochs complete, costs finite, every arena game counted, examples produced."""
+    from agogo_b200 import host
+    nn = host.DefaultConf(9, 9, 82)
+    nn.K, nn.SharedLayers, nn.FC, nn.BatchSize, nn.Features = 64, 2, 32, 16, 18
+    mc = host.MCTSConfig(PUCT=1.0, M=9, N=9, Timeout=100_000_000, PassPreference=K.DONT_PREFER_PASS, Budget=1000,
+                         DumbPass=True, RandomCount=0, Sims=12)
+    conf = host.Config(Name="go9", NNConf=nn, MCTSConf=mc, UpdateThreshold=0.55, Encoder=K.ENC_WQ18)
+    az = host.AZ(host.Game(K.GAME_WQ, 9, 9, 0, komi=7.5, max_moves=14), conf, lib=engine_lib, n_games=8, seed=7)
+    az.Learn(2, 8, 3, 6)
+    assert len(az.log) == 2
+    for l in az.log:
+        assert np.isfinite(l["first_cost"]) and np.isfinite(l["last_cost"]) and l["n_examples"] >= 16
+        assert sum(l["a"]) == 6 and sum(l["b"]) == 6
+
+
 def test_tc_tower_full_depth_c3(oracle, engine_lib):
     """The headline net (20 blocks x 256, 19x19, FC 512) end to end against the oracle: the fp16 hi/lo
     3-pass tower must hold 1e-4 through all 41 conv layers."""
