@@ -294,14 +294,27 @@ void heads_tiled_configure() {
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUDA_CHECK(cudaFuncSetAttribute(k_heads_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
-void heads_tiled(const NetLayout& L, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
-                 float* policy, int ldp, float* value, cudaStream_t st, unsigned long long* launches) {
-  const NetDims& d = L.d;
-  constexpr int SB = 8;
+template <int SB>
+static void launch_heads_tiled(const NetDims& d, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
+                               float* policy, int ldp, float* value, cudaStream_t st) {
   const size_t sm = (size_t)SB * (3 * d.HW() + d.A1 + d.FC) * 4;
   k_heads_tiled<SB><<<(n_max + SB - 1) / SB, 256, sm, st>>>(ph, vh, s.d + s.pW, s.d + s.pB, s.d + s.vW, s.d + s.vB, s.d + s.voW,
                                                           s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC);
+}
+// Samples per block: the most that still gives every SM a block (each sample's arithmetic does not depend on it)
+void heads_tiled(const NetLayout& L, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
+                 float* policy, int ldp, float* value, cudaStream_t st, unsigned long long* launches) {
+  const NetDims& d = L.d;
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  if (n_max >= 8 * num_sms) launch_heads_tiled<8>(d, s, ph, vh, n_dev, n_max, policy, ldp, value, st);
+  else if (n_max >= 4 * num_sms) launch_heads_tiled<4>(d, s, ph, vh, n_dev, n_max, policy, ldp, value, st);
+  else if (n_max >= 2 * num_sms) launch_heads_tiled<2>(d, s, ph, vh, n_dev, n_max, policy, ldp, value, st);
+  else launch_heads_tiled<1>(d, s, ph, vh, n_dev, n_max, policy, ldp, value, st);
   if (launches) (*launches)++;
 }
 
