@@ -15,6 +15,7 @@ UNITS = [
     ("mcts.cu", ["-fmad=false"]),
     ("nn_fp32.cu", ["-fmad=false"]),
     ("tower_tc.cu", []),
+    ("train_tc.cu", []),
     ("train.cu", []),
     ("engine.cu", []),
 ]

@@ -1,0 +1,441 @@
+// agogo_b200 — shared pieces of the tcgen05 kernels (tower_tc.cu: inference tower, train_tc.cu: training GEMMs):
+// PTX wrappers (mbarrier, TMA, tcgen05), shared-memory / instruction descriptors, the single-CTA implicit-GEMM 3x3
+// convolution kernel template and the host-side tensor-map builders.  Everything lives in an anonymous namespace: each
+// translation unit instantiates what it launches.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "mcts_dev.cuh"
+#include "tower_tc.cuh"
+
+namespace {
+
+
+constexpr int BM = 128;        // M tile (TMEM lanes)
+// K block per pipeline stage: 64 fp16 = 128 B rows (SWIZZLE_128B) or 32 fp16 = 64 B rows (SWIZZLE_64B, twice the
+// stages in the same shared memory).  Template parameter BKT of the kernel; chosen at tower allocation.
+constexpr int NTHREADS = 192;  // 6 warps
+__host__ __device__ constexpr int stage_bytes(int BN, int BKT) { return 2 * BM * BKT * 2 + 2 * BN * BKT * 2; }
+__host__ __device__ constexpr int num_stages(int BN, int BKT) { return 196608 / stage_bytes(BN, BKT) > 8 ? 8 : 196608 / stage_bytes(BN, BKT); }
+constexpr int AFF_BYTES = 4 * 2 * 4096;  // fused-pair epilogue: per epilogue warp two 32-row x 128-byte affine boxes (TMA, SWIZZLE_128B)
+__host__ __device__ constexpr int smem_bytes(int BN, int BKT, bool pair = false) {
+  return num_stages(BN, BKT) * stage_bytes(BN, BKT) + (pair ? AFF_BYTES : 0) + 1024 + 256;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), cta_group::1
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major swizzled operand descriptor: start>>4 | LBO (ignored for swizzled K-major) | SBO = 8 rows x row bytes
+// (1024 B for SWIZZLE_128B, 512 B for SWIZZLE_64B) | version 1 (bits 46-47) | layout type (bits 61-63: 2 = 128B, 4 = 64B)
+template <int BKT>
+__device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * BKT * 2) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(BKT == 64 ? 2 : 4) << 61;
+  return d;
+}
+// MN-major operand, SWIZZLE_128B: 64-element (128 B) runs along M/N, rows = K index; atoms of 8 K-rows (1024 B, SBO),
+// 64-wide M/N groups lbo_bytes apart (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// training operands carry a data-dependent power-of-two scale: the device word is ilogb(absmax) - 13 (or the
+// 0x80808080 fill when the tensor is all zero); scale exponent e = -word
+__device__ __forceinline__ int exp_decode(const int* e) { const int v = *e; return v < -100000 ? 0 : -v; }
+
+struct ConvArgs {
+  const int* n_dev;   // batch size (device)
+  int n_max;
+  int S, Wp, H, W;    // positions per sample (flat: (H+1)*(W+1), per-sample: H*(W+1)), row pitch W+1
+  int guard;          // zero rows in front of the activation buffers (flat layout only)
+  int mode3d, tps;    // per-sample layout: 3-D tensor map, tps = M tiles per sample
+  int cin;            // padded input channels (multiple of 64)
+  int n_total;        // GEMM N of the layer (fused: 2*K)
+  int cout;           // output channels (K)
+  const float2* aff;  // [HW][n_total] {A', B} in weight-row order
+  __half* out_hi;     // [(guard + rows)][cout]
+  __half* out_lo;
+  float act_scale;    // 2^ea
+  int* err;
+  int passes;         // 3: hi*hi + hi*lo + lo*hi (fp32-faithful, default); 2: drops lo*hi; 1: hi*hi only
+  // raw mode (training, K7): no affine / ReLU / split — the epilogue writes acc * 2^-(*exp_a + *exp_b) as fp32
+  float* out_raw;     // [(guard + rows)][n_total] or nullptr
+  const int* exp_a;   // power-of-two scales of the A and B operands (device: they are data dependent)
+  const int* exp_b;
+};
+
+template <int BN, bool PAIR, int BKT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+             const __grid_constant__ CUtensorMap tmAff, ConvArgs a) {
+  constexpr int BK = BKT;
+  constexpr int A_TILE_BYTES = BM * BK * 2;
+  constexpr int STAGES = num_stages(BN, BKT);
+  constexpr int STAGE_BYTES = stage_bytes(BN, BKT);
+  constexpr int B_TILE_BYTES = BN * BK * 2;
+  constexpr int OUTC = PAIR ? BN / 2 : BN;  // output channels per N tile
+  constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : 128);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int AFF = PAIR ? AFF_BYTES : 0;
+  const uint32_t aff_smem = smem_base + STAGES * STAGE_BYTES;  // PAIR: 4 warps x 2 x 4 KB affine boxes (1024-aligned)
+  const uint32_t bars = aff_smem + AFF;  // full[S], empty[S], tfull[2], tempty[2], afull[4][2]
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES * STAGE_BYTES + AFF + 240);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
+  auto afull_bar = [&](int quad, int buf) { return bars + 8u * (2 * STAGES + 4 + quad * 2 + buf); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int i = 0; i < 8; i++) mbar_init(afull_bar(i >> 1, i & 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n = min(*a.n_dev, a.n_max);
+  const int rows = n * a.S;
+  const int m_tiles = a.mode3d ? n * a.tps : (rows + BM - 1) / BM;
+  const int n_tiles = a.n_total / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int kc_per_tap = a.cin / BK;
+  const int kblocks = 9 * kc_per_tap;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          if (a.mode3d) {
+            const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM + dy * a.Wp + dx;  // may be <0 / >=S: zero fill
+            tma_load_3d(sa, &tmA_hi, full_bar(s), kc * BK, p0, b);
+            tma_load_3d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, p0, b);
+          } else {
+            const int arow = a.guard + m0 + dy * a.Wp + dx;
+            tma_load_2d(sa, &tmA_hi, full_bar(s), kc * BK, arow);
+            tma_load_2d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, arow);
+          }
+          tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), tap * a.cin + kc * BK, n0);
+          tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), tap * a.cin + kc * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+        const int acc = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE_BYTES;
+          const uint64_t dAh = make_desc_sw<BKT>(sa), dAl = make_desc_sw<BKT>(sa + A_TILE_BYTES);
+          const uint64_t dBh = make_desc_sw<BKT>(sa + 2 * A_TILE_BYTES), dBl = make_desc_sw<BKT>(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ks++) {
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 fp16 = 32 B along K inside the swizzle atom
+            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | ks) ? 1u : 0u);
+            if (a.passes >= 2) umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            if (a.passes >= 3) umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above have read it
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    uint32_t tcount = 0;
+    // Fused-pair layers: the per-(channel, point) affine of both branches ({A'a, Ba, A'b, Bb} per channel, rows = board
+    // positions in layout order) is staged through shared memory by TMA, 8 channels (= one 128-byte row) x this warp's
+    // 32 rows per box, double buffered and prefetched two boxes ahead across tiles.  (Reading it with per-thread global
+    // loads touches 32 cache lines per warp instruction: lane = row, 4 KB row pitch.)
+    constexpr int CH = OUTC / 8;  // boxes per tile
+    const uint32_t aff_buf = aff_smem + quad * 8192;
+    auto aff_issue = [&](uint32_t qq) {
+      if (!PAIR) return;
+      const int tile = blockIdx.x + (int)(qq / CH) * gridDim.x;
+      if (tile >= total_tiles) return;
+      const int j = qq % CH;
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int prow = a.mode3d ? (mt % a.tps) * BM + quad * 32 : (mt * BM + quad * 32) % a.S;
+      if (lane == 0) {
+        const uint32_t bar = afull_bar(quad, qq & 1);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(aff_buf + (qq & 1) * 4096, &tmAff, bar, (nt * OUTC + j * 8) * 4, prow);
+      }
+    };
+    aff_issue(0);
+    aff_issue(1);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      int r, p;  // r = row in the activation buffer (without guard), p = position inside the sample
+      bool inb;
+      if (a.mode3d) {
+        const int b = mt / a.tps;
+        p = (mt - b * a.tps) * BM + quad * 32 + lane;
+        r = b * a.S + p;
+        inb = p < a.S;
+      } else {
+        r = m0 + quad * 32 + lane;
+        p = r % a.S;
+        inb = r < rows;
+      }
+      const int y = p / a.Wp, x = p - y * a.Wp;
+      const bool valid = inb && y < a.H && x < a.W;
+      const int hw = y * a.W + x;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const float2* aff = a.aff + (size_t)(valid ? hw : 0) * a.n_total + n0;
+      __half* ohi = a.out_hi + (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      __half* olo = a.out_lo + (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      bool overflow = false;
+#pragma unroll 1
+      for (int c0 = 0; c0 < OUTC; c0 += 32) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row + c0, ra);
+        if (PAIR) tmem_ld32(t_row + BN / 2 + c0, rb);
+        tmem_ld_wait();
+        if (a.out_raw) {
+          if (valid) {
+            const float sc = exp2f(-(float)(exp_decode(a.exp_a) + exp_decode(a.exp_b)));
+            float4* o = reinterpret_cast<float4*>(a.out_raw + (size_t)(a.guard + r) * a.n_total + n0 + c0);
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              o[q] = make_float4(__uint_as_float(ra[4 * q]) * sc, __uint_as_float(ra[4 * q + 1]) * sc,
+                                 __uint_as_float(ra[4 * q + 2]) * sc, __uint_as_float(ra[4 * q + 3]) * sc);
+          }
+        } else if (PAIR) {
+#pragma unroll
+          for (int sub = 0; sub < 4; sub++) {
+            const uint32_t qq = tcount * CH + (c0 >> 3) + sub;
+            mbar_wait(afull_bar(quad, qq & 1), (qq >> 1) & 1);
+            const uint8_t* box = smem_al + (aff_buf - smem_base) + (qq & 1) * 4096 + lane * 128;
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const float4 f = *reinterpret_cast<const float4*>(box + ((k ^ (lane & 7)) << 4));  // SWIZZLE_128B
+              const int i = sub * 8 + k;
+              float v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+              v *= a.act_scale;
+              const __half h = __float2half_rn(v);
+              const float hf = __half2float(h);
+              overflow |= valid && !(fabsf(hf) <= 65504.0f);
+              hi[k] = h;
+              lo[k] = __float2half_rn(v - hf);
+            }
+            if (valid) {
+              *(uint4*)(ohi + c0 + sub * 8) = *(const uint4*)hi;
+              *(uint4*)(olo + c0 + sub * 8) = *(const uint4*)lo;
+            }
+            __syncwarp();
+            aff_issue(qq + 2);
+          }
+        } else if (valid) {
+          __align__(16) __half hi[32];
+          __align__(16) __half lo[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            float2 fa = __ldg(aff + c0 + i);
+            float v = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
+            if (PAIR) {
+              float2 fb = __ldg(aff + BN / 2 + c0 + i);
+              v += fmaxf(fmaf(fb.x, __uint_as_float(rb[i]), fb.y), 0.0f);
+            }
+            v *= a.act_scale;
+            __half h = __float2half_rn(v);
+            float hf = __half2float(h);
+            overflow |= !(fabsf(hf) <= 65504.0f);
+            hi[i] = h;
+            lo[i] = __float2half_rn(v - hf);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            *(uint4*)(ohi + c0 + q * 8) = *(const uint4*)(hi + q * 8);
+            *(uint4*)(olo + c0 + q * 8) = *(const uint4*)(lo + q * 8);
+          }
+        }
+      }
+      if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// 2-D fp16 row-major [rows][cols] tensor, box {bk cols, box_rows}, swizzle = row bytes of the box
+CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bk) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return m;
+}
+
+// fused-pair affine: fp32 [rows = board positions][cols = 4 floats per channel], box {32 floats = 128 B, 32 rows}
+CUtensorMap make_map_aff(void* base, uint64_t rows, uint64_t cols) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(affine) failed: " + std::to_string((int)r));
+  return m;
+}
+
+// per-sample layout: 3-D fp16 tensor [n][S][cols], box {64 cols, BM positions, 1 sample}
+CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {cols, S, n};
+  cuuint64_t strides[2] = {cols * 2, S * cols * 2};
+  cuuint32_t box[3] = {(cuuint32_t)bk, BM, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(3d) failed: " + std::to_string((int)r));
+  return m;
+}
+
+}  // namespace

@@ -21,385 +21,9 @@
 //     (tmem_full/tmem_empty mbarriers), persistent CTAs striding over (M-tile, N-tile).
 // Descriptor bit layouts follow the PTX ISA tcgen05 "shared memory descriptor" / "instruction
 // descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp in the image).
-#include <cuda.h>
-#include <cuda_fp16.h>
-
-#include <cmath>
-#include <cstdlib>
-#include <cstring>
-#include <stdexcept>
-
-#include "mcts_dev.cuh"
-#include "tower_tc.cuh"
+#include "tc_common.cuh"
 
 namespace {
-
-constexpr int BM = 128;        // M tile (TMEM lanes)
-// K block per pipeline stage: 64 fp16 = 128 B rows (SWIZZLE_128B) or 32 fp16 = 64 B rows (SWIZZLE_64B, twice the
-// stages in the same shared memory).  Template parameter BKT of the kernel; chosen at tower allocation.
-constexpr int NTHREADS = 192;  // 6 warps
-__host__ __device__ constexpr int stage_bytes(int BN, int BKT) { return 2 * BM * BKT * 2 + 2 * BN * BKT * 2; }
-__host__ __device__ constexpr int num_stages(int BN, int BKT) { return 196608 / stage_bytes(BN, BKT) > 8 ? 8 : 196608 / stage_bytes(BN, BKT); }
-constexpr int AFF_BYTES = 4 * 2 * 4096;  // fused-pair epilogue: per epilogue warp two 32-row x 128-byte affine boxes (TMA, SWIZZLE_128B)
-__host__ __device__ constexpr int smem_bytes(int BN, int BKT, bool pair = false) {
-  return num_stages(BN, BKT) * stage_bytes(BN, BKT) + (pair ? AFF_BYTES : 0) + 1024 + 256;
-}
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 inputs, fp32 accumulate), cta_group::1
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// K-major swizzled operand descriptor: start>>4 | LBO (ignored for swizzled K-major) | SBO = 8 rows x row bytes
-// (1024 B for SWIZZLE_128B, 512 B for SWIZZLE_64B) | version 1 (bits 46-47) | layout type (bits 61-63: 2 = 128B, 4 = 64B)
-template <int BKT>
-__device__ __forceinline__ uint64_t make_desc_sw(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * BKT * 2) >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(BKT == 64 ? 2 : 4) << 61;
-  return d;
-}
-// MN-major operand, SWIZZLE_128B: 64-element (128 B) runs along M/N, rows = K index; atoms of 8 K-rows (1024 B, SBO),
-// 64-wide M/N groups lbo_bytes apart (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor: D=F32 (bits 4-5 = 1), A=B=F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// training operands carry a data-dependent power-of-two scale: the device word is ilogb(absmax) - 13 (or the
-// 0x80808080 fill when the tensor is all zero); scale exponent e = -word
-__device__ __forceinline__ int exp_decode(const int* e) { const int v = *e; return v < -100000 ? 0 : -v; }
-
-struct ConvArgs {
-  const int* n_dev;   // batch size (device)
-  int n_max;
-  int S, Wp, H, W;    // positions per sample (flat: (H+1)*(W+1), per-sample: H*(W+1)), row pitch W+1
-  int guard;          // zero rows in front of the activation buffers (flat layout only)
-  int mode3d, tps;    // per-sample layout: 3-D tensor map, tps = M tiles per sample
-  int cin;            // padded input channels (multiple of 64)
-  int n_total;        // GEMM N of the layer (fused: 2*K)
-  int cout;           // output channels (K)
-  const float2* aff;  // [HW][n_total] {A', B} in weight-row order
-  __half* out_hi;     // [(guard + rows)][cout]
-  __half* out_lo;
-  float act_scale;    // 2^ea
-  int* err;
-  int passes;         // 3: hi*hi + hi*lo + lo*hi (fp32-faithful, default); 2: drops lo*hi; 1: hi*hi only
-  // raw mode (training, K7): no affine / ReLU / split — the epilogue writes acc * 2^-(*exp_a + *exp_b) as fp32
-  float* out_raw;     // [(guard + rows)][n_total] or nullptr
-  const int* exp_a;   // power-of-two scales of the A and B operands (device: they are data dependent)
-  const int* exp_b;
-};
-
-template <int BN, bool PAIR, int BKT>
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_conv3x3_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-             const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-             const __grid_constant__ CUtensorMap tmAff, ConvArgs a) {
-  constexpr int BK = BKT;
-  constexpr int A_TILE_BYTES = BM * BK * 2;
-  constexpr int STAGES = num_stages(BN, BKT);
-  constexpr int STAGE_BYTES = stage_bytes(BN, BKT);
-  constexpr int B_TILE_BYTES = BN * BK * 2;
-  constexpr int OUTC = PAIR ? BN / 2 : BN;  // output channels per N tile
-  constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : 128);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  constexpr int AFF = PAIR ? AFF_BYTES : 0;
-  const uint32_t aff_smem = smem_base + STAGES * STAGE_BYTES;  // PAIR: 4 warps x 2 x 4 KB affine boxes (1024-aligned)
-  const uint32_t bars = aff_smem + AFF;  // full[S], empty[S], tfull[2], tempty[2], afull[4][2]
-  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES * STAGE_BYTES + AFF + 240);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
-  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
-  auto afull_bar = [&](int quad, int buf) { return bars + 8u * (2 * STAGES + 4 + quad * 2 + buf); };
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
-    for (int i = 0; i < 8; i++) mbar_init(afull_bar(i >> 1, i & 1), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  const int n = min(*a.n_dev, a.n_max);
-  const int rows = n * a.S;
-  const int m_tiles = a.mode3d ? n * a.tps : (rows + BM - 1) / BM;
-  const int n_tiles = a.n_total / BN;
-  const int total_tiles = m_tiles * n_tiles;
-  const int kc_per_tap = a.cin / BK;
-  const int kblocks = 9 * kc_per_tap;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-        const int m0 = mt * BM, n0 = nt * BN;
-        for (int kb = 0; kb < kblocks; kb++, it++) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          if (a.mode3d) {
-            const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM + dy * a.Wp + dx;  // may be <0 / >=S: zero fill
-            tma_load_3d(sa, &tmA_hi, full_bar(s), kc * BK, p0, b);
-            tma_load_3d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, p0, b);
-          } else {
-            const int arow = a.guard + m0 + dy * a.Wp + dx;
-            tma_load_2d(sa, &tmA_hi, full_bar(s), kc * BK, arow);
-            tma_load_2d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), kc * BK, arow);
-          }
-          tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, full_bar(s), tap * a.cin + kc * BK, n0);
-          tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmB_lo, full_bar(s), tap * a.cin + kc * BK, n0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
-        const int acc = tcount & 1;
-        const uint32_t aph = (tcount >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; kb++, it++) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          const uint64_t dAh = make_desc_sw<BKT>(sa), dAl = make_desc_sw<BKT>(sa + A_TILE_BYTES);
-          const uint64_t dBh = make_desc_sw<BKT>(sa + 2 * A_TILE_BYTES), dBl = make_desc_sw<BKT>(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < BK / 16; ks++) {
-            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 fp16 = 32 B along K inside the swizzle atom
-            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (kb | ks) ? 1u : 0u);
-            if (a.passes >= 2) umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
-            if (a.passes >= 3) umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
-          }
-          umma_commit(empty_bar(s));  // frees the smem stage when the MMAs above have read it
-        }
-        umma_commit(tfull_bar(acc));  // accumulator complete
-      }
-    }
-  } else {
-    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
-    const int quad = warp & 3;
-    uint32_t tcount = 0;
-    // Fused-pair layers: the per-(channel, point) affine of both branches ({A'a, Ba, A'b, Bb} per channel, rows = board
-    // positions in layout order) is staged through shared memory by TMA, 8 channels (= one 128-byte row) x this warp's
-    // 32 rows per box, double buffered and prefetched two boxes ahead across tiles.  (Reading it with per-thread global
-    // loads touches 32 cache lines per warp instruction: lane = row, 4 KB row pitch.)
-    constexpr int CH = OUTC / 8;  // boxes per tile
-    const uint32_t aff_buf = aff_smem + quad * 8192;
-    auto aff_issue = [&](uint32_t qq) {
-      if (!PAIR) return;
-      const int tile = blockIdx.x + (int)(qq / CH) * gridDim.x;
-      if (tile >= total_tiles) return;
-      const int j = qq % CH;
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int prow = a.mode3d ? (mt % a.tps) * BM + quad * 32 : (mt * BM + quad * 32) % a.S;
-      if (lane == 0) {
-        const uint32_t bar = afull_bar(quad, qq & 1);
-        mbar_expect_tx(bar, 4096);
-        tma_load_2d(aff_buf + (qq & 1) * 4096, &tmAff, bar, (nt * OUTC + j * 8) * 4, prow);
-      }
-    };
-    aff_issue(0);
-    aff_issue(1);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
-      const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
-      const int m0 = mt * BM, n0 = nt * BN;
-      const int acc = tcount & 1;
-      const uint32_t aph = (tcount >> 1) & 1;
-      mbar_wait(tfull_bar(acc), aph);
-      tc_fence_after();
-      int r, p;  // r = row in the activation buffer (without guard), p = position inside the sample
-      bool inb;
-      if (a.mode3d) {
-        const int b = mt / a.tps;
-        p = (mt - b * a.tps) * BM + quad * 32 + lane;
-        r = b * a.S + p;
-        inb = p < a.S;
-      } else {
-        r = m0 + quad * 32 + lane;
-        p = r % a.S;
-        inb = r < rows;
-      }
-      const int y = p / a.Wp, x = p - y * a.Wp;
-      const bool valid = inb && y < a.H && x < a.W;
-      const int hw = y * a.W + x;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      const float2* aff = a.aff + (size_t)(valid ? hw : 0) * a.n_total + n0;
-      __half* ohi = a.out_hi + (size_t)(a.guard + r) * a.cout + nt * OUTC;
-      __half* olo = a.out_lo + (size_t)(a.guard + r) * a.cout + nt * OUTC;
-      bool overflow = false;
-#pragma unroll 1
-      for (int c0 = 0; c0 < OUTC; c0 += 32) {
-        uint32_t ra[32], rb[32];
-        tmem_ld32(t_row + c0, ra);
-        if (PAIR) tmem_ld32(t_row + BN / 2 + c0, rb);
-        tmem_ld_wait();
-        if (a.out_raw) {
-          if (valid) {
-            const float sc = exp2f(-(float)(exp_decode(a.exp_a) + exp_decode(a.exp_b)));
-            float4* o = reinterpret_cast<float4*>(a.out_raw + (size_t)(a.guard + r) * a.n_total + n0 + c0);
-#pragma unroll
-            for (int q = 0; q < 8; q++)
-              o[q] = make_float4(__uint_as_float(ra[4 * q]) * sc, __uint_as_float(ra[4 * q + 1]) * sc,
-                                 __uint_as_float(ra[4 * q + 2]) * sc, __uint_as_float(ra[4 * q + 3]) * sc);
-          }
-        } else if (PAIR) {
-#pragma unroll
-          for (int sub = 0; sub < 4; sub++) {
-            const uint32_t qq = tcount * CH + (c0 >> 3) + sub;
-            mbar_wait(afull_bar(quad, qq & 1), (qq >> 1) & 1);
-            const uint8_t* box = smem_al + (aff_buf - smem_base) + (qq & 1) * 4096 + lane * 128;
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const float4 f = *reinterpret_cast<const float4*>(box + ((k ^ (lane & 7)) << 4));  // SWIZZLE_128B
-              const int i = sub * 8 + k;
-              float v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
-              v *= a.act_scale;
-              const __half h = __float2half_rn(v);
-              const float hf = __half2float(h);
-              overflow |= valid && !(fabsf(hf) <= 65504.0f);
-              hi[k] = h;
-              lo[k] = __float2half_rn(v - hf);
-            }
-            if (valid) {
-              *(uint4*)(ohi + c0 + sub * 8) = *(const uint4*)hi;
-              *(uint4*)(olo + c0 + sub * 8) = *(const uint4*)lo;
-            }
-            __syncwarp();
-            aff_issue(qq + 2);
-          }
-        } else if (valid) {
-          __align__(16) __half hi[32];
-          __align__(16) __half lo[32];
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            float2 fa = __ldg(aff + c0 + i);
-            float v = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
-            if (PAIR) {
-              float2 fb = __ldg(aff + BN / 2 + c0 + i);
-              v += fmaxf(fmaf(fb.x, __uint_as_float(rb[i]), fb.y), 0.0f);
-            }
-            v *= a.act_scale;
-            __half h = __float2half_rn(v);
-            float hf = __half2float(h);
-            overflow |= !(fabsf(hf) <= 65504.0f);
-            hi[i] = h;
-            lo[i] = __float2half_rn(v - hf);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            *(uint4*)(ohi + c0 + q * 8) = *(const uint4*)(hi + q * 8);
-            *(uint4*)(olo + c0 + q * 8) = *(const uint4*)(lo + q * 8);
-          }
-        }
-      }
-      if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-  }
-}
 
 // -------------------------------------------------------------------------------------------------
 // CTA-pair version of the fused residual-block layer (cta_group::2): two CTAs of a cluster compute a 256 x 256 tile,
@@ -653,176 +277,6 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   }
 }
 
-// K7 backward-filter on the same pipeline: dW[co][ci][tap] = sum_p dz[p, co] * x[p + shift(tap), ci].
-// GEMM view: M = co, N = ci, K = board positions of the whole batch.  A = dz channel-major ([co][guard + positions],
-// K-major).  B = x in the forward's position-major NHWC buffer, fed to the tensor core as an MN-major operand: the tap
-// is a shift of the TMA ROW coordinate (a shift along the contiguous dimension would break TMA's 16-byte global
-// alignment).  Work item = (tap, co tile, ci tile, K split); each item writes its fp32
-// partial tile, k_dw_reduce sums the splits in a fixed order (deterministic, no atomics).
-struct DwArgs {
-  int co_tiles, ci_tiles, splits, kb_per_split;
-  int guard, Wp, Co, Ci;
-  float* partial;  // [splits][9][Co][Ci]
-  int passes;
-};
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_dw_tc(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-        const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, DwArgs a) {
-  constexpr int BK = 64;
-  constexpr int A_TILE_BYTES = BM * BK * 2;
-  constexpr int STAGES = num_stages(BN, BK);
-  constexpr int STAGE_BYTES = stage_bytes(BN, BK);
-  constexpr int B_TILE_BYTES = BN * BK * 2;
-  constexpr int TMEM_COLS = 2 * BN >= 512 ? 512 : (2 * BN >= 256 ? 256 : 128);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES * STAGE_BYTES + 128);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES + i); };
-  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES + 2 + i); };
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  const int total_items = 9 * a.co_tiles * a.ci_tiles * a.splits;
-  auto decode = [&](int item, int& tap, int& mt, int& nt, int& sp) {
-    sp = item % a.splits; item /= a.splits;
-    nt = item % a.ci_tiles; item /= a.ci_tiles;
-    mt = item % a.co_tiles; tap = item / a.co_tiles;
-  };
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int tap, mt, nt, sp;
-        decode(item, tap, mt, nt, sp);
-        const int shift = (tap / 3 - 1) * a.Wp + (tap % 3 - 1);
-        for (int kb = 0; kb < a.kb_per_split; kb++, it++) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          const int col = a.guard + (sp * a.kb_per_split + kb) * BK;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          tma_load_2d(sa, &tmA_hi, full_bar(s), col, mt * BM);
-          tma_load_2d(sa + A_TILE_BYTES, &tmA_lo, full_bar(s), col, mt * BM);
-#pragma unroll
-          for (int j = 0; j < BN / 64; j++) {  // [64 positions][64 channels] boxes, one per 64-wide N group
-            tma_load_2d(sa + 2 * A_TILE_BYTES + j * 8192, &tmB_hi, full_bar(s), nt * BN + j * 64, col + shift);
-            tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES + j * 8192, &tmB_lo, full_bar(s), nt * BN + j * 64, col + shift);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN) | (1u << 16);  // B operand MN-major
-      uint32_t it = 0, tcount = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, tcount++) {
-        const int acc = tcount & 1;
-        const uint32_t aph = (tcount >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < a.kb_per_split; kb++, it++) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * STAGE_BYTES;
-          const uint64_t dAh = make_desc_sw<BK>(sa), dAl = make_desc_sw<BK>(sa + A_TILE_BYTES);
-          const uint64_t dBh = make_desc_mn_sw128(sa + 2 * A_TILE_BYTES, 8192), dBl = make_desc_mn_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, 8192);
-#pragma unroll
-          for (int ks = 0; ks < BK / 16; ks++) {
-            const uint64_t adv = (uint64_t)(ks * 32 >> 4);          // A: 16 fp16 along K inside the swizzle atom
-            const uint64_t advb = (uint64_t)(ks * 16 * 128 >> 4);   // B: 16 K-rows of 128 B
-            umma_f16(d_tmem, dAh + adv, dBh + advb, idesc, (kb | ks) ? 1u : 0u);
-            if (a.passes >= 2) umma_f16(d_tmem, dAh + adv, dBl + advb, idesc, 1u);
-            if (a.passes >= 3) umma_f16(d_tmem, dAl + adv, dBh + advb, idesc, 1u);
-          }
-          umma_commit(empty_bar(s));
-        }
-        umma_commit(tfull_bar(acc));
-      }
-    }
-  } else {
-    const int quad = warp & 3;
-    uint32_t tcount = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, tcount++) {
-      int tap, mt, nt, sp;
-      decode(item, tap, mt, nt, sp);
-      const int acc = tcount & 1;
-      const uint32_t aph = (tcount >> 1) & 1;
-      mbar_wait(tfull_bar(acc), aph);
-      tc_fence_after();
-      const int co = mt * BM + quad * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      float* o = a.partial + ((size_t)(sp * 9 + tap) * a.Co + co) * a.Ci + nt * BN;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t ra[32];
-        tmem_ld32(t_row + c0, ra);
-        tmem_ld_wait();
-        if (co < a.Co) {
-#pragma unroll
-          for (int q = 0; q < 8; q++)
-            reinterpret_cast<float4*>(o + c0)[q] = make_float4(__uint_as_float(ra[4 * q]), __uint_as_float(ra[4 * q + 1]),
-                                                               __uint_as_float(ra[4 * q + 2]), __uint_as_float(ra[4 * q + 3]));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
-  }
-}
-// dW[co][ci][tap] = 2^-(ea+eb) * sum_split partial[split][tap][co][ci]
-__global__ void k_dw_reduce(const float* __restrict__ partial, int splits, int Co, int Ci, const int* __restrict__ ea,
-                            const int* __restrict__ eb, float* __restrict__ dW) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Co * Ci) return;
-  const float sc = exp2f(-(float)(exp_decode(ea) + exp_decode(eb)));
-  const size_t tap_stride = (size_t)Co * Ci;
-  for (int tap = 0; tap < 9; tap++) {
-    float acc = 0.0f;
-    for (int sp = 0; sp < splits; sp++) acc += partial[(size_t)(sp * 9 + tap) * tap_stride + idx];
-    dW[(size_t)idx * 9 + tap] = acc * sc;
-  }
-}
-// NCHW fp32 [B][C][HW] -> channel-major hi/lo [C][ld] at column guard + b*S + y*(W+1) + x, scaled by 2^(*exp)
-__global__ void k_pack_cmajor(const float* __restrict__ x, int B, int C, int H, int W, int ld, int guard, int S,
-                              const int* __restrict__ exp_in, __half* hi, __half* lo) {
-  const int HW = H * W, Wp = W + 1;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * C * HW) return;
-  const int hw = (int)(idx % HW), c = (int)((idx / HW) % C), b = (int)(idx / ((size_t)HW * C));
-  const int y = hw / W, xx = hw - y * W;
-  const float v = x[idx] * exp2f((float)exp_decode(exp_in));
-  const __half h = __float2half_rn(v);
-  const size_t o = (size_t)c * ld + guard + (size_t)b * S + y * Wp + xx;
-  hi[o] = h;
-  lo[o] = __float2half_rn(v - __half2float(h));
-}
-
 // fp32 NCHW planes -> zero-bordered NHWC fp16 hi/lo (channels padded to cpad)
 __global__ void k_pack_planes(const float* __restrict__ planes, const int* __restrict__ n_dev, int n_max, int F, int H,
                               int W, int cpad, int guard, int S, float scale, __half* hi, __half* lo) {
@@ -887,75 +341,18 @@ __global__ void k_head_convs_nhwc(const __half* __restrict__ hi, const __half* _
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-    if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled not available");
-    fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-// 2-D fp16 row-major [rows][cols] tensor, box {bk cols, box_rows}, swizzle = row bytes of the box
-CUtensorMap make_map(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, int bk) {
-  CUtensorMap m;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)bk, box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
-  return m;
-}
-
-// fused-pair affine: fp32 [rows = board positions][cols = 4 floats per channel], box {32 floats = 128 B, 32 rows}
-CUtensorMap make_map_aff(void* base, uint64_t rows, uint64_t cols) {
-  CUtensorMap m;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 4};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(affine) failed: " + std::to_string((int)r));
-  return m;
-}
-
-// per-sample layout: 3-D fp16 tensor [n][S][cols], box {64 cols, BM positions, 1 sample}
-CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk) {
-  CUtensorMap m;
-  cuuint64_t dims[3] = {cols, S, n};
-  cuuint64_t strides[2] = {cols * 2, S * cols * 2};
-  cuuint32_t box[3] = {(cuuint32_t)bk, BM, 1};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(3d) failed: " + std::to_string((int)r));
-  return m;
-}
-
-// dynamic shared memory opt-in of every instantiation, on the current device (the attribute is per function and per
-// device; called from the allocators, which run with the engine's device current)
+// dynamic shared memory opt-in of every instantiation this file launches, on the current device (the attribute is per
+// function and per device; called from the allocator, which runs with the engine's device current)
 template <int BN, bool PAIR, int BKT>
 void set_conv_attr() {
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc<BN, PAIR, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN, BKT, PAIR)));
 }
-void tc_configure_device() {
+void tower_configure_device() {
   set_conv_attr<256, true, 64>(); set_conv_attr<128, true, 64>(); set_conv_attr<256, false, 64>(); set_conv_attr<128, false, 64>();
   set_conv_attr<64, false, 64>();
   set_conv_attr<256, true, 32>(); set_conv_attr<128, true, 32>(); set_conv_attr<256, false, 32>(); set_conv_attr<128, false, 32>();
   set_conv_attr<64, false, 32>();
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
-  CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(256, 64)));
-  CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(128, 64)));
-  CUDA_CHECK(cudaFuncSetAttribute(k_dw_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(64, 64)));
 }
 
 struct Layer {
@@ -1033,12 +430,13 @@ void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const C
 
 }  // namespace
 
+
 bool tc_tower_supported(const NetDims& d) {
   return (d.K == 64 || d.K == 128 || d.K == 256) && d.F <= 64 && d.SharedLayers >= 0;
 }
 
 void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2) {
-  tc_configure_device();
+  tower_configure_device();
   Impl* I = new Impl;
   t.impl = I;
   I->d = d; I->n_max = n_max; I->ea = act_scale_log2;
@@ -1236,239 +634,4 @@ void tc_tower_profile_collect(TcTower& t, cudaStream_t st, double* conv_ms, doub
   for (auto& sp : I->conv_spans) { float ms; CUDA_CHECK(cudaEventElapsedTime(&ms, I->ev_pool[sp.first], I->ev_pool[sp.second])); *conv_ms += ms; *conv_launches += 1; }
   for (auto& sp : I->fwd_spans) { float ms; CUDA_CHECK(cudaEventElapsedTime(&ms, I->ev_pool[sp.first], I->ev_pool[sp.second])); *fwd_ms += ms; *fwd_calls += 1; }
   I->conv_spans.clear(); I->fwd_spans.clear(); I->ev_used = 0;
-}
-
-
-// =================================================================================================
-// K7 on tensor cores: the 3x3 convolutions of dual.Train (forward and backward-data) through the
-// same tcgen05 kernel in raw mode.  Both are the shifted-operand contraction
-//   out[p, n] = sum_tap sum_k A[p + shift(tap), k] * Bm[n, tap*C + k]
-// forward: A = x, Bm = filter;  backward-data: A = dz, Bm[ci, tap*Co + co] = filter[co][ci][8 - tap].
-// Operands arrive as fp32 NCHW (the training pass keeps that layout); they are split into fp16 hi/lo
-// at a data-dependent power-of-two scale (absmax -> exponent on device, gradients span many decades).
-namespace {
-
-__global__ void k_absmax_exp(const float* __restrict__ x, size_t n, int* exp_out) {
-  __shared__ float sh[32];
-  float m = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
-#pragma unroll
-  for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    m = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0f;
-#pragma unroll
-    for (int off = 16; off; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    // scale so that the largest magnitude lands in [2^13, 2^14): hi below fp16 overflow, lo as far from underflow as possible
-    if (threadIdx.x == 0) atomicMax(exp_out, (m > 0.0f && isfinite(m)) ? ilogbf(m) - 13 : -0x7fffffff);  // stores -e (max over blocks)
-  }
-}
-
-
-// NCHW fp32 [B][C][HW] -> flat zero-bordered NHWC hi/lo [guard + B*S][cpad], scaled by 2^e.  Tile = 64 channels x
-// 32 board points through shared memory: reads coalesced along hw, writes 128-byte runs along the channels.
-__global__ void __launch_bounds__(256) k_pack_nchw(const float* __restrict__ x, int B, int C, int H, int W, int cpad, int guard, int S,
-                                                   const int* __restrict__ exp_in, __half* hi, __half* lo) {
-  __shared__ float t[64][33];
-  const int HW = H * W, Wp = W + 1;
-  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const float sc = exp2f((float)exp_decode(exp_in));
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int c = c0 + ty + 8 * i, hw = hw0 + tx;
-    t[ty + 8 * i][tx] = (c < C && hw < HW) ? x[((size_t)b * C + c) * HW + hw] * sc : 0.0f;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int hw = hw0 + ty + 8 * i;
-    if (hw >= HW) continue;
-    const int y = hw / W, xx = hw - y * W;
-    const size_t o = ((size_t)guard + (size_t)b * S + y * Wp + xx) * cpad + c0 + 2 * tx;
-    const float v0 = t[2 * tx][ty + 8 * i], v1 = t[2 * tx + 1][ty + 8 * i];
-    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-    *reinterpret_cast<__half2*>(hi + o) = __halves2half2(h0, h1);
-    *reinterpret_cast<__half2*>(lo + o) = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
-  }
-}
-// flat NHWC fp32 [guard + B*S][ld] -> NCHW [B][C][HW] (assign or accumulate); 32 x 32 tiles through shared memory
-__global__ void __launch_bounds__(256) k_unpack_nchw(const float* __restrict__ raw, int B, int C, int H, int W, int ld, int guard, int S,
-                                                     float* out, int accumulate) {
-  __shared__ float t[32][33];
-  const int HW = H * W, Wp = W + 1;
-  const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int hw = hw0 + ty + 8 * i, c = c0 + tx;
-    float v = 0.0f;
-    if (hw < HW && c < C) { const int y = hw / W, xx = hw - y * W; v = raw[((size_t)guard + (size_t)b * S + y * Wp + xx) * ld + c]; }
-    t[ty + 8 * i][tx] = v;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int c = c0 + ty + 8 * i, hw = hw0 + tx;
-    if (c < C && hw < HW) {
-      const size_t o = ((size_t)b * C + c) * HW + hw;
-      if (accumulate) out[o] += t[tx][ty + 8 * i]; else out[o] = t[tx][ty + 8 * i];
-    }
-  }
-}
-// filter [Co][Ci][3][3] -> Bm hi/lo [rows][9*cpad]; flip = backward-data operand (rows = Ci, K = tap*Co + co, mirrored taps)
-__global__ void k_prep_filter(const float* __restrict__ w, int Co, int Ci, int cpad, int flip, const int* __restrict__ exp_in,
-                              __half* hi, __half* lo) {
-  const int rows = flip ? Ci : Co, kin = flip ? Co : Ci;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)rows * 9 * cpad) return;
-  const int kc = (int)(idx % cpad), tap = (int)((idx / cpad) % 9), row = (int)(idx / ((size_t)9 * cpad));
-  float v = 0.0f;
-  if (kc < kin) v = flip ? w[((size_t)kc * Ci + row) * 9 + (8 - tap)] : w[((size_t)row * Ci + kc) * 9 + tap];
-  v *= exp2f((float)exp_decode(exp_in));
-  const __half h = __float2half_rn(v);
-  hi[idx] = h;
-  lo[idx] = __float2half_rn(v - __half2float(h));
-}
-
-}  // namespace
-
-struct TcGemmImpl {
-  NetDims d;
-  int B, guard, S, rows_alloc, num_sms, cmax;
-  __half *a_hi = nullptr, *a_lo = nullptr;  // A operand [(rows)][cmax]
-  __half *w_hi = nullptr, *w_lo = nullptr;  // B operand [cmax][9*cmax]
-  float* raw = nullptr;                     // [(rows)][cmax]
-  int *exp_a = nullptr, *exp_b = nullptr, *dB = nullptr;
-  // backward-filter A operand (dz), channel-major [max(K,128)][ld]; the B operand (x) reuses a_hi/a_lo
-  __half *t_hi = nullptr, *t_lo = nullptr;
-  float* partial = nullptr;
-  int* exp_t = nullptr;
-  int ld = 0, splits = 1, kb_per_split = 0, crow = 0;
-  int last_cpad = 0;  // channel pitch the A buffers currently hold (their zero borders are only valid for that pitch)
-};
-
-bool tc_gemm_supported(const NetDims& d) { return d.K == 64 || d.K == 128 || d.K == 256; }
-
-void tc_gemm_create(TcGemm& g, const NetDims& d, int B) {
-  tc_configure_device();
-  TcGemmImpl* I = new TcGemmImpl;
-  g.impl = I;
-  I->d = d; I->B = B;
-  I->guard = ((d.W + 2 + 7) / 8) * 8;
-  I->S = (d.H + 1) * (d.W + 1);
-  I->rows_alloc = I->guard + B * I->S + I->guard + BM;
-  I->cmax = d.K;
-  int dev;
-  CUDA_CHECK(cudaGetDevice(&dev));
-  CUDA_CHECK(cudaDeviceGetAttribute(&I->num_sms, cudaDevAttrMultiProcessorCount, dev));
-  auto alloc_h = [&](size_t n) { __half* p; CUDA_CHECK(cudaMalloc(&p, n * 2)); CUDA_CHECK(cudaMemset(p, 0, n * 2)); return p; };
-  I->a_hi = alloc_h((size_t)I->rows_alloc * I->cmax); I->a_lo = alloc_h((size_t)I->rows_alloc * I->cmax);
-  I->w_hi = alloc_h((size_t)I->cmax * 9 * I->cmax); I->w_lo = alloc_h((size_t)I->cmax * 9 * I->cmax);
-  CUDA_CHECK(cudaMalloc(&I->raw, (size_t)I->rows_alloc * I->cmax * 4));
-  CUDA_CHECK(cudaMalloc(&I->exp_a, 4)); CUDA_CHECK(cudaMalloc(&I->exp_b, 4)); CUDA_CHECK(cudaMalloc(&I->dB, 4));
-  CUDA_CHECK(cudaMemcpy(I->dB, &B, 4, cudaMemcpyHostToDevice));
-  // backward-filter: K = positions, split so that 9 * tiles * splits fills the SMs once
-  {
-    const int bn = std::min(256, d.K), tiles = ((d.K + BM - 1) / BM) * (d.K / bn);
-    const int kb_total = (B * I->S + 63) / 64;
-    I->splits = std::max(1, std::min(kb_total, I->num_sms / (9 * tiles)));
-    I->kb_per_split = (kb_total + I->splits - 1) / I->splits;
-    I->ld = I->guard + I->splits * I->kb_per_split * 64 + I->guard + 64;
-    I->crow = std::max(d.K, BM);
-    I->t_hi = alloc_h((size_t)I->crow * I->ld); I->t_lo = alloc_h((size_t)I->crow * I->ld);
-    CUDA_CHECK(cudaMalloc(&I->partial, (size_t)I->splits * 9 * d.K * d.K * 4));
-    CUDA_CHECK(cudaMalloc(&I->exp_t, 4));
-  }
-}
-void tc_gemm_destroy(TcGemm& g) {
-  TcGemmImpl* I = (TcGemmImpl*)g.impl;
-  if (!I) return;
-  cudaFree(I->a_hi); cudaFree(I->a_lo); cudaFree(I->w_hi); cudaFree(I->w_lo); cudaFree(I->raw);
-  cudaFree(I->exp_a); cudaFree(I->exp_b); cudaFree(I->dB);
-  cudaFree(I->t_hi); cudaFree(I->t_lo); cudaFree(I->partial); cudaFree(I->exp_t);
-  delete I;
-  g.impl = nullptr;
-}
-
-static void absmax_exp(const float* x, size_t n, int* e, cudaStream_t st) {
-  CUDA_CHECK(cudaMemsetAsync(e, 0x80, 4, st));  // 0x80808080: below every real exponent
-  unsigned blocks = (unsigned)std::min<size_t>((n + 1023) / 1024, 1024);
-  k_absmax_exp<<<blocks, 256, 0, st>>>(x, n, e);
-}
-
-// out (NCHW [B][Cout][HW]) (+)= conv3x3(x (NCHW [B][Cin][HW]), filter [Co][Ci][3][3]) or its backward-data twin
-void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int fCo, int fCi, bool flip, float* out, int Cout,
-                  bool accumulate, cudaStream_t st, unsigned long long* launches) {
-  TcGemmImpl* I = (TcGemmImpl*)g.impl;
-  const NetDims& d = I->d;
-  const int HW = d.HW();
-  const int cpad = (Cin + 63) & ~63;           // K-chunk granularity of the kernel
-  if (cpad > I->cmax || Cout > I->cmax || (Cout % 64) != 0) throw std::runtime_error("tc_gemm_conv: unsupported channel count");
-  if (I->last_cpad != cpad) {
-    CUDA_CHECK(cudaMemsetAsync(I->a_hi, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    CUDA_CHECK(cudaMemsetAsync(I->a_lo, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    I->last_cpad = cpad;
-  }
-  absmax_exp(x, (size_t)I->B * Cin * HW, I->exp_a, st);
-  absmax_exp(filter, (size_t)fCo * fCi * 9, I->exp_b, st);
-  {
-    k_pack_nchw<<<dim3((HW + 31) / 32, cpad / 64, I->B), 256, 0, st>>>(x, I->B, Cin, d.H, d.W, cpad, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
-    size_t wt = (size_t)Cout * 9 * cpad;
-    k_prep_filter<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(filter, fCo, fCi, cpad, flip ? 1 : 0, I->exp_b, I->w_hi, I->w_lo);
-  }
-  const int bn = std::min(256, Cout);
-  // tensor maps over the (re-used) operand buffers for this shape
-  CUtensorMap mAh = make_map(I->a_hi, I->rows_alloc, cpad, BM, 64), mAl = make_map(I->a_lo, I->rows_alloc, cpad, BM, 64);
-  CUtensorMap mBh = make_map(I->w_hi, Cout, (uint64_t)9 * cpad, bn, 64), mBl = make_map(I->w_lo, Cout, (uint64_t)9 * cpad, bn, 64);
-  ConvArgs a;
-  a.n_dev = I->dB; a.n_max = I->B; a.S = I->S; a.Wp = d.W + 1; a.H = d.H; a.W = d.W; a.guard = I->guard; a.mode3d = 0; a.tps = 1;
-  a.cin = cpad; a.n_total = Cout; a.cout = Cout; a.aff = nullptr; a.out_hi = nullptr; a.out_lo = nullptr; a.act_scale = 1.0f;
-  a.err = nullptr; a.passes = 3; a.out_raw = I->raw; a.exp_a = I->exp_a; a.exp_b = I->exp_b;
-  const int max_tiles = ((I->B * I->S + BM - 1) / BM) * (Cout / bn);
-  const int grid = std::min(I->num_sms, max_tiles);
-  auto launch = [&](auto kern, int BNv) {
-    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, mBh, a);
-  };
-  if (bn == 256) launch(k_conv3x3_tc<256, false, 64>, 256);
-  else if (bn == 128) launch(k_conv3x3_tc<128, false, 64>, 128);
-  else launch(k_conv3x3_tc<64, false, 64>, 64);
-  {
-    k_unpack_nchw<<<dim3((HW + 31) / 32, (Cout + 31) / 32, I->B), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0);
-  }
-  if (launches) *launches += 6;
-}
-
-// dW[Co][Ci][3][3] = backward-filter of conv3x3 for x (NCHW [B][Ci][HW]) and dz (NCHW [B][Co][HW]); Ci == Co == K
-void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStream_t st, unsigned long long* launches) {
-  TcGemmImpl* I = (TcGemmImpl*)g.impl;
-  const NetDims& d = I->d;
-  const int C = d.K, HW = d.HW();
-  const size_t n = (size_t)I->B * C * HW;
-  if (I->last_cpad != C) {
-    CUDA_CHECK(cudaMemsetAsync(I->a_hi, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    CUDA_CHECK(cudaMemsetAsync(I->a_lo, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    I->last_cpad = C;
-  }
-  absmax_exp(dz, n, I->exp_t, st);
-  absmax_exp(x, n, I->exp_a, st);
-  k_pack_cmajor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, I->B, C, d.H, d.W, I->ld, I->guard, I->S, I->exp_t, I->t_hi, I->t_lo);
-  k_pack_nchw<<<dim3((HW + 31) / 32, C / 64, I->B), 256, 0, st>>>(x, I->B, C, d.H, d.W, C, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
-  const int bn = std::min(256, C);
-  CUtensorMap mAh = make_map(I->t_hi, I->crow, I->ld, BM, 64), mAl = make_map(I->t_lo, I->crow, I->ld, BM, 64);
-  CUtensorMap mBh = make_map(I->a_hi, I->rows_alloc, C, 64, 64), mBl = make_map(I->a_lo, I->rows_alloc, C, 64, 64);
-  DwArgs a;
-  a.co_tiles = (C + BM - 1) / BM; a.ci_tiles = C / bn; a.splits = I->splits; a.kb_per_split = I->kb_per_split;
-  a.guard = I->guard; a.Wp = d.W + 1; a.Co = C; a.Ci = C; a.partial = I->partial; a.passes = 3;
-  const int items = 9 * a.co_tiles * a.ci_tiles * a.splits;
-  const int grid = std::min(I->num_sms, items);
-  auto launch = [&](auto kern, int BNv) {
-    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, a);
-  };
-  if (bn == 256) launch(k_dw_tc<256>, 256);
-  else if (bn == 128) launch(k_dw_tc<128>, 128);
-  else launch(k_dw_tc<64>, 64);
-  k_dw_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(I->partial, I->splits, C, C, I->exp_t, I->exp_a, dW);
-  if (launches) *launches += 6;
 }
