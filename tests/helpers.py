@@ -165,3 +165,21 @@ def tame_gammas(engines, net, seed, target=0.9):
     for e in engines:
         e.net_set(net, p)
     return p
+
+
+def check_workers_golden(lib):
+    """tests/golden/workers_search.npz (tools/make_workers_golden.py): trees after the first Search and move records of
+    games searched with mcts.Config workers > 1 under the fixed schedule."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_workers_golden as M
+    gold = np.load(os.path.join(root, "tests", "golden", "workers_search.npz"))
+    for name, desc, table, values in M.cases():
+        trees, moves = M.run(lib, desc, table, values)
+        for i, t in enumerate(trees):
+            g = gold["%s_tree%d" % (name, i)]
+            assert t.shape == g.shape and (t == g).all(), (name, "tree", i)
+        for i, m in enumerate(moves):
+            assert list(m) == list(gold["%s_moves%d" % (name, i)]), (name, "moves", i)

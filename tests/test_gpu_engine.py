@@ -128,6 +128,11 @@ def test_parity_concurrent_workers(oracle, engine_lib, game, workers, sims):
     assert ca["sims"] == ca["searches"] * sims
 
 
+def test_engine_workers_golden(engine_lib):
+    """The committed worker-schedule fixture (generated from the oracle) reproduced by the device engine, bit for bit."""
+    H.check_workers_golden(engine_lib)
+
+
 def test_concurrent_workers_dual_net(oracle, engine_lib):
     """The same schedule with the dual network in the loop (fp32 tower): batch = games x workers per round."""
     def desc():

@@ -67,3 +67,7 @@ def test_oracle_single_worker_is_default(oracle):
         e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
         runs.append(H.play_and_collect(e, 2))
     H.assert_same_run(runs[0], runs[1], "workers 0 vs 1")
+
+
+def test_oracle_workers_golden(oracle):
+    H.check_workers_golden(oracle)
