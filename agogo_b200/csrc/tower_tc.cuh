@@ -21,13 +21,20 @@ void tc_tower_forward(TcTower& t, const NetLayout& L, const Snapshot& s, Fp32Scr
                       const int* n_dev, int n_max, float* policy, int ldp, float* value, int* err_flag, cudaStream_t st,
                       unsigned long long* launches);
 
-// K7: the 3x3 convolutions of the training pass (forward, backward-data) on the same tcgen05 kernel (raw epilogue)
+// K7: the 3x3 convolutions of the training pass (forward, backward-data, backward-filter) on tcgen05 (train_tc.cu)
 struct TcGemm { void* impl = nullptr; };
+enum {
+  TC_OPERAND_PACK = 0,           // absmax -> exponent, split into fp16 hi/lo into the slot
+  TC_OPERAND_PACK_KEEP_EXP = 1,  // split with the exponent the slot already holds (same tensor seen by an earlier call)
+  TC_OPERAND_REUSE = 2,          // the slot already holds this tensor
+};
 bool tc_gemm_supported(const NetDims& d);
 void tc_gemm_create(TcGemm& g, const NetDims& d, int B);
 void tc_gemm_destroy(TcGemm& g);
-// out[B][Cout][HW] (+)= conv3x3(x[B][Cin][HW], filter[fCo][fCi][3][3]); flip = backward-data (x = dz, Cin = fCo, Cout = fCi)
+// out[B][Cout][HW] (+)= conv3x3(x[B][Cin][HW], filter[fCo][fCi][3][3]); flip = backward-data (x = dz, Cin = fCo, Cout = fCi).
+// x is staged in operand slot a_slot (0: activations, 1: gradients) according to a_state.
 void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int fCo, int fCi, bool flip, float* out, int Cout,
-                  bool accumulate, cudaStream_t st, unsigned long long* launches);
-// dW[K][K][3][3] = sum over batch and positions of dz (x) shifted x  (backward-filter of a K->K 3x3 layer)
-void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStream_t st, unsigned long long* launches);
+                  bool accumulate, int a_slot, int a_state, cudaStream_t st, unsigned long long* launches);
+// dW[K][K][3][3] = sum over batch and positions of dz (x) shifted x  (backward-filter of a K->K 3x3 layer); x via slot 0,
+// the exponent of dz is left in slot 1
+void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, int x_state, cudaStream_t st, unsigned long long* launches);

@@ -404,11 +404,13 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   auto Pp = [&](int i) { return P + L.desc[i].offset; };
   auto Gp = [&](int i) { return T->grads + L.desc[i].offset; };
   unsigned long long nl = 0;
-  auto unit_fwd = [&](int ui, const float* x) {
+  // same_x: x is the tensor the previous tensor-core call of this pass staged (the second branch of a block)
+  auto unit_fwd = [&](int ui, const float* x, bool same_x = false) {
     const UnitH& u = L.units[ui];
     size_t n = (size_t)B * u.Co * HW;
     if (T->tc.impl && u.k == 3 && u.Co % 64 == 0)
-      tc_gemm_conv(T->tc, x, u.Ci, Pp(u.filter), u.Co, u.Ci, false, T->z[ui], u.Co, false, st, &nl);
+      tc_gemm_conv(T->tc, x, u.Ci, Pp(u.filter), u.Co, u.Ci, false, T->z[ui], u.Co, false, 0,
+                   same_x ? TC_OPERAND_REUSE : TC_OPERAND_PACK, st, &nl);
     else
       k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
     k_bn_stats<<<u.Co, 1024, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
@@ -421,7 +423,7 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   const size_t act = (size_t)B * K * HW;
   for (int i = 0; i < Lr; i++) {
     unit_fwd(1 + 2 * i, cur);
-    unit_fwd(2 + 2 * i, cur);
+    unit_fwd(2 + 2 * i, cur, true);
     k_add_relu<<<nblk(act), 256, 0, st>>>(T->y[1 + 2 * i], T->y[2 + 2 * i], T->cur[i + 1], act);
     nl++;
     cur = T->cur[i + 1];
@@ -446,13 +448,14 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   k_linear_bwd_in<<<nblk((size_t)B * HW), 256, 0, st>>>(Pp(L.vW), T->dh1, T->dvh, B, HW, FC);
   nl += 7;
   // ---- backward: units
-  auto unit_bwd = [&](int ui, const float* x, const float* dy, float* dx) {
+  auto unit_bwd = [&](int ui, const float* x, const float* dy, float* dx, bool same_x = false) {
     const UnitH& u = L.units[ui];
     size_t n = (size_t)B * u.Co * HW;
     k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n);
     k_bn_bwd_apply<<<u.Co, 1024, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
-    if (T->tc.impl && u.k == 3 && u.Ci == K && u.Co == K)
-      tc_gemm_dw(T->tc, x, T->tmp, Gp(u.filter), st, &nl);
+    const bool dw_tc = T->tc.impl && u.k == 3 && u.Ci == K && u.Co == K;
+    if (dw_tc)
+      tc_gemm_dw(T->tc, x, T->tmp, Gp(u.filter), same_x ? TC_OPERAND_REUSE : TC_OPERAND_PACK, st, &nl);
     else {
       const int slices = dw_slices(u, B * HW);
       const size_t nw = (size_t)u.Co * u.Ci * u.k * u.k;
@@ -462,7 +465,9 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
     }
     nl += 3;
     if (dx && T->tc.impl && u.k == 3 && u.Ci % 64 == 0 && u.Co % 64 == 0) {
-      tc_gemm_conv(T->tc, T->tmp, u.Co, Pp(u.filter), u.Co, u.Ci, true, dx, u.Ci, true, st, &nl);
+      // dz = T->tmp: its exponent was computed by the backward-filter call just above
+      tc_gemm_conv(T->tc, T->tmp, u.Co, Pp(u.filter), u.Co, u.Ci, true, dx, u.Ci, true, 1,
+                   dw_tc ? TC_OPERAND_PACK_KEEP_EXP : TC_OPERAND_PACK, st, &nl);
     } else if (dx) {  // dx += conv(dz, mirrored transposed filter)
       k_flip_filter<<<nblk((size_t)u.Ci * u.Co * u.k * u.k), 256, 0, st>>>(Pp(u.filter), T->wflip, u.Ci, u.Co, u.k);
       k_conv_fwd_tiled<true><<<dim3((B * HW + TT - 1) / TT, (u.Ci + TT - 1) / TT), 256, 0, st>>>(T->tmp, T->wflip, dx, B, u.Co, u.Ci, H, W, u.k);
@@ -480,7 +485,7 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
     CUDA_CHECK(cudaMemsetAsync(T->dprev, 0, act * 4, st));
     const float* xin = i == 0 ? T->y[0] : T->cur[i];
     unit_bwd(1 + 2 * i, xin, T->dl, T->dprev);
-    unit_bwd(2 + 2 * i, xin, T->dl, T->dprev);
+    unit_bwd(2 + 2 * i, xin, T->dl, T->dprev, true);
     std::swap(T->dcur, T->dprev);
   }
   unit_bwd(0, T->X, T->dcur, nullptr);

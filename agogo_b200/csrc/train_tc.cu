@@ -280,16 +280,22 @@ void train_configure_device() {
 struct TcGemmImpl {
   NetDims d;
   int B, guard, S, rows_alloc, num_sms, cmax;
-  __half *a_hi = nullptr, *a_lo = nullptr;  // A operand [(rows)][cmax]
+  // Two position-major (NHWC, zero-bordered) fp16 hi/lo operand slots [(rows)][cmax] with their power-of-two exponents:
+  // slot 0 holds activations x (forward A operand, backward-filter B operand), slot 1 holds gradients dz (backward-data
+  // A operand).  Keeping them apart lets the two branches of a block share one pack of x, and the backward-filter and
+  // backward-data passes of a unit share one absmax of dz.
+  struct Slot {
+    __half *hi = nullptr, *lo = nullptr;
+    int* exp = nullptr;
+    int cpad = 0;  // channel pitch the buffers currently hold (their zero borders are only valid for that pitch)
+  } slot[2];
   __half *w_hi = nullptr, *w_lo = nullptr;  // B operand [cmax][9*cmax]
   float* raw = nullptr;                     // [(rows)][cmax]
-  int *exp_a = nullptr, *exp_b = nullptr, *dB = nullptr;
-  // backward-filter A operand (dz), channel-major [max(K,128)][ld]; the B operand (x) reuses a_hi/a_lo
+  int *exp_b = nullptr, *dB = nullptr;
+  // backward-filter A operand (dz), channel-major [max(K,128)][ld], scaled by slot[1].exp
   __half *t_hi = nullptr, *t_lo = nullptr;
   float* partial = nullptr;
-  int* exp_t = nullptr;
   int ld = 0, splits = 1, kb_per_split = 0, crow = 0;
-  int last_cpad = 0;  // channel pitch the A buffers currently hold (their zero borders are only valid for that pitch)
 };
 
 bool tc_gemm_supported(const NetDims& d) { return d.K == 64 || d.K == 128 || d.K == 256; }
@@ -307,10 +313,13 @@ void tc_gemm_create(TcGemm& g, const NetDims& d, int B) {
   CUDA_CHECK(cudaGetDevice(&dev));
   CUDA_CHECK(cudaDeviceGetAttribute(&I->num_sms, cudaDevAttrMultiProcessorCount, dev));
   auto alloc_h = [&](size_t n) { __half* p; CUDA_CHECK(cudaMalloc(&p, n * 2)); CUDA_CHECK(cudaMemset(p, 0, n * 2)); return p; };
-  I->a_hi = alloc_h((size_t)I->rows_alloc * I->cmax); I->a_lo = alloc_h((size_t)I->rows_alloc * I->cmax);
+  for (auto& sl : I->slot) {
+    sl.hi = alloc_h((size_t)I->rows_alloc * I->cmax); sl.lo = alloc_h((size_t)I->rows_alloc * I->cmax);
+    CUDA_CHECK(cudaMalloc(&sl.exp, 4));
+  }
   I->w_hi = alloc_h((size_t)I->cmax * 9 * I->cmax); I->w_lo = alloc_h((size_t)I->cmax * 9 * I->cmax);
   CUDA_CHECK(cudaMalloc(&I->raw, (size_t)I->rows_alloc * I->cmax * 4));
-  CUDA_CHECK(cudaMalloc(&I->exp_a, 4)); CUDA_CHECK(cudaMalloc(&I->exp_b, 4)); CUDA_CHECK(cudaMalloc(&I->dB, 4));
+  CUDA_CHECK(cudaMalloc(&I->exp_b, 4)); CUDA_CHECK(cudaMalloc(&I->dB, 4));
   CUDA_CHECK(cudaMemcpy(I->dB, &B, 4, cudaMemcpyHostToDevice));
   // backward-filter: K = positions, split so that 9 * tiles * splits fills the SMs once
   {
@@ -322,15 +331,15 @@ void tc_gemm_create(TcGemm& g, const NetDims& d, int B) {
     I->crow = std::max(d.K, BM);
     I->t_hi = alloc_h((size_t)I->crow * I->ld); I->t_lo = alloc_h((size_t)I->crow * I->ld);
     CUDA_CHECK(cudaMalloc(&I->partial, (size_t)I->splits * 9 * d.K * d.K * 4));
-    CUDA_CHECK(cudaMalloc(&I->exp_t, 4));
   }
 }
 void tc_gemm_destroy(TcGemm& g) {
   TcGemmImpl* I = (TcGemmImpl*)g.impl;
   if (!I) return;
-  cudaFree(I->a_hi); cudaFree(I->a_lo); cudaFree(I->w_hi); cudaFree(I->w_lo); cudaFree(I->raw);
-  cudaFree(I->exp_a); cudaFree(I->exp_b); cudaFree(I->dB);
-  cudaFree(I->t_hi); cudaFree(I->t_lo); cudaFree(I->partial); cudaFree(I->exp_t);
+  for (auto& sl : I->slot) { cudaFree(sl.hi); cudaFree(sl.lo); cudaFree(sl.exp); }
+  cudaFree(I->w_hi); cudaFree(I->w_lo); cudaFree(I->raw);
+  cudaFree(I->exp_b); cudaFree(I->dB);
+  cudaFree(I->t_hi); cudaFree(I->t_lo); cudaFree(I->partial);
   delete I;
   g.impl = nullptr;
 }
@@ -341,34 +350,48 @@ static void absmax_exp(const float* x, size_t n, int* e, cudaStream_t st) {
   k_absmax_exp<<<blocks, 256, 0, st>>>(x, n, e);
 }
 
-// out (NCHW [B][Cout][HW]) (+)= conv3x3(x (NCHW [B][Cin][HW]), filter [Co][Ci][3][3]) or its backward-data twin
+// Brings the NCHW tensor x [B][C][HW] into operand slot `si` according to `state`; returns the number of kernels launched.
+static int fill_slot(TcGemmImpl* I, int si, const float* x, int C, int state, cudaStream_t st) {
+  if (state == TC_OPERAND_REUSE) return 0;
+  const NetDims& d = I->d;
+  TcGemmImpl::Slot& sl = I->slot[si];
+  const int cpad = (C + 63) & ~63;  // K-chunk granularity of the kernel
+  if (sl.cpad != cpad) {
+    CUDA_CHECK(cudaMemsetAsync(sl.hi, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
+    CUDA_CHECK(cudaMemsetAsync(sl.lo, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
+    sl.cpad = cpad;
+  }
+  int n = 1;
+  if (state == TC_OPERAND_PACK) { absmax_exp(x, (size_t)I->B * C * d.HW(), sl.exp, st); n++; }
+  k_pack_nchw<<<dim3((d.HW() + 31) / 32, cpad / 64, I->B), 256, 0, st>>>(x, I->B, C, d.H, d.W, cpad, I->guard, I->S, sl.exp, sl.hi, sl.lo);
+  return n;
+}
+
+// out (NCHW [B][Cout][HW]) (+)= conv3x3(x (NCHW [B][Cin][HW]), filter [Co][Ci][3][3]) or its backward-data twin.
+// x goes through operand slot a_slot (0: activations, 1: gradients) according to a_state.
 void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int fCo, int fCi, bool flip, float* out, int Cout,
-                  bool accumulate, cudaStream_t st, unsigned long long* launches) {
+                  bool accumulate, int a_slot, int a_state, cudaStream_t st, unsigned long long* launches) {
   TcGemmImpl* I = (TcGemmImpl*)g.impl;
   const NetDims& d = I->d;
   const int HW = d.HW();
-  const int cpad = (Cin + 63) & ~63;           // K-chunk granularity of the kernel
+  const int cpad = (Cin + 63) & ~63;
   if (cpad > I->cmax || Cout > I->cmax || (Cout % 64) != 0) throw std::runtime_error("tc_gemm_conv: unsupported channel count");
-  if (I->last_cpad != cpad) {
-    CUDA_CHECK(cudaMemsetAsync(I->a_hi, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    CUDA_CHECK(cudaMemsetAsync(I->a_lo, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    I->last_cpad = cpad;
-  }
-  absmax_exp(x, (size_t)I->B * Cin * HW, I->exp_a, st);
+  TcGemmImpl::Slot& sl = I->slot[a_slot];
+  if (a_state == TC_OPERAND_REUSE && sl.cpad != cpad) throw std::runtime_error("tc_gemm_conv: operand slot does not hold this shape");
+  int nl = fill_slot(I, a_slot, x, Cin, a_state, st);
   absmax_exp(filter, (size_t)fCo * fCi * 9, I->exp_b, st);
   {
-    k_pack_nchw<<<dim3((HW + 31) / 32, cpad / 64, I->B), 256, 0, st>>>(x, I->B, Cin, d.H, d.W, cpad, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
     size_t wt = (size_t)Cout * 9 * cpad;
     k_prep_filter<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(filter, fCo, fCi, cpad, flip ? 1 : 0, I->exp_b, I->w_hi, I->w_lo);
   }
   const int bn = std::min(256, Cout);
   // tensor maps over the (re-used) operand buffers for this shape
-  CUtensorMap mAh = make_map(I->a_hi, I->rows_alloc, cpad, BM, 64), mAl = make_map(I->a_lo, I->rows_alloc, cpad, BM, 64);
+  CUtensorMap mAh = make_map(sl.hi, I->rows_alloc, cpad, BM, 64), mAl = make_map(sl.lo, I->rows_alloc, cpad, BM, 64);
   CUtensorMap mBh = make_map(I->w_hi, Cout, (uint64_t)9 * cpad, bn, 64), mBl = make_map(I->w_lo, Cout, (uint64_t)9 * cpad, bn, 64);
   ConvArgs a;
   a.n_dev = I->dB; a.n_max = I->B; a.S = I->S; a.Wp = d.W + 1; a.H = d.H; a.W = d.W; a.guard = I->guard; a.mode3d = 0; a.tps = 1;
   a.cin = cpad; a.n_total = Cout; a.cout = Cout; a.aff = nullptr; a.out_hi = nullptr; a.out_lo = nullptr; a.act_scale = 1.0f;
-  a.err = nullptr; a.passes = 3; a.out_raw = I->raw; a.exp_a = I->exp_a; a.exp_b = I->exp_b;
+  a.err = nullptr; a.passes = 3; a.out_raw = I->raw; a.exp_a = sl.exp; a.exp_b = I->exp_b;
   const int max_tiles = ((I->B * I->S + BM - 1) / BM) * (Cout / bn);
   const int grid = std::min(I->num_sms, max_tiles);
   auto launch = [&](auto kern, int BNv) {
@@ -377,30 +400,27 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   if (bn == 256) launch(k_conv3x3_tc<256, false, 64>, 256);
   else if (bn == 128) launch(k_conv3x3_tc<128, false, 64>, 128);
   else launch(k_conv3x3_tc<64, false, 64>, 64);
-  {
-    k_unpack_nchw<<<dim3((HW + 31) / 32, (Cout + 31) / 32, I->B), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0);
-  }
-  if (launches) *launches += 6;
+  k_unpack_nchw<<<dim3((HW + 31) / 32, (Cout + 31) / 32, I->B), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0);
+  if (launches) *launches += nl + 4;
 }
 
-// dW[Co][Ci][3][3] = backward-filter of conv3x3 for x (NCHW [B][Ci][HW]) and dz (NCHW [B][Co][HW]); Ci == Co == K
-void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStream_t st, unsigned long long* launches) {
+// dW[K][K][3][3] = backward-filter of a K->K 3x3 layer for x (NCHW [B][K][HW]) and dz (NCHW [B][K][HW]).
+// x goes through slot 0 according to x_state; the exponent of dz is left in slot 1 (a following backward-data call on the
+// same dz passes TC_OPERAND_PACK_KEEP_EXP).
+void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, int x_state, cudaStream_t st, unsigned long long* launches) {
   TcGemmImpl* I = (TcGemmImpl*)g.impl;
   const NetDims& d = I->d;
   const int C = d.K, HW = d.HW();
   const size_t n = (size_t)I->B * C * HW;
-  if (I->last_cpad != C) {
-    CUDA_CHECK(cudaMemsetAsync(I->a_hi, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    CUDA_CHECK(cudaMemsetAsync(I->a_lo, 0, (size_t)I->rows_alloc * I->cmax * 2, st));
-    I->last_cpad = C;
-  }
-  absmax_exp(dz, n, I->exp_t, st);
-  absmax_exp(x, n, I->exp_a, st);
-  k_pack_cmajor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, I->B, C, d.H, d.W, I->ld, I->guard, I->S, I->exp_t, I->t_hi, I->t_lo);
-  k_pack_nchw<<<dim3((HW + 31) / 32, C / 64, I->B), 256, 0, st>>>(x, I->B, C, d.H, d.W, C, I->guard, I->S, I->exp_a, I->a_hi, I->a_lo);
+  TcGemmImpl::Slot& sx = I->slot[0];
+  if (x_state == TC_OPERAND_REUSE && sx.cpad != C) throw std::runtime_error("tc_gemm_dw: operand slot does not hold this shape");
+  int nl = fill_slot(I, 0, x, C, x_state, st);
+  int* exp_dz = I->slot[1].exp;
+  absmax_exp(dz, n, exp_dz, st);
+  k_pack_cmajor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, I->B, C, d.H, d.W, I->ld, I->guard, I->S, exp_dz, I->t_hi, I->t_lo);
   const int bn = std::min(256, C);
   CUtensorMap mAh = make_map(I->t_hi, I->crow, I->ld, BM, 64), mAl = make_map(I->t_lo, I->crow, I->ld, BM, 64);
-  CUtensorMap mBh = make_map(I->a_hi, I->rows_alloc, C, 64, 64), mBl = make_map(I->a_lo, I->rows_alloc, C, 64, 64);
+  CUtensorMap mBh = make_map(sx.hi, I->rows_alloc, C, 64, 64), mBl = make_map(sx.lo, I->rows_alloc, C, 64, 64);
   DwArgs a;
   a.co_tiles = (C + BM - 1) / BM; a.ci_tiles = C / bn; a.splits = I->splits; a.kb_per_split = I->kb_per_split;
   a.guard = I->guard; a.Wp = d.W + 1; a.Co = C; a.Ci = C; a.partial = I->partial; a.passes = 3;
@@ -412,6 +432,6 @@ void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, cudaStrea
   if (bn == 256) launch(k_dw_tc<256>, 256);
   else if (bn == 128) launch(k_dw_tc<128>, 128);
   else launch(k_dw_tc<64>, 64);
-  k_dw_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(I->partial, I->splits, C, C, I->exp_t, I->exp_a, dW);
-  if (launches) *launches += 6;
+  k_dw_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(I->partial, I->splits, C, C, exp_dz, sx.exp, dW);
+  if (launches) *launches += nl + 4;
 }
