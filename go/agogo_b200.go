@@ -138,3 +138,62 @@ func (e *Engine) Train(net int, Xs, Pi, V []float32, batches, iterations int, se
 	return check(e, C.az_train(e.h, C.int32_t(net), (*C.float)(unsafe.Pointer(&Xs[0])), (*C.float)(unsafe.Pointer(&Pi[0])),
 		(*C.float)(unsafe.Pointer(&V[0])), C.int32_t(batches), C.int32_t(iterations), 0.1, C.uint64_t(seed), nil))
 }
+
+// InitNet replaces dual.New + Init (dual.go:33-48) and Arena.newB (arena.go:205-224): fresh random weights in `net`.
+func (e *Engine) InitNet(net int, seed uint64) error {
+	return check(e, C.az_net_init(e.h, C.int32_t(net), C.uint64_t(seed)))
+}
+
+// CopyNet replaces `A.NN = B.NN` on promotion (agogo.go:161).
+func (e *Engine) CopyNet(dst, src int) error {
+	return check(e, C.az_net_copy(e.h, C.int32_t(dst), C.int32_t(src)))
+}
+
+// ResetStats replaces Agent.resetStats (agent.go:115-121).
+func (e *Engine) ResetStats(agent int) error {
+	return check(e, C.az_agent_reset_stats(e.h, C.int32_t(agent)))
+}
+
+// Search replaces Agent.Search (agent.go:77-80) on a caller-owned game.State (GTP / analysis): the position is
+// marshalled into an az_state (board colours, side to move, move number, passes, last move and up to 8 historical
+// boards for the 18-plane encoder) and searched on a fresh device tree for mcts.Config sims iterations (in rounds of
+// `Workers` concurrent descents).  Returns the chosen move and the visit counts of the root's children ([A] + pass).
+func (e *Engine) Search(agent int, s game.State, player game.Player, actionSpace int) (game.Single, []float32, error) {
+	raw := s.Board()
+	board := make([]int32, len(raw))
+	for i, c := range raw {
+		board[i] = int32(c)
+	}
+	var st C.az_state
+	st.board = (*C.int32_t)(unsafe.Pointer(&board[0]))
+	st.to_move, st.move_number, st.passes = C.int32_t(s.ToMove()), C.int32_t(s.MoveNumber()), C.int32_t(s.Passes())
+	st.last_move = C.int32_t(s.LastMove().Single)
+	nHist := s.MoveNumber()
+	if nHist > 8 {
+		nHist = 8
+	}
+	var hist []int32
+	for i := s.MoveNumber() - nHist; i < s.MoveNumber(); i++ { // oldest first; Historical(i) = board before move i
+		for _, c := range s.Historical(i) {
+			hist = append(hist, int32(c))
+		}
+	}
+	if len(hist) == nHist*len(board) && nHist > 0 {
+		st.n_hist, st.hist = C.int32_t(nHist), (*C.int32_t)(unsafe.Pointer(&hist[0]))
+	}
+	var best C.int32_t
+	visits := make([]float32, actionSpace+1)
+	err := check(e, C.az_search(e.h, C.int32_t(agent), &st, C.int32_t(player), &best, (*C.float)(unsafe.Pointer(&visits[0]))))
+	return game.Single(best), visits, err
+}
+
+// CommInit joins the gradient all-reduce group of a multi-process Learn (one process per GPU): rank 0 obtains the id
+// with UniqueID and hands it to the other ranks (any host-side channel).  After it, Train reduces gradients over NVLink.
+func UniqueID() ([128]byte, error) {
+	var id [128]byte
+	rc := C.az_comm_unique_id((*C.uint8_t)(unsafe.Pointer(&id[0])))
+	return id, check(nil, rc)
+}
+func (e *Engine) CommInit(id [128]byte, rank, world int) error {
+	return check(e, C.az_comm_init(e.h, C.int32_t(rank), C.int32_t(world), (*C.uint8_t)(unsafe.Pointer(&id[0]))))
+}
