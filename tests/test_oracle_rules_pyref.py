@@ -1,0 +1,65 @@
+"""The C++ oracle's rules (oracle/mnk.hpp, c4.hpp, wq.hpp through az_rules_apply / az_rules_status) against a second,
+independent plain-Python restatement of the same Go sources (tests/pyref_rules.py) on random positions — the reference's
+own tests hold 8 + 6 + 7 boards (tests/golden); this widens the pin on the oracle itself."""
+import numpy as np
+import pytest
+
+from agogo_b200 import _capi as K
+from tests import helpers as H
+from tests import pyref_rules as R
+
+
+def _boards(rng, n, cells, p_empty):
+    p = [p_empty, (1 - p_empty) / 2, (1 - p_empty) / 2]
+    return rng.choice([0, 1, 2], size=(n, cells), p=p).astype(np.int32)
+
+
+@pytest.mark.parametrize("m,n,k", [(3, 3, 3), (5, 5, 4), (4, 6, 3), (6, 4, 4)])
+def test_mnk_rules_vs_python(oracle, m, n, k):
+    rng = np.random.default_rng(m * 100 + n * 10 + k)
+    e = H.rules_engine(oracle, K.GAME_MNK, m, n, k)
+    boards = np.concatenate([_boards(rng, 150, m * n, 0.5), _boards(rng, 150, m * n, 0.15)])
+    players = rng.integers(1, 3, len(boards)).astype(np.int32)
+    moves = rng.integers(-1, m * n, len(boards)).astype(np.int32)
+    chk, app, out, taken = e.rules_apply(boards, players, moves)
+    ended, winner, sb, sw = e.rules_status(boards)
+    for i, b in enumerate(boards.tolist()):
+        c, a, o, t = R.mnk_apply(b, int(players[i]), int(moves[i]))
+        assert (bool(chk[i]), bool(app[i]), out[i].tolist(), int(taken[i])) == (c, a, o, t), (i, b, moves[i])
+        assert (bool(ended[i]), int(winner[i]), float(sb[i]), float(sw[i])) == R.mnk_status(b, m, n, k), (i, b)
+
+
+@pytest.mark.parametrize("rows,cols,nn", [(6, 7, 4), (5, 5, 3), (4, 8, 4)])
+def test_c4_rules_vs_python(oracle, rows, cols, nn):
+    rng = np.random.default_rng(rows * 100 + cols * 10 + nn)
+    e = H.rules_engine(oracle, K.GAME_C4, rows, cols, nn)
+    boards = np.concatenate([_boards(rng, 150, rows * cols, 0.5), _boards(rng, 150, rows * cols, 0.1)])
+    players = rng.integers(1, 3, len(boards)).astype(np.int32)
+    moves = rng.integers(-1, cols, len(boards)).astype(np.int32)
+    passes = rng.integers(0, 5, len(boards)).astype(np.int32)
+    chk, app, out, taken = e.rules_apply(boards, players, moves)
+    ended, winner, sb, sw = e.rules_status(boards, passes)
+    for i, b in enumerate(boards.tolist()):
+        c, a, o, t = R.c4_apply(b, rows, cols, int(players[i]), int(moves[i]))
+        assert (bool(chk[i]), bool(app[i]), out[i].tolist(), int(taken[i])) == (c, a, o, t), (i, b, moves[i])
+        assert (bool(ended[i]), int(winner[i]), float(sb[i]), float(sw[i])) == R.c4_status(b, rows, cols, nn, int(passes[i])), (i, b)
+
+
+@pytest.mark.parametrize("size", [5, 7, 9])
+def test_wq_rules_vs_python(oracle, size):
+    rng = np.random.default_rng(size)
+    e = H.rules_engine(oracle, K.GAME_WQ, size, size)
+    cells = size * size
+    base = np.concatenate([_boards(rng, 12, cells, 0.45), _boards(rng, 12, cells, 0.2)])
+    boards, players, moves = [], [], []
+    for j, b in enumerate(base):
+        for mv in range(cells):  # every point, occupied ones included (Game.Check does not reject them)
+            boards.append(b); players.append(1 + (mv + j) % 2); moves.append(mv)
+    boards = np.array(boards, np.int32)
+    chk, app, out, taken = e.rules_apply(boards, players, moves)
+    for i, b in enumerate(boards.tolist()):
+        c, a, o, t = R.wq_apply(b, size, players[i], moves[i])
+        assert (bool(chk[i]), bool(app[i]), out[i].tolist(), int(taken[i])) == (c, a, o, t), (i, moves[i])
+    _, _, sb, sw = e.rules_status(base)
+    for i, b in enumerate(base.tolist()):
+        assert (float(sb[i]), float(sw[i])) == (R.wq_score(b, size, 1), R.wq_score(b, size, 2)), i
