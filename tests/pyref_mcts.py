@@ -1,0 +1,367 @@
+"""A second, independent restatement of the reference's mcts package (tree.go, node.go, search.go, utils.go) in plain
+Python with numpy float32 scalars — written from the Go sources, not from oracle/mcts.hpp — used only to cross-check the
+C++ oracle's search bit for bit (tests/test_oracle_mcts_pyref.py).  Same canonical choices as the oracle: one worker,
+exactly `sims` pipeline calls per Search, Go's unstable sort.Sort pinned to a stable sort.  Game: m,n,k (mnk.go) driven
+the way mcts/example_test.go drives it — ONE tree searched by both colours, the caller applies the move to the shared
+state.  Evaluator: a table keyed by state.MoveNumber() (the Example's dummyNN shape)."""
+import numpy as np
+
+f32 = np.float32
+PASS, NIL = -1, -1
+BLACK, WHITE = 1, 2
+MAXTREESIZE = 25000000
+INVALID, ACTIVE = 0, 1
+
+
+def opponent(p):
+    return WHITE if p == BLACK else BLACK
+
+
+class MNK:  # game/mnk/mnk.go
+    def __init__(self, m, n, k):
+        self.m, self.n, self.k = m, n, k
+        self.board = [0] * (m * n)
+        self.history, self.hist_ptr, self.next = [], 0, 0
+
+    def clone(self):  # mnk.go:208-219
+        c = MNK(self.m, self.n, self.k)
+        c.board, c.history, c.hist_ptr, c.next = list(self.board), list(self.history), self.hist_ptr, self.next
+        return c
+
+    def move_number(self):
+        return len(self.history)
+
+    def passes(self):
+        return -1
+
+    def last_move(self):
+        return self.history[self.hist_ptr - 1] if self.history else (0, PASS)
+
+    def check(self, player, move):
+        if move == PASS:
+            return False
+        if move >= len(self.board):
+            return False
+        return self.board[move] == 0
+
+    def apply(self, player, move):  # in place
+        if not self.check(player, move):
+            return self
+        self.board[move] = player
+        self.hist_ptr += 1
+        if len(self.history) < self.hist_ptr:
+            self.history.append((player, move))
+        else:
+            self.history[self.hist_ptr - 1] = (player, move)
+        self.next = opponent(player)
+        return self
+
+    def undo_last_move(self):
+        if self.history:
+            self.board[self.history[self.hist_ptr - 1][1]] = 0
+            self.hist_ptr -= 1
+
+    def fwd(self):
+        if self.history:
+            self.hist_ptr += 1
+
+    def eq(self, other):
+        return self.board == other.board
+
+    def is_winner(self, colour):
+        from tests.pyref_rules import mnk_is_winner
+        return mnk_is_winner(self.board, self.m, self.n, self.k, colour)
+
+    def ended(self):
+        if self.is_winner(BLACK):
+            return True, BLACK
+        if self.is_winner(WHITE):
+            return True, WHITE
+        return all(c != 0 for c in self.board), 0
+
+
+class Node:
+    __slots__ = ("move", "visits", "status", "black", "min_psa", "score")
+
+    def __init__(self):
+        self.move, self.visits, self.status = 0, 0, 0
+        self.black, self.min_psa, self.score = f32(0), f32(2.0), f32(0)
+
+    def has_children(self):
+        return self.min_psa <= f32(1)
+
+    def is_expandable(self, r):
+        return f32(r) < self.min_psa
+
+    def evaluate(self, player):  # node.go:147-159 (virtual loss is 0 under one worker)
+        bs = self.black
+        if player == WHITE:
+            bs = f32(bs + f32(0))
+        s = f32(bs / f32(self.visits))
+        if player == WHITE:
+            s = f32(f32(1) - s)
+        return s
+
+
+class MCTS:
+    def __init__(self, game, puct, sims, table, values, M, N):
+        self.g, self.puct, self.sims, self.table, self.values = game, f32(puct), sims, table, values
+        self.max_depth = M * N
+        self.nodes, self.children, self.freelist, self.freeables = [], [], [], []
+        self.root, self.prev = NIL, None
+        self.evals = 0
+
+    # ---- tree.go
+    def alloc(self):
+        if not self.freelist:
+            self.nodes.append(Node())
+            self.children.append([])
+            return len(self.nodes) - 1
+        return self.freelist.pop()
+
+    def new(self, move, score):
+        n = self.alloc()
+        nd = self.nodes[n]
+        nd.move, nd.visits, nd.status, nd.score = move, 1, ACTIVE, f32(score)
+        return n
+
+    def free(self, n):
+        self.children[n] = []
+        self.freelist.append(n)
+        nd = self.nodes[n]
+        nd.move, nd.visits, nd.status, nd.black, nd.min_psa, nd.score = -1, 0, 0, f32(0), f32(2.0), f32(0)
+
+    def clean_children(self, root):
+        for kid in self.children[root]:
+            self.nodes[kid].status = INVALID
+            self.freeables.append(kid)
+            self.clean_children(kid)
+        self.children[root] = []
+
+    def cleanup(self, old, new):
+        for kid in self.children[old]:
+            if kid != new:
+                self.nodes[kid].status = INVALID
+                self.freeables.append(kid)
+                self.clean_children(kid)
+        self.children[old] = [new]
+
+    def find_child(self, n, move):
+        for kid in self.children[n]:
+            if self.nodes[kid].move == move:
+                return kid
+        return NIL
+
+    def min_psa_ratio(self):
+        ratio = f32(len(self.nodes)) / f32(MAXTREESIZE)  # node count: far below either threshold in these tests
+        return f32(0.01) if ratio > 0.95 else (f32(0.001) if ratio > 0.5 else f32(0))
+
+    # ---- the evaluator
+    def infer(self, state):
+        self.evals += 1
+        mn = state.move_number()
+        if 0 <= mn < len(self.table):
+            return self.table[mn], f32(self.values[mn])
+        return np.zeros(self.table.shape[1], np.float32), f32(0)
+
+    # ---- search.go
+    def expand_and_simulate(self, parent, state, min_psa_ratio):
+        n = self.nodes[parent]
+        if not n.is_expandable(min_psa_ratio):
+            return f32(0), False
+        if state.passes() >= 2:
+            return f32(0), False
+        policy, value = self.infer(state)
+        pass_prob = policy[len(policy) - 1]
+        player = state.next
+        if player == WHITE:
+            value = f32(f32(1) - value)
+        nodelist, legal_sum = [], f32(0)
+        for i in range(len(self.g.board)):
+            if state.check(player, i):
+                nodelist.append([i, f32(policy[i])])
+                legal_sum = f32(legal_sum + f32(policy[i]))
+        if state.check(player, PASS):
+            nodelist.append([PASS, f32(pass_prob)])
+            legal_sum = f32(legal_sum + f32(pass_prob))
+        if legal_sum > np.finfo(np.float32).smallest_subnormal:
+            for p in nodelist:
+                p[1] = f32(p[1] / legal_sum)
+        else:
+            with np.errstate(divide="ignore"):  # an empty list gives +Inf in Go too (float division), unused
+                prob = f32(f32(1) / f32(len(nodelist)))
+            for p in nodelist:
+                p[1] = prob
+        if not nodelist:
+            return value, True
+        nodelist.sort(key=lambda p: -float(p[1]))  # stable, best score first
+        max_psa = nodelist[0][1]
+        old_min = f32(max_psa * n.min_psa)
+        new_min = f32(max_psa * min_psa_ratio)
+        skipped = False
+        for move, score in nodelist:
+            if score < new_min:
+                skipped = True
+            elif score < old_min:
+                if self.find_child(parent, move) == NIL:
+                    self.children[parent].append(self.new(move, score))
+        n.min_psa = f32(min_psa_ratio) if skipped else f32(0)
+        return value, True
+
+    def select(self, nid, player):  # node.go:170-237
+        kids = self.children[nid]
+        parent_visits = 0
+        for kid in kids:
+            c = self.nodes[kid]
+            if c.status != INVALID:
+                parent_visits += c.visits
+        best, best_value = NIL, f32(-np.inf)
+        numerator = np.sqrt(f32(parent_visits))
+        for kid in kids:
+            c = self.nodes[kid]
+            if c.status != ACTIVE:
+                continue
+            assert c.visits > 0  # nodes are born with one visit (tree.go:110): the fpu branch is dead
+            qsa = c.evaluate(player)
+            denominator = f32(f32(1.0) + f32(c.visits))
+            last = f32(numerator / denominator)
+            puct = f32(f32(self.puct * c.score) * last)
+            usa = f32(qsa + puct)
+            if usa > best_value:
+                best_value, best = usa, kid
+        assert best != NIL
+        return best
+
+    def update(self, nid, score):
+        nd = self.nodes[nid]
+        nd.visits += 1
+        nd.black = f32(nd.black + f32(score))
+
+    def pipeline(self, cur, start, depth):
+        """Returns the result or None for the null result."""
+        depth += 1
+        if depth > self.max_depth:
+            return None
+        player = cur.next
+        n = self.nodes[start]
+        ret = None
+        if n.is_expandable(0) and cur.passes() >= 2:
+            raise AssertionError("mnk never passes")
+        elif n.is_expandable(0) and len(self.nodes) < MAXTREESIZE:
+            had = n.has_children()
+            value, ok = self.expand_and_simulate(start, cur, self.min_psa_ratio())
+            if not had and ok:
+                ret = value
+        if n.has_children() and ret is None:
+            nxt = self.select(start, player)
+            move = self.nodes[nxt].move
+            if cur.check(player, move):
+                cur = cur.apply(player, move)
+                ret = self.pipeline(cur, nxt, depth)
+        if ret is not None:
+            self.update(start, ret)
+        return ret
+
+    def new_root_state(self):
+        if self.root == NIL or self.prev is None:
+            return False
+        depth = self.g.move_number() - self.prev.move_number()
+        if depth < 0:
+            return False
+        tmp = self.g.clone()
+        for _ in range(depth):
+            tmp.undo_last_move()
+        if not tmp.eq(self.prev):
+            return False
+        for _ in range(depth):
+            tmp.fwd()
+            player, move = tmp.last_move()
+            old = self.root
+            new = self.find_child(old, move)
+            if new == NIL:
+                return False
+            self.root = new
+            self.cleanup(old, new)
+            self.prev = self.prev.apply(player, move)
+        if self.g.move_number() != self.prev.move_number():
+            return False
+        return self.g.eq(self.prev)
+
+    def update_root(self):
+        self.freeables = []
+        player = self.g.next
+        if not self.new_root_state() or self.root == NIL:
+            if self.g.check(player, PASS):
+                self.root = self.new(PASS, 0)
+            else:
+                for i in range(len(self.g.board)):
+                    if self.g.check(player, i):
+                        self.root = self.new(i, 0)
+                        break
+        self.prev = None
+        if not self.children[self.root]:
+            self.nodes[self.root].min_psa = f32(2.0)
+
+    def prepare_root(self, player):
+        root = self.nodes[self.root]
+        had = len(self.children[self.root]) > 0
+        value = f32(0)
+        if root.is_expandable(0):
+            value, _ = self.expand_and_simulate(self.root, self.g, self.min_psa_ratio())
+        if not had:
+            self.update(self.root, value)
+
+    def fancy_less(self, player, a, b):  # utils.go:17-47
+        li, lj = self.nodes[a], self.nodes[b]
+        if li.visits != lj.visits:
+            return li.visits > lj.visits
+        if li.visits == 0:
+            return li.score > lj.score
+        return li.evaluate(player) > lj.evaluate(player)
+
+    def best_move(self):  # search.go:341-390 with Config{DontPreferPass, DumbPass, RandomCount 0, ResignPercentage 0}
+        player = self.g.next
+        kids = self.children[self.root]
+        # stable insertion sort by fancySort.Less
+        out = []
+        for k in kids:
+            i = len(out)
+            while i > 0 and self.fancy_less(player, k, out[i - 1]):
+                i -= 1
+            out.insert(i, k)
+        kids[:] = out
+        if not kids:
+            return PASS
+        best = self.nodes[kids[0]].move
+        if best == PASS:  # DontPreferPass: first child that is not a pass and passes Check (noPass, search.go:531-545)
+            for kid in kids:
+                mv = self.nodes[kid].move
+                if mv != PASS and self.g.check(player, mv):
+                    best = mv
+                    break
+        return best  # shouldResign: ResignPercentage == 0 -> never
+
+    def search(self, player):
+        self.update_root()
+        self.g.next = player
+        for f in self.freeables:
+            self.free(f)
+        self.prepare_root(player)
+        for _ in range(self.sims):
+            self.pipeline(self.g.clone(), self.root, 0)
+        assert self.nodes[self.root].has_children()
+        best = self.best_move()
+        self.prev = self.g.clone()
+        return best
+
+    def dump(self):
+        rows = []
+
+        def rec(nid, d):
+            n = self.nodes[nid]
+            rows.append((d, n.move, n.visits, int(np.float32(n.black).view(np.uint32)), int(np.float32(n.score).view(np.uint32)),
+                         1 if n.has_children() else 0, len(self.children[nid])))
+            for kid in self.children[nid]:
+                rec(kid, d + 1)
+        rec(self.root, 0)
+        return np.array(rows, np.int64)
