@@ -28,6 +28,9 @@ class MNK:  # game/mnk/mnk.go
         c.board, c.history, c.hist_ptr, c.next = list(self.board), list(self.history), self.hist_ptr, self.next
         return c
 
+    def action_space(self):
+        return self.m * self.n
+
     def move_number(self):
         return len(self.history)
 
@@ -78,6 +81,84 @@ class MNK:  # game/mnk/mnk.go
         if self.is_winner(WHITE):
             return True, WHITE
         return all(c != 0 for c in self.board), 0
+
+
+class C4:  # game/c4/c4.go + game/c4/game.go, quirks kept: Apply never flips the player, MoveNumber() is always 1,
+    # Passes() is always 0, Clone pads history / historical with two zero entries, Eq compares other's board with itself
+    def __init__(self, rows, cols, nn):
+        self.rows, self.cols, self.nn = rows, cols, nn
+        self.board = [0] * (rows * cols)
+        self.history, self.historical = [], []
+        self.next, self.hist_ptr, self.move_count, self.pass_count = 0, 0, 0, 0
+
+    def clone(self):  # game.go:131-150
+        c = C4(self.rows, self.cols, self.nn)
+        c.board = list(self.board)
+        c.history = list(self.history) + [(0, 0), (0, 0)]
+        c.historical = [list(h) for h in self.historical] + [None, None]
+        c.next, c.hist_ptr, c.move_count, c.pass_count = self.next, self.hist_ptr, self.move_count, self.pass_count
+        return c
+
+    def action_space(self):
+        return self.cols
+
+    def move_number(self):
+        return self.move_count + 1
+
+    def passes(self):
+        return 0
+
+    def last_move(self):
+        return self.history[self.hist_ptr - 1] if self.history else (0, PASS)
+
+    def _drop_row(self, col):
+        for row in range(self.rows - 1, -1, -1):
+            if self.board[row * self.cols + col] == 0:
+                return row
+        return None
+
+    def check(self, player, move):
+        return move == PASS or self._drop_row(move) is not None
+
+    def apply(self, player, move):  # game.go:55-72, in place
+        hb = list(self.board)
+        ok = True
+        if move != PASS:
+            row = self._drop_row(move)
+            if row is None:
+                ok = False
+            else:
+                self.board[row * self.cols + move] = player
+        if ok:
+            self.history.append((player, move))
+            self.historical.append(hb)
+            self.hist_ptr += 1
+        self.pass_count = self.pass_count + 1 if move == PASS else 0
+        return self
+
+    def undo_last_move(self):
+        raise AssertionError("MoveNumber() is constant: newRootState never undoes a c4 move")
+
+    def fwd(self):
+        if self.history:
+            self.hist_ptr += 1
+
+    def eq(self, ot):  # game.go:98-129
+        if self.hist_ptr != ot.hist_ptr or self.move_count != ot.move_count:
+            return False
+        if len(self.history) != len(ot.history) or len(self.historical) != len(ot.historical):
+            return False
+        if any(a != b for a, b in zip(self.history, ot.history)):
+            return False
+        for a, b in zip(self.historical, ot.historical):
+            if a is not None and any(x != y for x, y in zip(a, b)):
+                return False
+        return True
+
+    def ended(self):
+        from tests.pyref_rules import c4_status
+        e, w, _, _ = c4_status(self.board, self.rows, self.cols, self.nn, self.pass_count)
+        return e, w
 
 
 class Node:
@@ -177,7 +258,7 @@ class MCTS:
         if player == WHITE:
             value = f32(f32(1) - value)
         nodelist, legal_sum = [], f32(0)
-        for i in range(len(self.g.board)):
+        for i in range(self.g.action_space()):
             if state.check(player, i):
                 nodelist.append([i, f32(policy[i])])
                 legal_sum = f32(legal_sum + f32(policy[i]))
@@ -246,7 +327,7 @@ class MCTS:
         n = self.nodes[start]
         ret = None
         if n.is_expandable(0) and cur.passes() >= 2:
-            raise AssertionError("mnk never passes")
+            raise AssertionError("neither mnk nor c4 ever report two passes")
         elif n.is_expandable(0) and len(self.nodes) < MAXTREESIZE:
             had = n.has_children()
             value, ok = self.expand_and_simulate(start, cur, self.min_psa_ratio())
@@ -294,7 +375,7 @@ class MCTS:
             if self.g.check(player, PASS):
                 self.root = self.new(PASS, 0)
             else:
-                for i in range(len(self.g.board)):
+                for i in range(self.g.action_space()):
                     if self.g.check(player, i):
                         self.root = self.new(i, 0)
                         break

@@ -60,3 +60,38 @@ def test_random_tables_vs_python(oracle, m, n, k, sims, seed):
     table /= table.sum(axis=1, keepdims=True)
     values = rng.uniform(0.02, 0.98, m * n + 2).astype(np.float32)
     _run_pair(oracle, m, n, k, sims, table, values, seed)
+
+
+@pytest.mark.parametrize("rows,cols,nn,sims,seed", [(6, 7, 4, 40, 11), (5, 5, 3, 60, 12), (4, 6, 4, 25, 13)])
+def test_c4_search_vs_python(oracle, rows, cols, nn, sims, seed):
+    """Connect-4 under the same flow: Pass is a legal child of every node, Apply never flips the side to move (so the
+    whole descent evaluates for the searching colour), MoveNumber() is the constant 1, no tree reuse, DontPreferPass picks
+    the first non-pass child when Pass sorts first."""
+    rng = np.random.default_rng(seed)
+    table = rng.random((3, cols + 1)).astype(np.float32)
+    table[:, cols] *= 3  # make Pass competitive so that noPass matters
+    table /= table.sum(axis=1, keepdims=True)
+    values = rng.uniform(0.05, 0.95, 3).astype(np.float32)
+    d = K.make_desc(K.GAME_C4, rows, cols, nn, sims=sims, nn=H.tiny_nn(rows, cols, cols + 1), n_games=1, flags=K.FLAG_SHARED_TREE,
+                    seed=seed, mcts_m=rows, mcts_n=cols)
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_TABLE)
+    e.set_table(0, table, values)
+    e.arena_begin(1, False)
+    g = P.C4(rows, cols, nn)
+    t = P.MCTS(g, 1.0, sims, table, values, rows, cols)
+    player, moves_py, alive, ply = P.BLACK, [], 1, 0
+    while alive:
+        assert not g.ended()[0]
+        best = t.search(player)
+        alive = e.arena_step()
+        got = e.tree_dump(0, 0).astype(np.int64) & 0xFFFFFFFF
+        want = t.dump() & 0xFFFFFFFF
+        assert got.shape == want.shape and (got == want).all(), (ply, got[:3], want[:3])
+        g.apply(player, best)
+        moves_py.append(best)
+        player = P.opponent(player)
+        ply += 1
+    rec = e.game_record(0)
+    e.arena_finish()
+    assert list(rec["moves"]) == moves_py and g.ended() == (True, rec["winner"])
