@@ -185,8 +185,10 @@ class Node:
 
 
 class MCTS:
-    def __init__(self, game, puct, sims, table, values, M, N):
+    def __init__(self, game, puct, sims, table, values, M, N, evaluator=None):
         self.g, self.puct, self.sims, self.table, self.values = game, f32(puct), sims, table, values
+        self.evaluator = evaluator  # callable(state) -> (policy, value); None = table keyed by MoveNumber()
+        self.cached_policies = {}   # tree.go:75: (board, move) -> count
         self.max_depth = M * N
         self.nodes, self.children, self.freelist, self.freeables = [], [], [], []
         self.root, self.prev = NIL, None
@@ -240,6 +242,8 @@ class MCTS:
     # ---- the evaluator
     def infer(self, state):
         self.evals += 1
+        if self.evaluator is not None:
+            return self.evaluator(state)
         mn = state.move_number()
         if 0 <= mn < len(self.table):
             return self.table[mn], f32(self.values[mn])
@@ -431,9 +435,21 @@ class MCTS:
         for _ in range(self.sims):
             self.pipeline(self.g.clone(), self.root, 0)
         assert self.nodes[self.root].has_children()
+        board_key = tuple(self.g.board)  # stands for current.Hash() taken before the move (search.go:96)
         best = self.best_move()
         self.prev = self.g.clone()
+        self.cached_policies[(board_key, best)] = self.cached_policies.get((board_key, best), 0.0) + 1.0
         return best
+
+    def policies(self, state):  # tree.go:128-142: counts of the moves Search chose at this board, normalised
+        key = tuple(state.board)
+        a1 = state.action_space() + 1
+        ret = np.array([self.cached_policies.get((key, i), 0.0) for i in range(a1)], np.float32)
+        total = f32(0)
+        for v in ret:
+            total = f32(total + v)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return (ret / total).astype(np.float32)
 
     def dump(self):
         rows = []
@@ -446,3 +462,64 @@ class MCTS:
                 rec(kid, d + 1)
         rec(self.root, 0)
         return np.array(rows, np.int64)
+
+
+# ---------------------------------------------------------------- arena.go / agent.go / dummy.go / cmd/tictactoe encoder
+_M64 = (1 << 64) - 1
+
+
+def _splitmix(s):  # the injected RNG specification (include/agogo_b200.h): splitmix64
+    s = (s + 0x9E3779B97F4A7C15) & _M64
+    z = s
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return s, z ^ (z >> 31)
+
+
+def derive_seed(seed, stream):
+    return _splitmix((seed ^ ((0xD1B54A32D192ED03 * (stream + 1)) & _M64)) & _M64)[1]
+
+
+def encode_two_plane(state):  # cmd/tictactoe/main.go:26-47
+    board = np.array([1.0 if c == BLACK else (-1.0 if c == WHITE else 0.001) for c in state.board], np.float32)
+    nxt = state.next
+    plane = np.full(len(state.board), 1.0 if nxt == BLACK else (-1.0 if nxt == WHITE else 0.0), np.float32)
+    return np.concatenate([board, plane])
+
+
+def dummy_evaluator(action_space, captured_player):  # dummy.go: uniform 1/outputSize over outputSize entries
+    value = f32(1 if captured_player == BLACK else (-1 if captured_player == WHITE else 0))
+    policy = np.full(action_space, f32(1) / f32(action_space), np.float32)
+    return lambda state: (policy, value)
+
+
+def arena_play(new_game, make_mcts, coin, record=True):
+    """Arena.Play (arena.go:80-179) for one game.  make_mcts(agent_index, game) builds the agent's fresh MCTS.  Returns
+    (moves, winner, a_player, examples [(board, policy, value)], per-ply dumps [(tree A, tree B)])."""
+    g = new_game()
+    trees = [make_mcts(0, g), make_mcts(1, g)]
+    players = [BLACK, WHITE] if coin == 0 else [WHITE, BLACK]
+    cur = 0 if coin == 0 else 1
+    g.next = players[cur]
+    moves, examples, dumps, pass_count = [], [], [], 0
+    while True:
+        ended, winner = g.ended()
+        if ended:
+            break
+        t = trees[cur]
+        best = t.search(players[cur])  # Agent.Search: SetGame(g) + Search(a.Player)
+        pass_count = pass_count + 1 if best == PASS else 0
+        if record:
+            pol = t.policies(g)
+            if np.isfinite(pol).all():
+                examples.append([encode_two_plane(g), pol, float(players[cur])])
+        dumps.append([tr.dump() if tr.root != NIL else np.zeros((0, 7), np.int64) for tr in trees])
+        g.apply(players[cur], best)
+        moves.append(best)
+        cur ^= 1
+        if pass_count >= 2:
+            ended, winner = g.ended()
+            break
+    for ex in examples:
+        ex[2] = 0.0 if winner == 0 else (1.0 if ex[2] == float(winner) else -1.0)
+    return moves, winner, players[0], examples, dumps

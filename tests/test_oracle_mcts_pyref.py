@@ -95,3 +95,43 @@ def test_c4_search_vs_python(oracle, rows, cols, nn, sims, seed):
     rec = e.game_record(0)
     e.arena_finish()
     assert list(rec["moves"]) == moves_py and g.ended() == (True, rec["winner"])
+
+
+@pytest.mark.parametrize("m,n,k,sims,dummy,seed", [(3, 3, 3, 30, (0, 0), 11), (3, 3, 3, 60, (1, 2), 12), (4, 4, 3, 25, (2, 1), 13)])
+def test_arena_two_agents_vs_python(oracle, m, n, k, sims, dummy, seed):
+    """Arena.Play with two agents, each searching its own tree (reuse across its own plies: two moves deep), the
+    dummyInferer, the coin flips of the injected RNG stream, examples (two-plane encoder, Policies = normalised counts of
+    the chosen move, colour -> outcome labels) and the win/loss/draw statistics: the oracle against the Python restatement."""
+    G_ = 6
+    d = K.make_desc(K.GAME_MNK, m, n, k, sims=sims, nn=H.tiny_nn(m, n, m * n + 1), n_games=G_, seed=seed)
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, dummy[0]); e.set_inferer(1, K.INF_DUMMY, dummy[1])
+    run = H.play_and_collect(e, G_)
+    state = P.derive_seed(seed, 0)
+    ex_all, stats = [], [[0, 0, 0], [0, 0, 0]]
+    for g in range(G_):
+        state, r = P._splitmix(state)
+        coin = r % 2
+        def make(agent, game):
+            return P.MCTS(game, 1.0, sims, None, None, m, n, evaluator=P.dummy_evaluator(m * n, dummy[agent]))
+        moves, winner, a_player, examples, dumps = P.arena_play(lambda: P.MNK(m, n, k), make, coin)
+        rec = run["records"][g]
+        assert list(rec["moves"]) == moves and rec["winner"] == winner and rec["a_player"] == a_player and rec["n_examples"] == len(examples)
+        for ply, (ta, tb) in enumerate(dumps):
+            for t, want in enumerate((ta, tb)):
+                got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
+                assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (g, ply, t)
+        ex_all += examples
+        b_player = P.opponent(a_player)
+        if winner == 0:
+            stats[0][2] += 1; stats[1][2] += 1
+        elif winner == a_player:
+            stats[0][0] += 1; stats[1][1] += 1
+        elif winner == b_player:
+            stats[1][0] += 1; stats[0][1] += 1
+    boards, pols, vals = run["examples"]
+    assert len(ex_all) == len(vals)
+    for i, (b, p, v) in enumerate(ex_all):
+        assert (boards[i] == b).all() and (pols[i] == p).all() and vals[i] == v, i
+    for a in (0, 1):
+        assert tuple(run["stats"][a]) == tuple(float(x) for x in stats[a])
