@@ -18,6 +18,8 @@ def opponent(p):
 
 
 class MNK:  # game/mnk/mnk.go
+    supports_undo = True
+
     def __init__(self, m, n, k):
         self.m, self.n, self.k = m, n, k
         self.board = [0] * (m * n)
@@ -85,6 +87,8 @@ class MNK:  # game/mnk/mnk.go
 
 class C4:  # game/c4/c4.go + game/c4/game.go, quirks kept: Apply never flips the player, MoveNumber() is always 1,
     # Passes() is always 0, Clone pads history / historical with two zero entries, Eq compares other's board with itself
+    supports_undo = True
+
     def __init__(self, rows, cols, nn):
         self.rows, self.cols, self.nn = rows, cols, nn
         self.board = [0] * (rows * cols)
@@ -159,6 +163,64 @@ class C4:  # game/c4/c4.go + game/c4/game.go, quirks kept: Apply never flips the
         from tests.pyref_rules import c4_status
         e, w, _, _ = c4_status(self.board, self.rows, self.cols, self.nn, self.pass_count)
         return e, w
+
+
+class WQ:  # game/wq/wq.go + game/wq/game.go.  What the reference leaves unfinished (it panics) follows the repository's
+    # stated completion (DESIGN.md §2 "wq gap"): pass = board no-op + passes++ (a stone resets it), historical = board
+    # before each move, Score = Board.Score as implemented, no undo (so no tree reuse), Apply returns a new state.
+    supports_undo = False
+
+    def __init__(self, size, komi):
+        self.size, self.komi = size, komi
+        self.board = [0] * (size * size)
+        self.history, self.historical = [], []
+        self.next, self.n_passes = BLACK, 0
+
+    def clone(self):
+        c = WQ(self.size, self.komi)
+        c.board, c.history, c.historical = list(self.board), list(self.history), list(self.historical)
+        c.next, c.n_passes = self.next, self.n_passes
+        return c
+
+    def action_space(self):
+        return self.size * self.size
+
+    def move_number(self):
+        return len(self.history)
+
+    def passes(self):
+        return self.n_passes
+
+    def check(self, player, move):  # game.go:65-79: occupied points are not rejected
+        from tests.pyref_rules import wq_board_check
+        if move == PASS:
+            return True
+        if move >= len(self.board):
+            return False
+        return wq_board_check(self.board, self.size, player, move)[1]
+
+    def apply(self, player, move):  # game.go:81-92: a new state; Board.Apply's error is ignored
+        from tests.pyref_rules import wq_apply
+        ns = self.clone()
+        ns.historical.append(list(self.board))
+        if move == PASS:
+            ns.n_passes = self.n_passes + 1
+        else:
+            ns.board = wq_apply(self.board, self.size, player, move)[2]
+            ns.n_passes = 0
+        ns.next = opponent(player)
+        ns.history.append((player, move))
+        return ns
+
+    def score(self, p):
+        from tests.pyref_rules import wq_score
+        return f32(wq_score(self.board, self.size, p))
+
+    def ended(self):  # game.go:94-115
+        if self.n_passes < 2:
+            return False, 0
+        ws, bs = self.score(WHITE), self.score(BLACK)
+        return True, (0 if ws == bs else (WHITE if ws > bs else BLACK))
 
 
 class Node:
@@ -330,8 +392,8 @@ class MCTS:
         player = cur.next
         n = self.nodes[start]
         ret = None
-        if n.is_expandable(0) and cur.passes() >= 2:
-            raise AssertionError("neither mnk nor c4 ever report two passes")
+        if n.is_expandable(0) and cur.passes() >= 2:  # search.go:226-228, utils.go:62-67
+            ret = f32(f32(cur.score(BLACK) - cur.score(WHITE)) - f32(cur.komi))
         elif n.is_expandable(0) and len(self.nodes) < MAXTREESIZE:
             had = n.has_children()
             value, ok = self.expand_and_simulate(start, cur, self.min_psa_ratio())
@@ -352,6 +414,8 @@ class MCTS:
             return False
         depth = self.g.move_number() - self.prev.move_number()
         if depth < 0:
+            return False
+        if depth > 0 and not self.g.supports_undo:  # wq: UndoLastMove panics in the reference -> a fresh root
             return False
         tmp = self.g.clone()
         for _ in range(depth):
@@ -493,7 +557,28 @@ def dummy_evaluator(action_space, captured_player):  # dummy.go: uniform 1/outpu
     return lambda state: (policy, value)
 
 
-def arena_play(new_game, make_mcts, coin, record=True):
+def encode_wq18(state):  # encoding_helper.go:29-68
+    size = len(state.board)
+    out = np.zeros(18 * size, np.float32)
+    if state.next == BLACK:
+        bstart, wstart, nstart, enc = 0, 8 * size, 16 * size, 1.0
+    else:
+        bstart, wstart, nstart, enc = 8 * size, 0, 17 * size, -1.0
+    current = state.move_number() - 1
+    for i in range(1, 8):
+        h = current - i
+        if 0 < h < current:
+            past = state.historical[h]
+            two = np.array([1.0 if c == BLACK else (-1.0 if c == WHITE else 0.0) for c in past], np.float32)
+            out[bstart:bstart + size] = two
+            out[wstart:wstart + size] = -two
+        bstart += size
+        wstart += size
+    out[nstart:nstart + size] = enc
+    return out
+
+
+def arena_play(new_game, make_mcts, coin, record=True, encoder=None, max_moves=0):
     """Arena.Play (arena.go:80-179) for one game.  make_mcts(agent_index, game) builds the agent's fresh MCTS.  Returns
     (moves, winner, a_player, examples [(board, policy, value)], per-ply dumps [(tree A, tree B)])."""
     g = new_game()
@@ -507,18 +592,20 @@ def arena_play(new_game, make_mcts, coin, record=True):
         if ended:
             break
         t = trees[cur]
-        best = t.search(players[cur])  # Agent.Search: SetGame(g) + Search(a.Player)
+        t.g = g                        # Agent.Search: MCTS.SetGame(g) ...
+        best = t.search(players[cur])  # ... + Search(a.Player)
         pass_count = pass_count + 1 if best == PASS else 0
         if record:
             pol = t.policies(g)
             if np.isfinite(pol).all():
-                examples.append([encode_two_plane(g), pol, float(players[cur])])
+                examples.append([(encoder or encode_two_plane)(g), pol, float(players[cur])])
         dumps.append([tr.dump() if tr.root != NIL else np.zeros((0, 7), np.int64) for tr in trees])
-        g.apply(players[cur], best)
+        g = g.apply(players[cur], best)
         moves.append(best)
         cur ^= 1
-        if pass_count >= 2:
-            ended, winner = g.ended()
+        if pass_count >= 2:  # arena.go:134-136: `winner` keeps the value of the last loop condition (None)
+            break
+        if max_moves and len(moves) >= max_moves:  # the repository's cap for games that never end
             break
     for ex in examples:
         ex[2] = 0.0 if winner == 0 else (1.0 if ex[2] == float(winner) else -1.0)

@@ -135,3 +135,34 @@ def test_arena_two_agents_vs_python(oracle, m, n, k, sims, dummy, seed):
         assert (boards[i] == b).all() and (pols[i] == p).all() and vals[i] == v, i
     for a in (0, 1):
         assert tuple(run["stats"][a]) == tuple(float(x) for x in stats[a])
+
+
+@pytest.mark.parametrize("size,sims,cap,dummy,seed", [(5, 20, 30, (1, 2), 21), (5, 40, 24, (0, 0), 22), (7, 12, 20, (2, 1), 23)])
+def test_arena_go_vs_python(oracle, size, sims, cap, dummy, seed):
+    """Go (wq) through the same Arena: Pass is a child of every node, two passes end a descent with combinedScore
+    (blackScore - whiteScore - komi), Apply returns new states, no tree reuse, 18-plane WQEncoder with its history
+    planes, the move cap; Board.check / Apply / Score from tests/pyref_rules.py."""
+    G_ = 4
+    d = K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=sims, n_games=G_, seed=seed, max_moves=cap,
+                    nn=H.tiny_nn(size, size, size * size + 1, features=18))
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, dummy[0]); e.set_inferer(1, K.INF_DUMMY, dummy[1])
+    run = H.play_and_collect(e, G_)
+    state = P.derive_seed(seed, 0)
+    ex_all = []
+    for g in range(G_):
+        state, r = P._splitmix(state)
+        def make(agent, game):
+            return P.MCTS(game, 1.0, sims, None, None, size, size, evaluator=P.dummy_evaluator(size * size, dummy[agent]))
+        moves, winner, a_player, examples, dumps = P.arena_play(lambda: P.WQ(size, 7.5), make, r % 2, encoder=P.encode_wq18, max_moves=cap)
+        rec = run["records"][g]
+        assert list(rec["moves"]) == moves and rec["winner"] == winner and rec["a_player"] == a_player and rec["n_examples"] == len(examples), (g, rec, moves)
+        for ply, pair in enumerate(dumps):
+            for t, want in enumerate(pair):
+                got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
+                assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (g, ply, t)
+        ex_all += examples
+    boards, pols, vals = run["examples"]
+    assert len(ex_all) == len(vals)
+    for i, (b, p, v) in enumerate(ex_all):
+        assert (boards[i] == b).all() and (pols[i] == p).all() and vals[i] == v, i
