@@ -224,11 +224,11 @@ class WQ:  # game/wq/wq.go + game/wq/game.go.  What the reference leaves unfinis
 
 
 class Node:
-    __slots__ = ("move", "visits", "status", "black", "min_psa", "score")
+    __slots__ = ("move", "visits", "status", "black", "min_psa", "score", "vloss")
 
     def __init__(self):
         self.move, self.visits, self.status = 0, 0, 0
-        self.black, self.min_psa, self.score = f32(0), f32(2.0), f32(0)
+        self.black, self.min_psa, self.score, self.vloss = f32(0), f32(2.0), f32(0), f32(0)
 
     def has_children(self):
         return self.min_psa <= f32(1)
@@ -236,10 +236,10 @@ class Node:
     def is_expandable(self, r):
         return f32(r) < self.min_psa
 
-    def evaluate(self, player):  # node.go:147-159 (virtual loss is 0 under one worker)
+    def evaluate(self, player):  # node.go:147-159: the virtual loss is added for White only
         bs = self.black
         if player == WHITE:
-            bs = f32(bs + f32(0))
+            bs = f32(bs + self.vloss)
         s = f32(bs / f32(self.visits))
         if player == WHITE:
             s = f32(f32(1) - s)
@@ -247,8 +247,9 @@ class Node:
 
 
 class MCTS:
-    def __init__(self, game, puct, sims, table, values, M, N, evaluator=None):
+    def __init__(self, game, puct, sims, table, values, M, N, evaluator=None, workers=1):
         self.g, self.puct, self.sims, self.table, self.values = game, f32(puct), sims, table, values
+        self.workers = workers      # > 1: the fixed schedule of concurrent pipeline calls (include/agogo_b200.h)
         self.evaluator = evaluator  # callable(state) -> (policy, value); None = table keyed by MoveNumber()
         self.cached_policies = {}   # tree.go:75: (board, move) -> count
         self.max_depth = M * N
@@ -318,6 +319,10 @@ class MCTS:
             return f32(0), False
         if state.passes() >= 2:
             return f32(0), False
+        return self.expand_after_checks(parent, state, min_psa_ratio)
+
+    def expand_after_checks(self, parent, state, min_psa_ratio):  # search.go:274-338
+        n = self.nodes[parent]
         policy, value = self.infer(state)
         pass_prob = policy[len(policy) - 1]
         player = state.next
@@ -409,6 +414,55 @@ class MCTS:
             self.update(start, ret)
         return ret
 
+    def run_workers(self, iterations):
+        """search.go:112-130 starts runtime.NumCPU() pipeline calls at once; their interleaving is fixed here as the header
+        states it: rounds of `workers` descents, each marking its path with the virtual-loss flag (search.go:222, a store
+        of 3.0) and stopping where it needs an evaluation; null results and terminals complete (and clear their flags) at
+        once; then the pending calls finish in start order — expansion (candidates an earlier call of the round created
+        are found by findChild), Update along the path, undoVirtualLoss (a store of 0)."""
+        left = iterations
+        while left > 0:
+            v = min(self.workers, left)
+            left -= v
+            pending = []
+            for _ in range(v):
+                cur, node, depth, path, ret, wait = self.g.clone(), self.root, 0, [], None, False
+                while True:
+                    depth += 1
+                    if depth > self.max_depth:
+                        break
+                    player = cur.next
+                    n = self.nodes[node]
+                    n.vloss = f32(3.0)
+                    path.append(node)
+                    if n.is_expandable(0) and cur.passes() >= 2:
+                        ret = f32(f32(cur.score(BLACK) - cur.score(WHITE)) - f32(cur.komi))
+                        break
+                    if n.is_expandable(0) and len(self.nodes) < MAXTREESIZE and n.is_expandable(self.min_psa_ratio()):
+                        assert not n.has_children()
+                        pending.append((path, cur))
+                        wait = True
+                        break
+                    if not n.has_children():
+                        break
+                    nxt = self.select(node, player)
+                    move = self.nodes[nxt].move
+                    if not cur.check(player, move):
+                        break
+                    cur = cur.apply(player, move)
+                    node = nxt
+                if not wait:
+                    self.finish_path(path, ret)
+            for path, st in pending:  # a leaf an earlier call of the round expanded: min_psa is 0 now, nothing is created
+                value, ok = self.expand_after_checks(path[-1], st, self.min_psa_ratio())
+                self.finish_path(path, value if ok else None)
+
+    def finish_path(self, path, ret):
+        for nid in reversed(path):
+            if ret is not None:
+                self.update(nid, ret)
+            self.nodes[nid].vloss = f32(0)
+
     def new_root_state(self):
         if self.root == NIL or self.prev is None:
             return False
@@ -496,8 +550,11 @@ class MCTS:
         for f in self.freeables:
             self.free(f)
         self.prepare_root(player)
-        for _ in range(self.sims):
-            self.pipeline(self.g.clone(), self.root, 0)
+        if self.workers > 1:
+            self.run_workers(self.sims)
+        else:
+            for _ in range(self.sims):
+                self.pipeline(self.g.clone(), self.root, 0)
         assert self.nodes[self.root].has_children()
         board_key = tuple(self.g.board)  # stands for current.Hash() taken before the move (search.go:96)
         best = self.best_move()

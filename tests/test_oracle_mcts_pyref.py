@@ -166,3 +166,34 @@ def test_arena_go_vs_python(oracle, size, sims, cap, dummy, seed):
     assert len(ex_all) == len(vals)
     for i, (b, p, v) in enumerate(ex_all):
         assert (boards[i] == b).all() and (pols[i] == p).all() and vals[i] == v, i
+
+
+@pytest.mark.parametrize("game,workers,sims,seed", [("ttt", 2, 30, 31), ("ttt", 5, 48, 32), ("ttt", 64, 40, 33), ("go5", 4, 22, 34), ("go5", 7, 30, 35)])
+def test_worker_schedule_vs_python(oracle, game, workers, sims, seed):
+    """mcts.Config workers > 1: the oracle's SearchRunWorkers against the Python statement of the same fixed schedule
+    (rounds of descents with virtual-loss flags — White-only penalty, node.go:150-152 — colliding leaves, short last round)."""
+    G_ = 3
+    if game == "ttt":
+        m = n = 3
+        d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=sims, nn=H.tiny_nn(3, 3, 10), n_games=G_, seed=seed, workers=workers)
+        new_game, enc, cap, cells = (lambda: P.MNK(3, 3, 3)), None, 0, 9
+    else:
+        m = n = 5
+        d = K.make_desc(K.GAME_WQ, 5, 5, 0, komi=7.5, sims=sims, n_games=G_, seed=seed, max_moves=16, workers=workers,
+                        nn=H.tiny_nn(5, 5, 26, features=18))
+        new_game, enc, cap, cells = (lambda: P.WQ(5, 7.5)), P.encode_wq18, 16, 25
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    run = H.play_and_collect(e, G_)
+    state = P.derive_seed(seed, 0)
+    for g in range(G_):
+        state, r = P._splitmix(state)
+        def make(agent, gm):
+            return P.MCTS(gm, 1.0, sims, None, None, m, n, evaluator=P.dummy_evaluator(cells, 1 + agent), workers=workers)
+        moves, winner, a_player, examples, dumps = P.arena_play(new_game, make, r % 2, encoder=enc, max_moves=cap)
+        rec = run["records"][g]
+        assert list(rec["moves"]) == moves and rec["winner"] == winner, (g, rec, moves)
+        for ply, pair in enumerate(dumps):
+            for t, want in enumerate(pair):
+                got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
+                assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (g, ply, t)
