@@ -191,6 +191,9 @@ class WQ:  # game/wq/wq.go + game/wq/game.go.  What the reference leaves unfinis
     def passes(self):
         return self.n_passes
 
+    def last_move(self):  # game.go:54-59: (None, Pass) for an empty history
+        return self.history[-1] if self.history else (0, PASS)
+
     def check(self, player, move):  # game.go:65-79: occupied points are not rejected
         from tests.pyref_rules import wq_board_check
         if move == PASS:
@@ -247,8 +250,13 @@ class Node:
 
 
 class MCTS:
-    def __init__(self, game, puct, sims, table, values, M, N, evaluator=None, workers=1):
+    def __init__(self, game, puct, sims, table, values, M, N, evaluator=None, workers=1, conf=None, tree_seed=0):
         self.g, self.puct, self.sims, self.table, self.values = game, f32(puct), sims, table, values
+        # the rest of mcts.Config (tree.go:15-29); defaults = the Example's: DontPreferPass, DumbPass, no sampling, no resign
+        self.conf = dict(pass_preference=0, dumb_pass=True, resign_percentage=0.0, random_count=0, random_min_visits=0,
+                         random_temperature=0.0, M=M, N=N)
+        self.conf.update(conf or {})
+        self.rng_state = tree_seed  # MCTS.rand (tree.go:84), injected: splitmix64 stream
         self.workers = workers      # > 1: the fixed schedule of concurrent pipeline calls (include/agogo_b200.h)
         self.evaluator = evaluator  # callable(state) -> (policy, value); None = table keyed by MoveNumber()
         self.cached_policies = {}   # tree.go:75: (board, move) -> count
@@ -522,27 +530,81 @@ class MCTS:
             return li.score > lj.score
         return li.evaluate(player) > lj.evaluate(player)
 
-    def best_move(self):  # search.go:341-390 with Config{DontPreferPass, DumbPass, RandomCount 0, ResignPercentage 0}
+    def randomize_children(self, of):  # tree.go:212-247
+        accum, norm, vec = f32(0), f32(0), []
+        kids = self.children[of]
+        for kid in kids:
+            visits = self.nodes[kid].visits
+            if norm == 0:
+                norm = f32(visits)
+                if visits <= self.conf["random_min_visits"]:
+                    return
+            if visits > self.conf["random_min_visits"]:
+                base = float(f32(f32(visits) / norm))
+                expo = float(f32(f32(1) / f32(self.conf["random_temperature"])))
+                accum = f32(accum + f32(base ** expo))  # math32.Pow = float32(math.Pow(float64, float64))
+                vec.append(accum)
+        self.rng_state, r = _splitmix(self.rng_state)
+        rnd = f32(f32(r >> 40) * f32(1.0 / 16777216.0)) * accum  # rand.Float32() stand-in: 24 high bits
+        rnd = f32(rnd)
+        index = 0
+        for i, a in enumerate(vec):
+            if rnd < a:
+                index = i
+                break
+        if index == 0:
+            return
+        for i in range(len(kids) - index):
+            kids[i], kids[i + index] = kids[i + index], kids[i]
+
+    def no_pass_best_move(self, best, best_score, player):  # search.go:531-563
+        for kid in self.children[self.root]:
+            mv = self.nodes[kid].move
+            ok = self.g.check(player, mv)
+            if mv != PASS and ok:
+                nd = self.nodes[kid]
+                return mv, (nd.evaluate(player) if nd.visits != 0 else f32(1))
+        return best, best_score
+
+    def should_resign(self, best_score, player):  # search.go:502-529
+        c = self.conf
+        if c["pass_preference"] == 2 or c["resign_percentage"] == 0:
+            return False
+        if self.g.move_number() <= (c["M"] * c["N"]) // 4:
+            return False
+        threshold = f32(0.1) if c["resign_percentage"] < 0 else f32(c["resign_percentage"])
+        return not (best_score > threshold)
+
+    def best_move(self):  # search.go:341-390
+        c = self.conf
         player = self.g.next
         kids = self.children[self.root]
-        # stable insertion sort by fancySort.Less
-        out = []
+        out = []  # stable insertion sort by fancySort.Less
         for k in kids:
             i = len(out)
             while i > 0 and self.fancy_less(player, k, out[i - 1]):
                 i -= 1
             out.insert(i, k)
         kids[:] = out
+        if self.g.move_number() < c["random_count"]:
+            self.randomize_children(self.root)
         if not kids:
             return PASS
-        best = self.nodes[kids[0]].move
-        if best == PASS:  # DontPreferPass: first child that is not a pass and passes Check (noPass, search.go:531-545)
-            for kid in kids:
-                mv = self.nodes[kid].move
-                if mv != PASS and self.g.check(player, mv):
-                    best = mv
-                    break
-        return best  # shouldResign: ResignPercentage == 0 -> never
+        first = self.nodes[kids[0]]
+        best, best_score = first.move, first.evaluate(player)
+        root_score = self.nodes[self.root].score  # Node.Score(): the prior
+        losing = (root_score > 0 and player == WHITE) or (root_score < 0 and player == BLACK)
+        if c["pass_preference"] == 0 and best == PASS:
+            best, best_score = self.no_pass_best_move(best, best_score, player)
+        elif not c["dumb_pass"] and best == PASS:
+            if losing:
+                best, best_score = self.no_pass_best_move(best, best_score, player)
+        elif not c["dumb_pass"] and self.g.last_move()[1] == PASS:
+            if not losing:
+                best = PASS
+        if best == PASS and self.should_resign(best_score, player):
+            best = -2
+        return best
 
     def search(self, player):
         self.update_root()

@@ -197,3 +197,46 @@ def test_worker_schedule_vs_python(oracle, game, workers, sims, seed):
             for t, want in enumerate(pair):
                 got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
                 assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (g, ply, t)
+
+
+@pytest.mark.parametrize("name,conf", [
+    ("sample-T1", dict(random_count=5, random_min_visits=1, random_temperature=1.0)),
+    ("sample-T0.5", dict(random_count=9, random_min_visits=2, random_temperature=0.5)),
+    ("preferpass-smart", dict(pass_preference=1, dumb_pass=False)),
+    ("dontresign-smart", dict(pass_preference=2, dumb_pass=False, resign_percentage=0.3)),
+    ("dontpreferpass-smart", dict(pass_preference=0, dumb_pass=False)),
+])
+def test_config_options_vs_python(oracle, name, conf):
+    """The remaining mcts.Config options inside bestMove (search.go:341-390): temperature sampling of the root's children
+    (randomizeChildren with the injected tree RNG, math32.Pow), PassPreference x DumbPass (the `LastMove().IsPass()` branch
+    fires on the empty history too), shouldResign's early exits — oracle against the Python restatement, on tic-tac-toe
+    for the sampling cases and on 5x5 Go for the pass logic."""
+    G_, seed, sims = 4, 41, 24
+    go = "smart" in name
+    if go:
+        d = K.make_desc(K.GAME_WQ, 5, 5, 0, komi=7.5, sims=sims, n_games=G_, seed=seed, max_moves=14,
+                        nn=H.tiny_nn(5, 5, 26, features=18), pass_preference=conf["pass_preference"], dumb_pass=0)
+        new_game, enc, cap, cells, m = (lambda: P.WQ(5, 7.5)), P.encode_wq18, 14, 25, 5
+    else:
+        d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=sims, nn=H.tiny_nn(3, 3, 10), n_games=G_, seed=seed)
+        new_game, enc, cap, cells, m = (lambda: P.MNK(3, 3, 3)), None, 0, 9, 3
+    d.mcts.random_count = conf.get("random_count", 0)
+    d.mcts.random_min_visits = conf.get("random_min_visits", 0)
+    d.mcts.random_temperature = conf.get("random_temperature", 0.0)
+    d.mcts.resign_percentage = conf.get("resign_percentage", 0.0)
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    run = H.play_and_collect(e, G_)
+    state = P.derive_seed(seed, 0)
+    tree_seed = P.derive_seed(seed, 1)
+    for g in range(G_):
+        state, r = P._splitmix(state)
+        def make(agent, gm):
+            return P.MCTS(gm, 1.0, sims, None, None, m, m, evaluator=P.dummy_evaluator(cells, 1 + agent), conf=conf, tree_seed=tree_seed)
+        moves, winner, a_player, examples, dumps = P.arena_play(new_game, make, r % 2, encoder=enc, max_moves=cap)
+        rec = run["records"][g]
+        assert list(rec["moves"]) == moves and rec["winner"] == winner and rec["n_examples"] == len(examples), (name, g, rec, moves)
+        for ply, pair in enumerate(dumps):
+            for t, want in enumerate(pair):
+                got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
+                assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (name, g, ply, t)
