@@ -85,3 +85,29 @@ for fname, fmt in (("E4M3", E4M3), ("E5M2", E5M2)):
     # error of using ah8 instead of ah in the correction: add (ah - ah8) * bm8?  -> needs another pass; report as is
     report("fp16 hi*hi + %s (hi8*mid8 + mid8*hi8)" % fname, (ah @ bh + c2) * s16, 2.0)
 report("fp32 GEMM (numpy)", A @ B, 0)
+
+# ---- robustness: activations spanning many binades (ReLU of a heavy-tailed pre-activation) with FIXED fp8 scales chosen
+# from the fp16 scale plus headroom (the engine cannot take an absmax of a layer's output before writing it)
+print()
+for tail, head in ((1.0, 3), (2.0, 3), (2.0, 6)):
+    xh = (np.maximum(rng.normal(0, 1, (NB, C, H, W)), 0) * np.exp(tail * rng.normal(0, 1, (NB, C, H, W)))).astype(np.float32)
+    xph = np.pad(xh, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    colsh = np.stack([xph[:, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)], axis=1)
+    Ah = colsh.transpose(0, 3, 4, 1, 2).reshape(NB * H * W, 9 * C)
+    refh = Ah.astype(np.float64) @ B.astype(np.float64)
+    rms_h = np.sqrt((refh ** 2).mean())
+    # fp16 split at a fixed activation scale with `head` binades of headroom over this batch's absmax
+    ah, al, ea = split16(Ah, target=13 - head)
+    s16h = np.float32(2.0 ** -(ea + eb))
+    p_hi = (E4M3["emax"] - 1 - head) - (13 - head)          # hi8 = E4M3(hi * 2^p_hi): same headroom in the fp8 format
+    ah8 = to_fp8(ah * np.float32(2.0 ** p_hi), **E4M3)
+    bl8 = to_fp8(bl * np.float32(2.0 ** -p_hi), **E4M3)      # the product keeps the accumulator's scale
+    q = 5 + head                                            # |lo| <= 2^-11 * 2^(13-head): its bound maps to 2^7
+    al8 = to_fp8(al * np.float32(2.0 ** q), **E4M3)
+    bh8 = to_fp8(bh * np.float32(2.0 ** -q), **E4M3)        # weights (max in [2^6, 2^7)) pay for it: 2^(2-head) at most
+    y3 = (ah @ bh + ah @ bl + al @ bh) * s16h
+    y8 = (ah @ bh + ah8 @ bl8 + al8 @ bh8) * s16h
+    for nm, y in (("3 fp16 passes", y3), ("fp16 + 2 x E4M3, fixed scales", y8)):
+        err = y.astype(np.float64) - refh
+        print("lognormal tail %.1f, headroom 2^%d: %-32s rel. rms err %.2e  (activation max/median %.0f)" %
+              (tail, head, nm, np.sqrt((err ** 2).mean()) / rms_h, Ah.max() / np.median(Ah[Ah > 0])))
