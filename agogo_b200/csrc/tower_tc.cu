@@ -21,6 +21,8 @@
 //     (tmem_full/tmem_empty mbarriers), persistent CTAs striding over (M-tile, N-tile).
 // Descriptor bit layouts follow the PTX ISA tcgen05 "shared memory descriptor" / "instruction
 // descriptor" tables (cross-checked against cute/arch/mma_sm100_desc.hpp in the image).
+#include <cuda_fp8.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -277,6 +279,255 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// EXPERIMENT (AZ_TC_FP8=1, not the product path; DESIGN.md §10, tools/precision_study_fp8.py): the CTA-pair layer with
+// its two correction passes on the FP8 tensor path.  acc = hi16(x)·hi16(w)  [kind::f16]
+//                                                         + e4m3(hi·2^pa)·e4m3(w_lo·2^-pa) + e4m3(x_lo·2^q)·e4m3(w_hi·2^-q)  [kind::f8f6f4]
+// — every product carries the accumulator's scale, so the three kinds accumulate into the same fp32 TMEM tile.  FP8 MMAs
+// take K = 32 per instruction at twice the fp16 rate: 4 + 2 + 2 instructions per 64-wide K block instead of 12.
+// Activations travel as hi16 + lo16 (the heads and the next layer's re-split need lo16) + h8 + l8; a stage holds
+// A16 16 KB | A_h8 8 KB | A_l8 8 KB | B16 16 KB | B_h8 8 KB | B_l8 8 KB = 64 KB as before (fp8 tiles: 64-byte rows, SWIZZLE_64B).
+struct ConvArgsF8 {
+  ConvArgs c;
+  uint8_t* out_h8;  // [(guard + rows)][cout] e4m3(hi16 * 2^pa)
+  uint8_t* out_l8;  // [(guard + rows)][cout] e4m3(lo * 2^q)
+  float scale_h8, scale_l8;  // 2^pa, 2^q
+};
+__device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_conv3x3_tc2_f8(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmAh8,
+                 const __grid_constant__ CUtensorMap tmAl8, const __grid_constant__ CUtensorMap tmB16,
+                 const __grid_constant__ CUtensorMap tmBh8, const __grid_constant__ CUtensorMap tmBl8,
+                 const __grid_constant__ CUtensorMap tmAff, ConvArgsF8 af) {
+  const ConvArgs& a = af.c;
+  constexpr int BK = 64, BN = 256, OUTC = 128;
+  constexpr int T16 = BM * BK * 2, T8 = BM * BK;  // 16 KB / 8 KB operand tiles (128 rows)
+  constexpr int OFF_AH8 = T16, OFF_AL8 = T16 + T8, OFF_B16 = T16 + 2 * T8, OFF_BH8 = 2 * T16 + 2 * T8, OFF_BL8 = 2 * T16 + 3 * T8;
+  static_assert(2 * T16 + 4 * T8 == STAGE2_BYTES, "stage layout");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t aff_smem = smem_base + STAGES2 * STAGE2_BYTES;
+  const uint32_t bars = aff_smem + AFF_BYTES;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + STAGES2 * STAGE2_BYTES + AFF_BYTES + 240);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES2 + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (2 * STAGES2 + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (2 * STAGES2 + 2 + i); };
+  auto afull_bar = [&](int quad, int buf) { return bars + 8u * (2 * STAGES2 + 4 + quad * 2 + buf); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; s++) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+    for (int i = 0; i < 8; i++) mbar_init(afull_bar(i >> 1, i & 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n = min(*a.n_dev, a.n_max);
+  const int rows = n * a.S;
+  const int m_tiles = a.mode3d ? n * a.tps : (rows + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int n_tiles = a.n_total / BN;
+  const int total_tiles = m_pairs * n_tiles;
+  const int kc_per_tap = a.cin / BK;
+  const int kblocks = 9 * kc_per_tap;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+        const int mt = 2 * mp + (int)rank;
+        const int m0 = mt * BM, n0 = nt * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES2;
+          const uint32_t ph = (it / STAGES2) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const int tap = kb / kc_per_tap, kc = kb - tap * kc_per_tap;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const uint32_t sa = smem_base + s * STAGE2_BYTES;
+          const uint32_t lbar = full_bar(s) & PEER_MASK;
+          mbar_expect_tx_cluster(lbar, STAGE2_BYTES);
+          if (a.mode3d) {
+            const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM + dy * a.Wp + dx;
+            tma2_load_3d(sa, &tmA16, lbar, kc * BK, p0, b);
+            tma2_load_3d(sa + OFF_AH8, &tmAh8, lbar, kc * BK, p0, b);
+            tma2_load_3d(sa + OFF_AL8, &tmAl8, lbar, kc * BK, p0, b);
+          } else {
+            const int arow = a.guard + m0 + dy * a.Wp + dx;
+            tma2_load_2d(sa, &tmA16, lbar, kc * BK, arow);
+            tma2_load_2d(sa + OFF_AH8, &tmAh8, lbar, kc * BK, arow);
+            tma2_load_2d(sa + OFF_AL8, &tmAl8, lbar, kc * BK, arow);
+          }
+          const int kcol = tap * a.cin + kc * BK;
+          tma2_load_2d(sa + OFF_B16, &tmB16, lbar, kcol, n0);
+          tma2_load_2d(sa + OFF_BH8, &tmBh8, lbar, kcol, n0);
+          tma2_load_2d(sa + OFF_BL8, &tmBl8, lbar, kcol, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);  // formats 0/0: F16 x F16 for kind::f16, E4M3 x E4M3 for kind::f8f6f4
+      uint32_t it = 0, tcount = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
+        const int acc = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++, it++) {
+          const int s = it % STAGES2;
+          const uint32_t ph = (it / STAGES2) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * STAGE2_BYTES;
+          const uint64_t dA16 = make_desc_sw<64>(sa), dB16 = make_desc_sw<64>(sa + OFF_B16);
+          // fp8 tiles: 64-byte rows = the SWIZZLE_64B form of the descriptor (what make_desc_sw<32> encodes for fp16)
+          const uint64_t dAh8 = make_desc_sw<32>(sa + OFF_AH8), dAl8 = make_desc_sw<32>(sa + OFF_AL8);
+          const uint64_t dBh8 = make_desc_sw<32>(sa + OFF_BH8), dBl8 = make_desc_sw<32>(sa + OFF_BL8);
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)  // 16 fp16 = 32 B per step
+            umma2_f16(d_tmem, dA16 + (uint64_t)(ks * 2), dB16 + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {  // 32 fp8 = 32 B per step
+            umma2_f8(d_tmem, dAh8 + (uint64_t)(ks * 2), dBl8 + (uint64_t)(ks * 2), idesc, 1u);
+            umma2_f8(d_tmem, dAl8 + (uint64_t)(ks * 2), dBh8 + (uint64_t)(ks * 2), idesc, 1u);
+          }
+          umma2_commit_mc(empty_bar(s));
+        }
+        umma2_commit_mc(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    uint32_t tcount = 0;
+    constexpr int CH = OUTC / 8;
+    const uint32_t aff_buf = aff_smem + quad * 8192;
+    auto aff_issue = [&](uint32_t qq) {
+      const int tile = cluster_id + (int)(qq / CH) * n_clusters;
+      if (tile >= total_tiles) return;
+      const int j = qq % CH;
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int prow = a.mode3d ? (mt % a.tps) * BM + quad * 32 : (mt * BM + quad * 32) % a.S;
+      if (lane == 0) {
+        const uint32_t bar = afull_bar(quad, qq & 1);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(aff_buf + (qq & 1) * 4096, &tmAff, bar, (nt * OUTC + j * 8) * 4, prow);
+      }
+    };
+    aff_issue(0);
+    aff_issue(1);
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int m0 = mt * BM;
+      const int acc = tcount & 1;
+      const uint32_t aph = (tcount >> 1) & 1;
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      int r, p;
+      bool inb;
+      if (a.mode3d) {
+        const int b = mt / a.tps;
+        p = (mt - b * a.tps) * BM + quad * 32 + lane;
+        r = b * a.S + p;
+        inb = p < a.S && mt < m_tiles;
+      } else {
+        r = m0 + quad * 32 + lane;
+        p = r % a.S;
+        inb = r < rows;
+      }
+      const int y = p / a.Wp, x = p - y * a.Wp;
+      const bool valid = inb && y < a.H && x < a.W;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const size_t orow = (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      bool overflow = false;
+#pragma unroll 1
+      for (int c0 = 0; c0 < OUTC; c0 += 32) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row + c0, ra);
+        tmem_ld32(t_row + BN / 2 + c0, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < 4; sub++) {
+          const uint32_t qq = tcount * CH + (c0 >> 3) + sub;
+          mbar_wait(afull_bar(quad, qq & 1), (qq >> 1) & 1);
+          const uint8_t* box = smem_al + (aff_buf - smem_base) + (qq & 1) * 4096 + lane * 128;
+          __align__(16) __half hi[8];
+          __align__(16) __half lo[8];
+          __align__(8) uint8_t h8[8];
+          __align__(8) uint8_t l8[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const float4 f = *reinterpret_cast<const float4*>(box + ((k ^ (lane & 7)) << 4));
+            const int i = sub * 8 + k;
+            float v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+            v *= a.act_scale;
+            const __half h = __float2half_rn(v);
+            const float hf = __half2float(h);
+            overflow |= valid && !(fabsf(hf) <= 65504.0f);
+            const float res = v - hf;
+            hi[k] = h;
+            lo[k] = __float2half_rn(res);
+            h8[k] = to_e4m3(hf * af.scale_h8);
+            l8[k] = to_e4m3(res * af.scale_l8);
+          }
+          if (valid) {
+            *(uint4*)(a.out_hi + orow + c0 + sub * 8) = *(const uint4*)hi;
+            *(uint4*)(a.out_lo + orow + c0 + sub * 8) = *(const uint4*)lo;
+            *(uint2*)(af.out_h8 + orow + c0 + sub * 8) = *(const uint2*)h8;
+            *(uint2*)(af.out_l8 + orow + c0 + sub * 8) = *(const uint2*)l8;
+          }
+          __syncwarp();
+          aff_issue(qq + 2);
+        }
+      }
+      if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & PEER_MASK);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+// (hi16, lo16) -> (e4m3(hi * 2^pa), e4m3(lo * 2^q)) for the rows a non-fp8 kernel produced (the init conv's output)
+__global__ void k_split_fp8(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t n, float scale_h8, float scale_l8,
+                            uint8_t* h8, uint8_t* l8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  h8[i] = to_e4m3(__half2float(hi[i]) * scale_h8);
+  l8[i] = to_e4m3(__half2float(lo[i]) * scale_l8);
+}
+
 // fp32 NCHW planes -> zero-bordered NHWC fp16 hi/lo (channels padded to cpad)
 __global__ void k_pack_planes(const float* __restrict__ planes, const int* __restrict__ n_dev, int n_max, int F, int H,
                               int W, int cpad, int guard, int S, float scale, __half* hi, __half* lo) {
@@ -353,6 +604,31 @@ void tower_configure_device() {
   set_conv_attr<256, true, 32>(); set_conv_attr<128, true, 32>(); set_conv_attr<256, false, 32>(); set_conv_attr<128, false, 32>();
   set_conv_attr<64, false, 32>();
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_f8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
+}
+
+// e4m3 operands (AZ_TC_FP8 experiment): [rows][cols] bytes, box {64 bytes, box_rows}, SWIZZLE_64B
+CUtensorMap make_map_u8(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(u8) failed: " + std::to_string((int)r));
+  return m;
+}
+CUtensorMap make_map3d_u8(void* base, uint64_t n, uint64_t S, uint64_t cols) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {cols, S, n};
+  cuuint64_t strides[2] = {cols, S * cols};
+  cuuint32_t box[3] = {64, BM, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(u8, 3d) failed: " + std::to_string((int)r));
+  return m;
 }
 
 struct Layer {
@@ -364,11 +640,19 @@ struct Layer {
   int aff_rows = 0;
   CUtensorMap mB_hi, mB_lo, mAff;
   CUtensorMap mB2_hi, mB2_lo;               // CTA-pair kernel: 128-row boxes (each CTA of the pair loads half of the N tile)
+  // AZ_TC_FP8 experiment: e4m3(w_hi * 2^-q), e4m3(w_lo * 2^-pa), 64-byte-row boxes
+  uint8_t *w_h8 = nullptr, *w_l8 = nullptr;
+  CUtensorMap mB2_h8, mB2_l8;
 };
 struct Impl {
   NetDims d;
   int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1, bk = 64;
   int pair_clusters = 0;  // > 0: fused layers run on k_conv3x3_tc2 with this many co-resident CTA pairs
+  // AZ_TC_FP8=1 (experiment): correction passes on the FP8 tensor path; activations also travel as e4m3 h8 / l8
+  bool fp8 = false;
+  int pa = 0, q = 10;  // h8 = e4m3(hi16 * 2^pa), l8 = e4m3(lo * 2^q); weights carry the inverse factors
+  uint8_t *x_h8[2] = {nullptr, nullptr}, *x_l8[2] = {nullptr, nullptr};
+  CUtensorMap mX_h8[2], mX_l8[2];
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
   __half *x_hi[2] = {nullptr, nullptr}, *x_lo[2] = {nullptr, nullptr};  // [(guard+rows+guard)][K]
   CUtensorMap mIn_hi, mIn_lo, mX_hi[2], mX_lo[2];
@@ -420,6 +704,22 @@ void launch_conv_pair2(const Impl& I, const Layer& L, const CUtensorMap& ah, con
   const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
   const int clusters = std::min(I.pair_clusters, pair_tiles);
   k_conv3x3_tc2<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(ah, al, L.mB2_hi, L.mB2_lo, L.mAff, a);
+}
+void launch_conv_pair2_f8(const Impl& I, const Layer& L, int in, int out, const int* n_dev, int* err, cudaStream_t st) {
+  ConvArgsF8 af;
+  ConvArgs& a = af.c;
+  a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
+  a.mode3d = I.mode3d; a.tps = I.tps;
+  a.cin = L.cin; a.n_total = L.n_total; a.cout = I.d.K; a.aff = L.aff; a.out_hi = I.x_hi[out]; a.out_lo = I.x_lo[out];
+  a.act_scale = ldexpf(1.0f, I.ea); a.err = err; a.passes = 3;
+  a.out_raw = nullptr; a.exp_a = nullptr; a.exp_b = nullptr;
+  af.out_h8 = I.x_h8[out]; af.out_l8 = I.x_l8[out];
+  af.scale_h8 = ldexpf(1.0f, I.pa); af.scale_l8 = ldexpf(1.0f, I.q);
+  const int m_tiles = I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM;
+  const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
+  const int clusters = std::min(I.pair_clusters, pair_tiles);
+  k_conv3x3_tc2_f8<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(I.mX_hi[in], I.mX_h8[in], I.mX_l8[in], L.mB2_hi, L.mB2_h8,
+                                                                  L.mB2_l8, L.mAff, af);
 }
 void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                    const int* n_dev, int* err, cudaStream_t st) {
@@ -476,6 +776,17 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
       I->pair_clusters = std::min(nc, I->num_sms / 2);
     }
   }
+  if (const char* f8 = getenv("AZ_TC_FP8")) I->fp8 = f8[0] == '1' && I->pair_clusters > 0 && 2 * d.K >= 256;
+  if (I->fp8) {
+    I->pa = 2 - I->ea;  // an activation of 1.0 lands at 2^2 in e4m3 (representable up to 112, saturating above)
+    I->q = 10;          // weights' hi parts (max in [2^13, 2^14)) land at 2^3..2^4
+    for (int i = 0; i < 2; i++) {
+      CUDA_CHECK(cudaMalloc(&I->x_h8[i], (size_t)I->rows_alloc * d.K)); CUDA_CHECK(cudaMemset(I->x_h8[i], 0, (size_t)I->rows_alloc * d.K));
+      CUDA_CHECK(cudaMalloc(&I->x_l8[i], (size_t)I->rows_alloc * d.K)); CUDA_CHECK(cudaMemset(I->x_l8[i], 0, (size_t)I->rows_alloc * d.K));
+      if (I->mode3d) { I->mX_h8[i] = make_map3d_u8(I->x_h8[i], n_max, I->S, d.K); I->mX_l8[i] = make_map3d_u8(I->x_l8[i], n_max, I->S, d.K); }
+      else { I->mX_h8[i] = make_map_u8(I->x_h8[i], I->rows_alloc, d.K, BM); I->mX_l8[i] = make_map_u8(I->x_l8[i], I->rows_alloc, d.K, BM); }
+    }
+  }
   // layers: init (single), then SharedLayers fused pairs
   const int K = d.K, HW = d.HW();
   for (int l = 0; l <= d.SharedLayers; l++) {
@@ -496,6 +807,10 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
     }
     L.mB_hi = make_map(L.w_hi, L.n_total, ktot, L.bn, I->bk); L.mB_lo = make_map(L.w_lo, L.n_total, ktot, L.bn, I->bk);
     if (L.pair && L.bn == 256) { L.mB2_hi = make_map(L.w_hi, L.n_total, ktot, 128, 64); L.mB2_lo = make_map(L.w_lo, L.n_total, ktot, 128, 64); }
+    if (I->fp8 && L.pair && L.bn == 256) {
+      CUDA_CHECK(cudaMalloc(&L.w_h8, (size_t)L.n_total * ktot)); CUDA_CHECK(cudaMalloc(&L.w_l8, (size_t)L.n_total * ktot));
+      L.mB2_h8 = make_map_u8(L.w_h8, L.n_total, ktot, 128); L.mB2_l8 = make_map_u8(L.w_l8, L.n_total, ktot, 128);
+    }
     I->layers.push_back(L);
   }
   CUDA_CHECK(cudaDeviceSynchronize());
@@ -506,7 +821,8 @@ void tc_tower_free(TcTower& t) {
   if (!I) return;
   cudaFree(I->xin_hi); cudaFree(I->xin_lo);
   for (int i = 0; i < 2; i++) { cudaFree(I->x_hi[i]); cudaFree(I->x_lo[i]); }
-  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); cudaFree(L.affq); }
+  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); cudaFree(L.affq); cudaFree(L.w_h8); cudaFree(L.w_l8); }
+  for (int i = 0; i < 2; i++) { cudaFree(I->x_h8[i]); cudaFree(I->x_l8[i]); }
   for (cudaEvent_t e : I->ev_pool) cudaEventDestroy(e);
   delete I;
   t.impl = nullptr;
@@ -535,9 +851,12 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
       for (size_t i = 0; i < (size_t)K * ci_real * 9; i++) mx = std::max(mx, std::fabs(f[i]));
     }
     int ew = 0;
-    if (mx > 0 && std::isfinite(mx)) { int e2; frexpf(mx, &e2); ew = 7 - e2; }  // mx*2^ew in [64,128)
+    const bool f8 = I->fp8 && L.pair && L.bn == 256;  // experiment: hi parts up at [2^13, 2^14) so that the e4m3 copies keep bits
+    if (mx > 0 && std::isfinite(mx)) { int e2; frexpf(mx, &e2); ew = (f8 ? 14 : 7) - e2; }  // mx*2^ew in [64,128)
     const float wscale = ldexpf(1.0f, ew);
     std::vector<__half> whi((size_t)L.n_total * ktot, __float2half_rn(0.0f)), wlo((size_t)L.n_total * ktot, __float2half_rn(0.0f));
+    std::vector<uint8_t> wh8(f8 ? (size_t)L.n_total * ktot : 0, 0), wl8(f8 ? (size_t)L.n_total * ktot : 0, 0);
+    const float inv_q = ldexpf(1.0f, -I->q), inv_pa = ldexpf(1.0f, -I->pa);
     std::vector<float2> aff((size_t)HW * L.n_total);
     const int half_bn = L.pair ? L.bn / 2 : L.bn;
     const float fold = ldexpf(1.0f, -(I->ea + ew)) * inv_sd;
@@ -553,6 +872,10 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
           size_t o = (size_t)row * ktot + (size_t)tap * L.cin + ci;
           whi[o] = hh;
           wlo[o] = __float2half_rn(w - __half2float(hh));
+          if (f8) {
+            wh8[o] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hh) * inv_q, __NV_SATFINITE, __NV_E4M3);
+            wl8[o] = (uint8_t)__nv_cvt_float_to_fp8((w - __half2float(hh)) * inv_pa, __NV_SATFINITE, __NV_E4M3);
+          }
         }
       const float* g = h.data() + u[br]->gamma + (size_t)ch * HW;
       const float* be = h.data() + u[br]->beta + (size_t)ch * HW;
@@ -560,6 +883,10 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
     }
     CUDA_CHECK(cudaMemcpy(L.w_hi, whi.data(), whi.size() * 2, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(L.w_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
+    if (f8) {
+      CUDA_CHECK(cudaMemcpy(L.w_h8, wh8.data(), wh8.size(), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(L.w_l8, wl8.data(), wl8.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_CHECK(cudaMemcpy(L.aff, aff.data(), aff.size() * sizeof(float2), cudaMemcpyHostToDevice));
     if (L.pair) {
       std::vector<float> q((size_t)L.aff_rows * K * 4, 0.0f);
@@ -600,8 +927,16 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   int cur = 0;
   dispatch_conv(*I, I->layers[0], I->mIn_hi, I->mIn_lo, I->x_hi[0], I->x_lo[0], n_dev, err_flag, st);
   if (launches) (*launches)++;
+  if (I->fp8) {  // experiment: the init conv's output also as e4m3 h8 / l8 for the first fused layer
+    const size_t ne = (size_t)I->rows_alloc * d.K;
+    k_split_fp8<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(I->x_hi[0], I->x_lo[0], ne, ldexpf(1.0f, I->pa), ldexpf(1.0f, I->q),
+                                                             I->x_h8[0], I->x_l8[0]);
+    if (launches) (*launches)++;
+  }
   for (size_t l = 1; l < I->layers.size(); l++) {
     size_t e0 = I->profile ? I->ev_get(st) : 0;
+    if (I->fp8 && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
+    else
     dispatch_conv(*I, I->layers[l], I->mX_hi[cur], I->mX_lo[cur], I->x_hi[cur ^ 1], I->x_lo[cur ^ 1], n_dev, err_flag, st);
     if (I->profile) I->conv_spans.push_back({e0, I->ev_get(st)});
     if (launches) (*launches)++;
