@@ -407,6 +407,27 @@ def test_tc_tower_full_depth_c3(oracle, engine_lib):
     assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
 
 
+@pytest.mark.skipif(__import__("os").environ.get("AZ_RUN_EXPERIMENTS") != "1",
+                    reason="unvalidated experiment kernels only run on request (AZ_RUN_EXPERIMENTS=1)")
+def test_fp8_correction_passes_experiment(oracle, engine_lib, monkeypatch):
+    """AZ_TC_FP8=1: the fused layers with E4M3 correction passes, full C3 depth, against the oracle at
+    the north star's 1e-4 — the gate this variant has to pass before it can replace the 3 x fp16 kernel."""
+    monkeypatch.setenv("AZ_TC_FP8", "1")
+    size, A1 = 19, 362
+    def desc():
+        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4,
+                           nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=A1))
+    eo, etc = oracle.create(desc()), engine_lib.create(desc())
+    H.tame_gammas([eo, etc], 0, 99)
+    for e in (eo, etc):
+        e.set_inferer(0, K.INF_DUAL)
+    planes = _wq_planes(np.random.default_rng(8), 3, size)
+    po, vo = eo.infer(0, planes)
+    ptc, vtc = etc.infer(0, planes)
+    print("fp8 corrections: dp=%.3g dv=%.3g" % (np.abs(ptc - po).max(), np.abs(vtc - vo).max()))
+    assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
+
+
 def test_c2_shapes_selfplay(oracle, engine_lib):
     """BASELINE config C2 shapes (9x9 wq, 6-block x 64 net, FC 128, WQEncoder) at reduced game/sim counts:
     tensor-core tower in the loop, move sequences and evaluation counts equal to the oracle's."""
