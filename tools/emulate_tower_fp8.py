@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""CPU emulation of the whole tensor-core tower (numpy) with the engine's exact operand formats and power-of-two scales,
+to predict the end-to-end error of the AZ_TC_FP8 experiment before it runs on hardware: the 20-block x 256 net of config
+C3 on a few 19x19 positions, (a) fp16 hi/lo with three passes (the product), (b) hi*hi in fp16 + the two correction passes
+in E4M3 with the scales tower_tc.cu uses (ea = -2, pa = 2 - ea, q = 10, weights' hi parts in [2^13, 2^14)), both against a
+float64 forward of the same weights (tests/pyref_dual.py).  Usage: python tools/emulate_tower_fp8.py [blocks] [boards]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+from agogo_b200 import _capi as K  # noqa: E402
+from tests import helpers as H  # noqa: E402
+from tests import pyref_dual as D  # noqa: E402
+
+blocks = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+NB = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+size, C, EA, QW = 19, 256, -2, 10
+PA = 2 - EA
+
+
+def e4m3(x):
+    x = x.astype(np.float64)
+    sign, a = np.sign(x), np.abs(x)
+    e = np.clip(np.floor(np.log2(np.where(a > 0, a, 1.0))), -6, 8)
+    qn = 2.0 ** (e - 3)
+    return (sign * np.minimum(np.round(a / qn) * qn, 448.0)).astype(np.float32)
+
+
+def f16(x):
+    return x.astype(np.float16).astype(np.float32)
+
+
+def im2col(x):  # [N,C,H,W] -> [N*H*W, 9*C] (tap-major like the engine's K order)
+    N, Cc, Hh, Ww = x.shape
+    xp = np.pad(x, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    cols = np.stack([xp[:, :, ky:ky + Hh, kx:kx + Ww] for ky in range(3) for kx in range(3)], axis=1)
+    return cols.transpose(0, 3, 4, 1, 2).reshape(N * Hh * Ww, 9 * Cc)
+
+
+def conv_emulated(x, w, mode):
+    """x real-valued fp32 [N,Ci,H,W]; returns conv(x, w) as the tensor-core pipeline would accumulate it (fp32)."""
+    N = x.shape[0]
+    mx = np.abs(w).max()
+    e2 = int(np.floor(np.log2(mx))) + 1                      # frexp exponent: mx = m * 2^e2, m in [0.5, 1)
+    ew = (14 if mode == "fp8" else 7) - e2
+    xs = (x * np.float32(2.0 ** EA)).astype(np.float32)      # x16 units
+    xh = f16(xs); xl = f16(xs - xh)
+    ws = (w * np.float32(2.0 ** ew)).astype(np.float32)
+    wh = f16(ws); wl_exact = (ws - wh).astype(np.float32); wl = f16(wl_exact)
+    A_h, A_l = im2col(xh), im2col(xl)
+    Bm = lambda t: t.transpose(2, 3, 1, 0).reshape(9 * t.shape[1], t.shape[0])
+    acc = A_h @ Bm(wh)
+    if mode == "fp16x3":
+        acc = acc + A_h @ Bm(wl) + A_l @ Bm(wh)
+    elif mode == "fp16x2":  # calibration: the two-pass tower measured 6.5e-5 worst-case |dvalue| on hardware
+        acc = acc + A_h @ Bm(wl)
+    else:
+        xh8 = e4m3(xh * np.float32(2.0 ** PA)); wl8 = e4m3(wl_exact * np.float32(2.0 ** -PA))
+        xl8 = e4m3((xs - xh) * np.float32(2.0 ** QW)); wh8 = e4m3(wh * np.float32(2.0 ** -QW))
+        acc = acc + im2col(xh8) @ Bm(wl8) + im2col(xl8) @ Bm(wh8)
+    out = acc * np.float32(2.0 ** -(EA + ew))
+    return out.reshape(N, size, size, -1).transpose(0, 3, 1, 2)
+
+
+def tower(net, X, mode):
+    u = net.units
+    aff = lambda unit: (unit.gamma[0] / np.sqrt(D.EPS), unit.beta[0])
+    g, b = aff(u[0])
+    cur = np.maximum(g * conv_emulated(X, u[0].w.astype(np.float32), "fp16x3") + b, 0).astype(np.float32)
+    for i in range(net.L):
+        ua, ub = u[1 + 2 * i], u[2 + 2 * i]
+        ga, ba = aff(ua); gb, bb = aff(ub)
+        za = conv_emulated(cur, ua.w.astype(np.float32), mode)
+        zb = conv_emulated(cur, ub.w.astype(np.float32), mode)
+        cur = (np.maximum(ga * za + ba, 0) + np.maximum(gb * zb + bb, 0)).astype(np.float32)
+    return cur
+
+
+def heads(net, cur):
+    B = cur.shape[0]
+    ph = np.maximum(net.pu.gamma[0] * (D.conv(cur, net.pu.w) / np.sqrt(D.EPS)) + net.pu.beta[0], 0).reshape(B, -1)
+    logits = ph @ net.pw + net.pb[0]
+    vh = np.maximum(net.vu.gamma[0] * (D.conv(cur, net.vu.w) / np.sqrt(D.EPS)) + net.vu.beta[0], 0).reshape(B, -1)
+    h1 = np.maximum(vh @ net.vw + net.vb[0], 0)
+    vraw = (h1 @ net.ow + net.ob[0]).reshape(B)
+    ex = np.exp(logits)
+    return ex / ex.sum(axis=1, keepdims=True), np.tanh(vraw)
+
+
+lib = K.load(os.path.join(ROOT, "oracle", "libazoracle.so"))
+d = K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=2, seed=2, max_moves=4,
+                nn=dict(k=C, shared_layers=blocks, fc=512, batch_size=2, features=18, action_space=362))
+e = lib.create(d)
+H.tame_gammas([e], 0, 99)
+net = D.Net(D.unpack(e, 0), blocks)
+rng = np.random.default_rng(8)
+X = (rng.random((NB, 18, size, size)) < 0.25).astype(np.float64) * rng.choice([1.0, -1.0], (NB, 18, size, size))
+p_ref, v_ref = net.infer(X)
+for mode in ("fp16x3", "fp16x2", "fp8"):
+    cur = tower(net, X.astype(np.float32), mode)
+    p, v = heads(net, cur.astype(np.float64))
+    print("%-7s blocks %d: max|dpolicy| %.3e  max|dvalue| %.3e   (tolerance 1e-4)" % (mode, blocks, np.abs(p - p_ref).max(), np.abs(v - v_ref).max()), flush=True)
