@@ -86,6 +86,24 @@ for fname, fmt in (("E4M3", E4M3), ("E5M2", E5M2)):
     report("fp16 hi*hi + %s (hi8*mid8 + mid8*hi8)" % fname, (ah @ bh + c2) * s16, 2.0)
 report("fp32 GEMM (numpy)", A @ B, 0)
 
+
+def mxfp4(x, axis):
+    """E2M1 with one power-of-two (UE8M0) scale per 32 consecutive elements along `axis` (kind::mxf4, 4x the fp16 rate)."""
+    x = np.moveaxis(x.astype(np.float64), axis, -1)
+    shp = x.shape
+    xb = x.reshape(shp[:-1] + (shp[-1] // 32, 32))
+    m = np.abs(xb).max(axis=-1, keepdims=True)
+    e = np.where(m > 0, np.floor(np.log2(np.where(m > 0, m, 1.0))) - 2, 0)  # block max lands in [4, 8): E2M1 max is 6
+    y = xb / 2.0 ** e
+    grid = np.array([0, 0.5, 1, 1.5, 2, 3, 4, 6])
+    idx = np.abs(np.abs(y)[..., None] - grid).argmin(axis=-1)
+    q = np.sign(y) * grid[idx] * 2.0 ** e
+    return np.moveaxis(q.reshape(shp), -1, axis).astype(np.float32)
+
+
+corr4 = mxfp4(ah, 1) @ mxfp4(bl, 0) + mxfp4(al, 1) @ mxfp4(bh, 0)
+report("fp16 hi*hi + MXFP4 (hi*lo + lo*hi), block scale per 32", (ah @ bh + corr4) * s16, 1.5)
+
 # ---- robustness: activations spanning many binades (ReLU of a heavy-tailed pre-activation) with FIXED fp8 scales chosen
 # from the fp16 scale plus headroom (the engine cannot take an absmax of a layer's output before writing it)
 print()
