@@ -56,6 +56,14 @@ __host__ __device__ inline int opp(int p) { return p == C_BLACK ? C_WHITE : C_BL
     if (_e != cudaSuccess) throw CudaError(_e, #x, __FILE__, __LINE__);                    \
   } while (0)
 
+// after every <<<>>>: a bad launch configuration (grid wrap, missing shared-memory opt-in) is reported only by
+// cudaGetLastError — later synchronisations return success.  cudaPeekAtLastError is legal during stream capture.
+#define LAUNCH_CHECK()                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = cudaPeekAtLastError();                                                \
+    if (_e != cudaSuccess) { cudaGetLastError(); throw CudaError(_e, "kernel launch", __FILE__, __LINE__); } \
+  } while (0)
+
 struct CudaError {
   cudaError_t code;
   std::string msg;

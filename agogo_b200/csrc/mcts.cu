@@ -982,36 +982,36 @@ void mcts_set_smem_limits(const GameP& P, int cellsP) {
 }
 #define SMEM(P, E) (ws_bytes(P, (E).cellsP) * WPB)
 void launch_arena_begin(const GameP& P, const EngineDev& E, int n_games, const int* coins, cudaStream_t s) {
-  k_arena_begin<<<grid_for(E.G, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games, coins);
+  k_arena_begin<<<grid_for(E.G, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games, coins); LAUNCH_CHECK();
 }
 void launch_assign_slots(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
-  k_assign_slots<<<1, 32, 0, s>>>(E, n_games, P.shared_tree);
+  k_assign_slots<<<1, 32, 0, s>>>(E, n_games, P.shared_tree); LAUNCH_CHECK();
 }
 void launch_search_begin(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
-  k_search_begin<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games);
+  k_search_begin<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games); LAUNCH_CHECK();
 }
 void launch_encode_roots(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
-  k_encode_roots<<<grid_for(n_games, WPB), WPB * 32, 0, s>>>(P, E, n_games);
+  k_encode_roots<<<grid_for(n_games, WPB), WPB * 32, 0, s>>>(P, E, n_games); LAUNCH_CHECK();
 }
 void launch_select(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
-  k_select<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games);
+  k_select<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games); LAUNCH_CHECK();
 }
 void launch_infer_simple(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
-  k_infer_simple<<<grid_for(n_games, WPB), WPB * 32, 0, s>>>(P, E, n_games);
+  k_infer_simple<<<grid_for(n_games, WPB), WPB * 32, 0, s>>>(P, E, n_games); LAUNCH_CHECK();
 }
 void launch_expand_backup(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
-  k_expand_backup<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games);
+  k_expand_backup<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games); LAUNCH_CHECK();
 }
 void launch_search_end(const GameP& P, const EngineDev& E, int n_games, int record, cudaStream_t s) {
-  k_search_end<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games, record);
+  k_search_end<<<grid_for(n_games, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games, record); LAUNCH_CHECK();
 }
 void launch_rules_apply(const GameP& P, int cellsP, int n, const int* boards, const int* players, const int* moves,
                         int* check, int* applied, int* out_boards, int* taken, cudaStream_t s) {
   k_rules_apply<<<grid_for(n, WPB), WPB * 32, ws_bytes(P, cellsP) * WPB, s>>>(P, cellsP, n, boards, players, moves, check,
-                                                                            applied, out_boards, taken, nullptr);
+                                                                            applied, out_boards, taken, nullptr); LAUNCH_CHECK();
 }
 void launch_rules_status(const GameP& P, int cellsP, int n, const int* boards, const int* passes, int* ended, int* winner,
                          float* sb, float* sw, cudaStream_t s) {
   k_rules_status<<<grid_for(n, WPB), WPB * 32, ws_bytes(P, cellsP) * WPB, s>>>(P, cellsP, n, boards, passes, ended, winner,
-                                                                             sb, sw);
+                                                                             sb, sw); LAUNCH_CHECK();
 }

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <stdexcept>
 #include <thread>
 
 #include "nn.cuh"
@@ -303,7 +304,7 @@ static void launch_heads_tiled(const NetDims& d, const Snapshot& s, const float*
                                float* policy, int ldp, float* value, cudaStream_t st) {
   const size_t sm = (size_t)SB * (3 * d.HW() + d.A1 + d.FC) * 4;
   k_heads_tiled<SB><<<(n_max + SB - 1) / SB, 256, sm, st>>>(ph, vh, s.d + s.pW, s.d + s.pB, s.d + s.vW, s.d + s.vB, s.d + s.voW,
-                                                          s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC);
+                                                          s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC); LAUNCH_CHECK();
 }
 // Samples per block: the most that still gives every SM a block (each sample's arithmetic does not depend on it)
 void heads_tiled(const NetLayout& L, const Snapshot& s, const float* ph, const float* vh, const int* n_dev, int n_max,
@@ -336,9 +337,10 @@ static void run_unit(const NetLayout& L, const Snapshot& s, int ui, const float*
   const SnapUnit& u = s.units[ui];
   size_t total = (size_t)n_max * u.Co * L.d.HW();
   int threads = 128;
+  if ((total + threads - 1) / threads > 0x7fffffffull) throw std::runtime_error("k_unit_f32: batch x channels x points exceeds the grid limit");
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
   k_unit_f32<<<blocks, threads, 0, st>>>(x, s.d + u.filter, s.d + u.gamma, s.d + u.beta, out, n_dev, n_max, u.Ci, u.Co,
-                                         L.d.H, L.d.W, u.k, mode);
+                                         L.d.H, L.d.W, u.k, mode); LAUNCH_CHECK();
   if (launches) (*launches)++;
 }
 
@@ -349,8 +351,9 @@ void heads_fp32(const NetLayout& L, const Snapshot& s, Fp32Scratch& sc, const fl
   run_unit(L, s, pu, tower, sc.ph, n_dev, n_max, 0, st, launches);
   run_unit(L, s, vu, tower, sc.vh, n_dev, n_max, 0, st, launches);
   size_t sm = (size_t)(d.A1 + d.FC) * 4;
+  if (sm > 48 * 1024) throw std::runtime_error("k_heads_f32: ActionSpace + FC exceeds 48 KB of shared memory (use the tiled heads)");
   k_heads_f32<<<n_max, 128, sm, st>>>(sc.ph, sc.vh, s.d + s.pW, s.d + s.pB, s.d + s.vW, s.d + s.vB, s.d + s.voW,
-                                      s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC);
+                                      s.d + s.voB, policy, ldp, value, n_dev, n_max, d.HW(), d.A1, d.FC); LAUNCH_CHECK();
   if (launches) (*launches)++;
 }
 

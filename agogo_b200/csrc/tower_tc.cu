@@ -680,7 +680,7 @@ void launch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUt
   a.out_raw = nullptr; a.exp_a = nullptr; a.exp_b = nullptr;
   const int max_tiles = (I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM) * (L.n_total / BN);
   const int grid = std::min(I.num_sms, max_tiles);
-  k_conv3x3_tc<BN, PAIR, BKT><<<grid, NTHREADS, smem_bytes(BN, BKT, PAIR), st>>>(ah, al, L.mB_hi, L.mB_lo, PAIR ? L.mAff : L.mB_hi, a);
+  k_conv3x3_tc<BN, PAIR, BKT><<<grid, NTHREADS, smem_bytes(BN, BKT, PAIR), st>>>(ah, al, L.mB_hi, L.mB_lo, PAIR ? L.mAff : L.mB_hi, a); LAUNCH_CHECK();
 }
 template <int BKT>
 void dispatch_conv_bk(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
@@ -703,7 +703,7 @@ void launch_conv_pair2(const Impl& I, const Layer& L, const CUtensorMap& ah, con
   const int m_tiles = I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM;
   const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
   const int clusters = std::min(I.pair_clusters, pair_tiles);
-  k_conv3x3_tc2<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(ah, al, L.mB2_hi, L.mB2_lo, L.mAff, a);
+  k_conv3x3_tc2<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(ah, al, L.mB2_hi, L.mB2_lo, L.mAff, a); LAUNCH_CHECK();
 }
 void launch_conv_pair2_f8(const Impl& I, const Layer& L, int in, int out, const int* n_dev, int* err, cudaStream_t st) {
   ConvArgsF8 af;
@@ -719,7 +719,7 @@ void launch_conv_pair2_f8(const Impl& I, const Layer& L, int in, int out, const 
   const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
   const int clusters = std::min(I.pair_clusters, pair_tiles);
   k_conv3x3_tc2_f8<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(I.mX_hi[in], I.mX_h8[in], I.mX_l8[in], L.mB2_hi, L.mB2_h8,
-                                                                  L.mB2_l8, L.mAff, af);
+                                                                  L.mB2_l8, L.mAff, af); LAUNCH_CHECK();
 }
 void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                    const int* n_dev, int* err, cudaStream_t st) {
@@ -921,7 +921,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   {
     size_t total = (size_t)n_max * d.HW() * 64;
     k_pack_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planes, n_dev, n_max, d.F, d.H, d.W, 64, I->guard, I->S, scale,
-                                                                  I->xin_hi, I->xin_lo);
+                                                                  I->xin_hi, I->xin_lo); LAUNCH_CHECK();
     if (launches) (*launches)++;
   }
   int cur = 0;
@@ -930,7 +930,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   if (I->fp8) {  // experiment: the init conv's output also as e4m3 h8 / l8 for the first fused layer
     const size_t ne = (size_t)I->rows_alloc * d.K;
     k_split_fp8<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(I->x_hi[0], I->x_lo[0], ne, ldexpf(1.0f, I->pa), ldexpf(1.0f, I->q),
-                                                             I->x_h8[0], I->x_l8[0]);
+                                                             I->x_h8[0], I->x_l8[0]); LAUNCH_CHECK();
     if (launches) (*launches)++;
   }
   for (size_t l = 1; l < I->layers.size(); l++) {
@@ -948,7 +948,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
     size_t warps = (size_t)n_max * d.HW();
     k_head_convs_nhwc<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
         I->x_hi[cur], I->x_lo[cur], n_dev, n_max, d.K, d.H, d.W, I->guard, I->S, 1.0f / scale, s.d + pu.filter, s.d + pu.gamma,
-        s.d + pu.beta, s.d + vu.filter, s.d + vu.gamma, s.d + vu.beta, sc.ph, sc.vh);
+        s.d + pu.beta, s.d + vu.filter, s.d + vu.gamma, s.d + vu.beta, sc.ph, sc.vh); LAUNCH_CHECK();
     if (launches) (*launches)++;
   }
   heads_tiled(NL, s, sc.ph, sc.vh, n_dev, n_max, policy, ldp, value, st, launches);

@@ -412,9 +412,9 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
       tc_gemm_conv(T->tc, x, u.Ci, Pp(u.filter), u.Co, u.Ci, false, T->z[ui], u.Co, false, 0,
                    same_x ? TC_OPERAND_REUSE : TC_OPERAND_PACK, st, &nl);
     else
-      k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k);
-    k_bn_stats<<<u.Co, 1024, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW);
-    k_bn_apply<<<nblk(n), 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], Pp(u.gamma), Pp(u.beta), T->xn[ui], T->y[ui], n, u.Co, HW);
+      k_conv_fwd_tiled<false><<<dim3((B * HW + TT - 1) / TT, (u.Co + TT - 1) / TT), 256, 0, st>>>(x, Pp(u.filter), T->z[ui], B, u.Ci, u.Co, H, W, u.k); LAUNCH_CHECK();
+    k_bn_stats<<<u.Co, 1024, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], B, u.Co, HW); LAUNCH_CHECK();
+    k_bn_apply<<<nblk(n), 256, 0, st>>>(T->z[ui], T->mean[ui], T->var[ui], Pp(u.gamma), Pp(u.beta), T->xn[ui], T->y[ui], n, u.Co, HW); LAUNCH_CHECK();
     nl += 3;
   };
   // ---- forward
@@ -424,35 +424,35 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   for (int i = 0; i < Lr; i++) {
     unit_fwd(1 + 2 * i, cur);
     unit_fwd(2 + 2 * i, cur, true);
-    k_add_relu<<<nblk(act), 256, 0, st>>>(T->y[1 + 2 * i], T->y[2 + 2 * i], T->cur[i + 1], act);
+    k_add_relu<<<nblk(act), 256, 0, st>>>(T->y[1 + 2 * i], T->y[2 + 2 * i], T->cur[i + 1], act); LAUNCH_CHECK();
     nl++;
     cur = T->cur[i + 1];
   }
   unit_fwd(pu, cur);
   unit_fwd(vu, cur);
-  k_linear_fwd<<<nblk((size_t)B * A), 256, 0, st>>>(T->y[pu], Pp(L.pW), Pp(L.pB), T->logits, B, 2 * HW, A, 0);
-  k_linear_fwd<<<nblk((size_t)B * FC), 256, 0, st>>>(T->y[vu], Pp(L.vW), Pp(L.vB), T->h1, B, HW, FC, 1);
-  k_linear_fwd<<<nblk(B), 256, 0, st>>>(T->h1, Pp(L.voW), Pp(L.voB), T->vraw, B, FC, 1, 0);
-  k_loss<<<1, 256, 0, st>>>(T->logits, T->Pi, T->vraw, T->V, T->dlog, T->dv, T->cost, B, A);
+  k_linear_fwd<<<nblk((size_t)B * A), 256, 0, st>>>(T->y[pu], Pp(L.pW), Pp(L.pB), T->logits, B, 2 * HW, A, 0); LAUNCH_CHECK();
+  k_linear_fwd<<<nblk((size_t)B * FC), 256, 0, st>>>(T->y[vu], Pp(L.vW), Pp(L.vB), T->h1, B, HW, FC, 1); LAUNCH_CHECK();
+  k_linear_fwd<<<nblk(B), 256, 0, st>>>(T->h1, Pp(L.voW), Pp(L.voB), T->vraw, B, FC, 1, 0); LAUNCH_CHECK();
+  k_loss<<<1, 256, 0, st>>>(T->logits, T->Pi, T->vraw, T->V, T->dlog, T->dv, T->cost, B, A); LAUNCH_CHECK();
   nl += 4;
   // ---- backward: heads
   CUDA_CHECK(cudaMemcpyAsync(Gp(L.pB), T->dlog, (size_t)B * A * 4, cudaMemcpyDeviceToDevice, st));
-  k_linear_bwd_w<<<nblk((size_t)2 * HW * A), 256, 0, st>>>(T->y[pu], T->dlog, Gp(L.pW), B, 2 * HW, A);
-  k_linear_bwd_in<<<nblk((size_t)B * 2 * HW), 256, 0, st>>>(Pp(L.pW), T->dlog, T->dph, B, 2 * HW, A);
+  k_linear_bwd_w<<<nblk((size_t)2 * HW * A), 256, 0, st>>>(T->y[pu], T->dlog, Gp(L.pW), B, 2 * HW, A); LAUNCH_CHECK();
+  k_linear_bwd_in<<<nblk((size_t)B * 2 * HW), 256, 0, st>>>(Pp(L.pW), T->dlog, T->dph, B, 2 * HW, A); LAUNCH_CHECK();
   CUDA_CHECK(cudaMemcpyAsync(Gp(L.voB), T->dv, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
-  k_linear_bwd_w<<<nblk(FC), 256, 0, st>>>(T->h1, T->dv, Gp(L.voW), B, FC, 1);
-  k_linear_bwd_in<<<nblk((size_t)B * FC), 256, 0, st>>>(Pp(L.voW), T->dv, T->dh1, B, FC, 1);
-  k_relu_mask<<<nblk((size_t)B * FC), 256, 0, st>>>(T->h1, T->dh1, (size_t)B * FC);
+  k_linear_bwd_w<<<nblk(FC), 256, 0, st>>>(T->h1, T->dv, Gp(L.voW), B, FC, 1); LAUNCH_CHECK();
+  k_linear_bwd_in<<<nblk((size_t)B * FC), 256, 0, st>>>(Pp(L.voW), T->dv, T->dh1, B, FC, 1); LAUNCH_CHECK();
+  k_relu_mask<<<nblk((size_t)B * FC), 256, 0, st>>>(T->h1, T->dh1, (size_t)B * FC); LAUNCH_CHECK();
   CUDA_CHECK(cudaMemcpyAsync(Gp(L.vB), T->dh1, (size_t)B * FC * 4, cudaMemcpyDeviceToDevice, st));
-  k_linear_bwd_w<<<nblk((size_t)HW * FC), 256, 0, st>>>(T->y[vu], T->dh1, Gp(L.vW), B, HW, FC);
-  k_linear_bwd_in<<<nblk((size_t)B * HW), 256, 0, st>>>(Pp(L.vW), T->dh1, T->dvh, B, HW, FC);
+  k_linear_bwd_w<<<nblk((size_t)HW * FC), 256, 0, st>>>(T->y[vu], T->dh1, Gp(L.vW), B, HW, FC); LAUNCH_CHECK();
+  k_linear_bwd_in<<<nblk((size_t)B * HW), 256, 0, st>>>(Pp(L.vW), T->dh1, T->dvh, B, HW, FC); LAUNCH_CHECK();
   nl += 7;
   // ---- backward: units
   auto unit_bwd = [&](int ui, const float* x, const float* dy, float* dx, bool same_x = false) {
     const UnitH& u = L.units[ui];
     size_t n = (size_t)B * u.Co * HW;
-    k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n);
-    k_bn_bwd_apply<<<u.Co, 1024, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW);
+    k_bn_bwd_pre<<<nblk(n), 256, 0, st>>>(dy, T->y[ui], T->xn[ui], Pp(u.gamma), Gp(u.gamma), Gp(u.beta), T->tmp, n); LAUNCH_CHECK();
+    k_bn_bwd_apply<<<u.Co, 1024, 0, st>>>(T->tmp, T->xn[ui], T->var[ui], B, u.Co, HW); LAUNCH_CHECK();
     const bool dw_tc = T->tc.impl && u.k == 3 && u.Ci == K && u.Co == K;
     if (dw_tc)
       tc_gemm_dw(T->tc, x, T->tmp, Gp(u.filter), same_x ? TC_OPERAND_REUSE : TC_OPERAND_PACK, st, &nl);
@@ -460,8 +460,8 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
       const int slices = dw_slices(u, B * HW);
       const size_t nw = (size_t)u.Co * u.Ci * u.k * u.k;
       k_conv_bwd_w_tiled<<<dim3((u.Ci * u.k * u.k + TT - 1) / TT, (u.Co + TT - 1) / TT, slices), 256, 0, st>>>(
-          x, T->tmp, slices > 1 ? T->dwpart : Gp(u.filter), B, u.Ci, u.Co, H, W, u.k);
-      if (slices > 1) { k_sum_slices<<<nblk(nw), 256, 0, st>>>(T->dwpart, slices, nw, Gp(u.filter)); nl++; }
+          x, T->tmp, slices > 1 ? T->dwpart : Gp(u.filter), B, u.Ci, u.Co, H, W, u.k); LAUNCH_CHECK();
+      if (slices > 1) { k_sum_slices<<<nblk(nw), 256, 0, st>>>(T->dwpart, slices, nw, Gp(u.filter)); LAUNCH_CHECK(); nl++; }
     }
     nl += 3;
     if (dx && T->tc.impl && u.k == 3 && u.Ci % 64 == 0 && u.Co % 64 == 0) {
@@ -469,8 +469,8 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
       tc_gemm_conv(T->tc, T->tmp, u.Co, Pp(u.filter), u.Co, u.Ci, true, dx, u.Ci, true, 1,
                    dw_tc ? TC_OPERAND_PACK_KEEP_EXP : TC_OPERAND_PACK, st, &nl);
     } else if (dx) {  // dx += conv(dz, mirrored transposed filter)
-      k_flip_filter<<<nblk((size_t)u.Ci * u.Co * u.k * u.k), 256, 0, st>>>(Pp(u.filter), T->wflip, u.Ci, u.Co, u.k);
-      k_conv_fwd_tiled<true><<<dim3((B * HW + TT - 1) / TT, (u.Ci + TT - 1) / TT), 256, 0, st>>>(T->tmp, T->wflip, dx, B, u.Co, u.Ci, H, W, u.k);
+      k_flip_filter<<<nblk((size_t)u.Ci * u.Co * u.k * u.k), 256, 0, st>>>(Pp(u.filter), T->wflip, u.Ci, u.Co, u.k); LAUNCH_CHECK();
+      k_conv_fwd_tiled<true><<<dim3((B * HW + TT - 1) / TT, (u.Ci + TT - 1) / TT), 256, 0, st>>>(T->tmp, T->wflip, dx, B, u.Co, u.Ci, H, W, u.k); LAUNCH_CHECK();
       nl += 2;
     }
   };
@@ -480,7 +480,7 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
   for (int i = Lr - 1; i >= 0; i--) {
     // out = relu(l1 + l2): gate on the block output
     CUDA_CHECK(cudaMemcpyAsync(T->dl, T->dcur, act * 4, cudaMemcpyDeviceToDevice, st));
-    k_relu_mask<<<nblk(act), 256, 0, st>>>(T->cur[i + 1], T->dl, act);
+    k_relu_mask<<<nblk(act), 256, 0, st>>>(T->cur[i + 1], T->dl, act); LAUNCH_CHECK();
     nl++;
     CUDA_CHECK(cudaMemsetAsync(T->dprev, 0, act * 4, st));
     const float* xin = i == 0 ? T->y[0] : T->cur[i];
@@ -584,11 +584,12 @@ void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params
   else if (world == 8) AZ_LAUNCH_K8(8);
   else AZ_LAUNCH_K8(0);
 #undef AZ_LAUNCH_K8
+  LAUNCH_CHECK();
   if (launches) (*launches)++;
 }
 
 void train_sgd(TrainWS& ws, const NetLayout& L, float* P, float lr, float gscale, cudaStream_t st, unsigned long long* launches) {
   TrainImpl* T = (TrainImpl*)ws.impl;
-  k_sgd<<<(unsigned)std::min<size_t>((L.total / 4 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(P, T->grads, lr, gscale, L.total);
+  k_sgd<<<(unsigned)std::min<size_t>((L.total / 4 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(P, T->grads, lr, gscale, L.total); LAUNCH_CHECK();
   if (launches) (*launches)++;
 }

@@ -347,7 +347,7 @@ void tc_gemm_destroy(TcGemm& g) {
 static void absmax_exp(const float* x, size_t n, int* e, cudaStream_t st) {
   CUDA_CHECK(cudaMemsetAsync(e, 0x80, 4, st));  // 0x80808080: below every real exponent
   unsigned blocks = (unsigned)std::min<size_t>((n + 1023) / 1024, 1024);
-  k_absmax_exp<<<blocks, 256, 0, st>>>(x, n, e);
+  k_absmax_exp<<<blocks, 256, 0, st>>>(x, n, e); LAUNCH_CHECK();
 }
 
 // Brings the NCHW tensor x [B][C][HW] into operand slot `si` according to `state`; returns the number of kernels launched.
@@ -363,7 +363,7 @@ static int fill_slot(TcGemmImpl* I, int si, const float* x, int C, int state, cu
   }
   int n = 1;
   if (state == TC_OPERAND_PACK) { absmax_exp(x, (size_t)I->B * C * d.HW(), sl.exp, st); n++; }
-  k_pack_nchw<<<dim3((d.HW() + 31) / 32, cpad / 64, I->B), 256, 0, st>>>(x, I->B, C, d.H, d.W, cpad, I->guard, I->S, sl.exp, sl.hi, sl.lo);
+  k_pack_nchw<<<dim3((d.HW() + 31) / 32, cpad / 64, I->B), 256, 0, st>>>(x, I->B, C, d.H, d.W, cpad, I->guard, I->S, sl.exp, sl.hi, sl.lo); LAUNCH_CHECK();
   return n;
 }
 
@@ -382,7 +382,7 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   absmax_exp(filter, (size_t)fCo * fCi * 9, I->exp_b, st);
   {
     size_t wt = (size_t)Cout * 9 * cpad;
-    k_prep_filter<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(filter, fCo, fCi, cpad, flip ? 1 : 0, I->exp_b, I->w_hi, I->w_lo);
+    k_prep_filter<<<(unsigned)((wt + 255) / 256), 256, 0, st>>>(filter, fCo, fCi, cpad, flip ? 1 : 0, I->exp_b, I->w_hi, I->w_lo); LAUNCH_CHECK();
   }
   const int bn = std::min(256, Cout);
   // tensor maps over the (re-used) operand buffers for this shape
@@ -395,12 +395,12 @@ void tc_gemm_conv(TcGemm& g, const float* x, int Cin, const float* filter, int f
   const int max_tiles = ((I->B * I->S + BM - 1) / BM) * (Cout / bn);
   const int grid = std::min(I->num_sms, max_tiles);
   auto launch = [&](auto kern, int BNv) {
-    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, mBh, a);
+    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, mBh, a); LAUNCH_CHECK();
   };
   if (bn == 256) launch(k_conv3x3_tc<256, false, 64>, 256);
   else if (bn == 128) launch(k_conv3x3_tc<128, false, 64>, 128);
   else launch(k_conv3x3_tc<64, false, 64>, 64);
-  k_unpack_nchw<<<dim3((HW + 31) / 32, (Cout + 31) / 32, I->B), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0);
+  k_unpack_nchw<<<dim3((HW + 31) / 32, (Cout + 31) / 32, I->B), 256, 0, st>>>(I->raw, I->B, Cout, d.H, d.W, Cout, I->guard, I->S, out, accumulate ? 1 : 0); LAUNCH_CHECK();
   if (launches) *launches += nl + 4;
 }
 
@@ -417,7 +417,7 @@ void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, int x_sta
   int nl = fill_slot(I, 0, x, C, x_state, st);
   int* exp_dz = I->slot[1].exp;
   absmax_exp(dz, n, exp_dz, st);
-  k_pack_cmajor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, I->B, C, d.H, d.W, I->ld, I->guard, I->S, exp_dz, I->t_hi, I->t_lo);
+  k_pack_cmajor<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dz, I->B, C, d.H, d.W, I->ld, I->guard, I->S, exp_dz, I->t_hi, I->t_lo); LAUNCH_CHECK();
   const int bn = std::min(256, C);
   CUtensorMap mAh = make_map(I->t_hi, I->crow, I->ld, BM, 64), mAl = make_map(I->t_lo, I->crow, I->ld, BM, 64);
   CUtensorMap mBh = make_map(sx.hi, I->rows_alloc, C, 64, 64), mBl = make_map(sx.lo, I->rows_alloc, C, 64, 64);
@@ -427,11 +427,11 @@ void tc_gemm_dw(TcGemm& g, const float* x, const float* dz, float* dW, int x_sta
   const int items = 9 * a.co_tiles * a.ci_tiles * a.splits;
   const int grid = std::min(I->num_sms, items);
   auto launch = [&](auto kern, int BNv) {
-    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, a);
+    kern<<<grid, NTHREADS, smem_bytes(BNv, 64), st>>>(mAh, mAl, mBh, mBl, a); LAUNCH_CHECK();
   };
   if (bn == 256) launch(k_dw_tc<256>, 256);
   else if (bn == 128) launch(k_dw_tc<128>, 128);
   else launch(k_dw_tc<64>, 64);
-  k_dw_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(I->partial, I->splits, C, C, exp_dz, sx.exp, dW);
+  k_dw_reduce<<<(C * C + 255) / 256, 256, 0, st>>>(I->partial, I->splits, C, C, exp_dz, sx.exp, dW); LAUNCH_CHECK();
   if (launches) *launches += nl + 4;
 }

@@ -650,3 +650,45 @@ def test_arena_play_chunking_and_single_slot(oracle, engine_lib):
         for xa, xb in zip(runs[0][1], other[1]):
             assert xa.shape == xb.shape and (xa.view(np.uint32) == xb.view(np.uint32)).all()
         assert runs[0][2:] == other[2:]
+
+
+@pytest.mark.parametrize("size,inferer,workers,sims,plies,temp", [
+    (19, "dummy", 1, 96, 6, 0.0),     # all 362 priors equal: every Select is decided by the first-strict-max tie-break
+    (19, "table", 1, 160, 8, 0.0),    # distinct priors per depth: rank sort over 362 entries, 3 x 128-wide Select strides
+    (19, "ties", 1, 96, 6, 0.0),      # priors quantised to 8 levels: the stable rank sort must keep index order in ties
+    (19, "table", 16, 160, 6, 0.0),   # the fixed worker schedule on 362-child nodes (virtual-loss flags, short last round)
+    (19, "table", 1, 64, 10, 1.0),    # temperature sampling from the per-tree RNG spreads the 8 games over different lines
+    (13, "table", 1, 128, 8, 0.0),    # 170 children: two strides, the second partial
+    (13, "dummy", 16, 64, 6, 0.0),
+])
+def test_parity_wq_full_board_search(oracle, engine_lib, size, inferer, workers, sims, plies, temp):
+    """The headline board size against the oracle, bit for bit: nodes with more than 128
+    children take the multi-stride path of Node.Select (node.go:170-237) and the >128-entry rank sort of
+    expandAndSimulate (search.go:314-330) on every simulation of BASELINE config C3; trees after every ply, moves,
+    examples, statistics and counters equal the oracle's."""
+    A1 = size * size + 1
+    def desc():
+        d = K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=sims, n_games=8, seed=31, max_moves=plies, workers=workers,
+                        nn=H.tiny_nn(size, size, A1, features=18))
+        if temp:
+            d.mcts.random_count, d.mcts.random_temperature, d.mcts.random_min_visits = plies, temp, 0
+        return d
+    eo, eg = _pair(oracle, engine_lib, desc)
+    rng = np.random.default_rng(size * 100 + sims)
+    table = rng.random((96, A1)).astype(np.float32)
+    if inferer == "ties":
+        table = np.ceil(table * 8).astype(np.float32)
+    table /= table.sum(axis=1, keepdims=True)
+    values = rng.uniform(0.05, 0.95, 96).astype(np.float32)
+    for e in (eo, eg):
+        if inferer == "dummy":
+            e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+        else:
+            e.set_table(0, table, values); e.set_table(1, table[::-1].copy(), values[::-1].copy())
+    a, b = H.play_and_collect(eo, 8), H.play_and_collect(eg, 8)
+    H.assert_same_run(a, b, "wq%d-%s-w%d" % (size, inferer, workers))
+    c = a["counters"]
+    assert c["sims"] == c["searches"] * sims
+    assert c["select_children"] > 128 * c["select_levels"]  # the strided path really ran
+    if temp:
+        assert len({tuple(r["moves"]) for r in a["records"]}) >= 4
