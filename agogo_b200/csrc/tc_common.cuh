@@ -426,11 +426,11 @@ CUtensorMap make_map_aff(void* base, uint64_t rows, uint64_t cols) {
 }
 
 // per-sample layout: 3-D fp16 tensor [n][S][cols], box {64 cols, BM positions, 1 sample}
-CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk) {
+CUtensorMap make_map3d(void* base, uint64_t n, uint64_t S, uint64_t cols, int bk, uint32_t box_rows = BM) {
   CUtensorMap m;
   cuuint64_t dims[3] = {cols, S, n};
   cuuint64_t strides[2] = {cols * 2, S * cols * 2};
-  cuuint32_t box[3] = {(cuuint32_t)bk, BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)bk, box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

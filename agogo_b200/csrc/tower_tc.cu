@@ -301,7 +301,7 @@ __device__ __forceinline__ void umma2_f8(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+__device__ __forceinline__ uint8_t to_e5m2(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_conv3x3_tc2_f8(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmAh8,
@@ -390,7 +390,8 @@ k_conv3x3_tc2_f8(const __grid_constant__ CUtensorMap tmA16, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN);  // formats 0/0: F16 x F16 for kind::f16, E4M3 x E4M3 for kind::f8f6f4
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);  // kind::f16: F16 x F16
+      constexpr uint32_t idesc8 = idesc | (1u << 7);      // kind::f8f6f4: A = E5M2 (activations), B = E4M3 (filters)
       uint32_t it = 0, tcount = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
         const int acc = tcount & 1;
@@ -413,8 +414,8 @@ k_conv3x3_tc2_f8(const __grid_constant__ CUtensorMap tmA16, const __grid_constan
             umma2_f16(d_tmem, dA16 + (uint64_t)(ks * 2), dB16 + (uint64_t)(ks * 2), idesc, (kb | ks) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 2; ks++) {  // 32 fp8 = 32 B per step
-            umma2_f8(d_tmem, dAh8 + (uint64_t)(ks * 2), dBl8 + (uint64_t)(ks * 2), idesc, 1u);
-            umma2_f8(d_tmem, dAl8 + (uint64_t)(ks * 2), dBh8 + (uint64_t)(ks * 2), idesc, 1u);
+            umma2_f8(d_tmem, dAh8 + (uint64_t)(ks * 2), dBl8 + (uint64_t)(ks * 2), idesc8, 1u);
+            umma2_f8(d_tmem, dAl8 + (uint64_t)(ks * 2), dBh8 + (uint64_t)(ks * 2), idesc8, 1u);
           }
           umma2_commit_mc(empty_bar(s));
         }
@@ -493,8 +494,293 @@ k_conv3x3_tc2_f8(const __grid_constant__ CUtensorMap tmA16, const __grid_constan
             const float res = v - hf;
             hi[k] = h;
             lo[k] = __float2half_rn(res);
-            h8[k] = to_e4m3(hf * af.scale_h8);
-            l8[k] = to_e4m3(res * af.scale_l8);
+            h8[k] = to_e5m2(hf * af.scale_h8);
+            l8[k] = to_e5m2(res * af.scale_l8);
+          }
+          if (valid) {
+            *(uint4*)(a.out_hi + orow + c0 + sub * 8) = *(const uint4*)hi;
+            *(uint4*)(a.out_lo + orow + c0 + sub * 8) = *(const uint4*)lo;
+            *(uint2*)(af.out_h8 + orow + c0 + sub * 8) = *(const uint2*)h8;
+            *(uint2*)(af.out_l8 + orow + c0 + sub * 8) = *(const uint2*)l8;
+          }
+          __syncwarp();
+          aff_issue(qq + 2);
+        }
+      }
+      if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & PEER_MASK);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+// -------------------------------------------------------------------------------------------------
+// Halo form of the FP8-correction layer (the product path of the fused layers, AZ_TC_FP8 unset or 2).
+// The per-tap kernel above re-loads the activation tile nine times per 64-channel chunk (one shifted 128-row box per
+// tap): 64 KB of shared-memory fill per K block on top of the 64 KB the tensor cores read — with the FP8 corrections a
+// K block is 8 MMA slots (1024 clk), so fill + operand reads need 128 B/clk, the whole shared-memory bandwidth of the SM
+// (ncu: tensor pipe 78 % active, profiles/r02_summary.md).  Here ONE box of BM + 2*(Wp+1) consecutive board positions
+// (170 -> 176 rows for 19x19) is loaded per (tile, 64-channel chunk) and the nine taps are row-shifted views of it: the
+// operand descriptor simply starts (Wp+1) + dy*Wp + dx rows into the tile.  TMA and the tensor core both apply the
+// 128B / 64B swizzle to absolute shared-memory address bits, so a start address that is row- but not pattern-aligned
+// reads what TMA wrote (base-offset field 0; tools/probe_rowshift.cu, profiles/r02_probe_rowshift.txt: exact for every
+// shift, fp16/SWIZZLE_128B and fp8/SWIZZLE_64B).  Loop order kc outer, tap inner; activation stages (2 x hrows x 256 B)
+// and filter stages (3 x 32 KB) have their own full/empty barriers.  Fill per K block: 32 KB of filters + 1/9 of a
+// 44 KB activation stage = 37 KB instead of 64 KB.
+// Activation correction operands are E5M2 at the fp16 operand's own scale — h8 = e5m2(hi16), l8 = e5m2(lo * 2^11) — so
+// they can neither saturate nor flush before fp16 itself does (E4M3's 2^-9..448 range did both on heavy-tailed
+// activations); filters stay E4M3 (static, scaled exactly per layer): w_l8 = e4m3(w_lo), w_h8 = e4m3(w_hi * 2^-11).
+constexpr int NBST = 3;
+constexpr int BST_BYTES = 2 * BM * 64 + 2 * BM * 64;  // B16 16 KB | B_h8 8 KB | B_l8 8 KB
+__host__ __device__ constexpr int smem_bytes_f8h(int hrows) { return 2 * hrows * 256 + NBST * BST_BYTES + AFF_BYTES + 1024 + 256; }
+constexpr int F8H_MAX_HROWS = 176;
+
+struct ConvArgsF8H {
+  ConvArgs c;
+  uint8_t* out_h8;  // [(guard + rows)][cout] e5m2(hi16)
+  uint8_t* out_l8;  // [(guard + rows)][cout] e5m2(lo * 2^11)
+  float scale_l8;   // 2^11
+  int hrows;        // rows of an activation stage: BM + 2*halo rounded up to 16
+  int halo;         // Wp + 1
+};
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_conv3x3_tc2_f8h(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmAh8,
+                  const __grid_constant__ CUtensorMap tmAl8, const __grid_constant__ CUtensorMap tmB16,
+                  const __grid_constant__ CUtensorMap tmBh8, const __grid_constant__ CUtensorMap tmBl8,
+                  const __grid_constant__ CUtensorMap tmAff, ConvArgsF8H af) {
+  const ConvArgs& a = af.c;
+  constexpr int BK = 64, BN = 256, OUTC = 128;
+  constexpr int T16 = BM * BK * 2, T8 = BM * BK;  // filter tiles: 16 KB / 8 KB (128 rows each)
+  const uint32_t A16_BYTES = (uint32_t)af.hrows * 128u, A8_BYTES = (uint32_t)af.hrows * 64u, AST_BYTES = (uint32_t)af.hrows * 256u;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_smem = smem_base + 2 * AST_BYTES;
+  const uint32_t aff_smem = w_smem + NBST * BST_BYTES;
+  const uint32_t bars = aff_smem + AFF_BYTES;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + (bars - smem_base) + 240);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  auto xfull_bar = [&](int s) { return bars + 8u * s; };                   // activation stages
+  auto xempty_bar = [&](int s) { return bars + 8u * (2 + s); };
+  auto wfull_bar = [&](int s) { return bars + 8u * (4 + s); };             // filter stages
+  auto wempty_bar = [&](int s) { return bars + 8u * (4 + NBST + s); };
+  auto tfull_bar = [&](int i) { return bars + 8u * (4 + 2 * NBST + i); };
+  auto tempty_bar = [&](int i) { return bars + 8u * (6 + 2 * NBST + i); };
+  auto afull_bar = [&](int quad, int buf) { return bars + 8u * (8 + 2 * NBST + quad * 2 + buf); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; s++) { mbar_init(xfull_bar(s), 2); mbar_init(xempty_bar(s), 1); }
+    for (int s = 0; s < NBST; s++) { mbar_init(wfull_bar(s), 2); mbar_init(wempty_bar(s), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 8); }
+    for (int i = 0; i < 8; i++) mbar_init(afull_bar(i >> 1, i & 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int n = min(*a.n_dev, a.n_max);
+  const int rows = n * a.S;
+  const int m_tiles = a.mode3d ? n * a.tps : (rows + BM - 1) / BM;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int n_tiles = a.n_total / BN;
+  const int total_tiles = m_pairs * n_tiles;
+  const int kcn = a.cin / BK;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const uint32_t my_tiles = cluster_id < total_tiles ? (uint32_t)((total_tiles - cluster_id + n_clusters - 1) / n_clusters) : 0u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own activation halo tile + own half of the filter tile =====
+      const uint32_t total_x = my_tiles * (uint32_t)kcn, total_w = total_x * 9u;
+      uint32_t xi = 0;
+      auto issue_x = [&](uint32_t i) {
+        const int tl = (int)(i / (uint32_t)kcn), kc = (int)i - tl * kcn;
+        const int tile = cluster_id + tl * n_clusters;
+        const int mt = 2 * (tile / n_tiles) + (int)rank;
+        const uint32_t sa = smem_base + (i & 1u) * AST_BYTES;
+        const uint32_t lbar = xfull_bar((int)(i & 1u)) & PEER_MASK;
+        mbar_expect_tx_cluster(lbar, AST_BYTES);
+        if (a.mode3d) {
+          const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM - af.halo;  // <0 / >=S / b>=n: TMA zero fill
+          tma2_load_3d(sa, &tmA16, lbar, kc * BK, p0, b);
+          tma2_load_3d(sa + A16_BYTES, &tmAh8, lbar, kc * BK, p0, b);
+          tma2_load_3d(sa + A16_BYTES + A8_BYTES, &tmAl8, lbar, kc * BK, p0, b);
+        } else {
+          const int arow = a.guard + mt * BM - af.halo;
+          tma2_load_2d(sa, &tmA16, lbar, kc * BK, arow);
+          tma2_load_2d(sa + A16_BYTES, &tmAh8, lbar, kc * BK, arow);
+          tma2_load_2d(sa + A16_BYTES + A8_BYTES, &tmAl8, lbar, kc * BK, arow);
+        }
+      };
+      for (uint32_t t = 0; t < total_w; t++) {
+        const uint32_t i = t / 9u;
+        // activation stage i must be in flight before its filters; stage i+1 is prefetched as soon as its buffer is free
+        while (xi < total_x && xi <= i + 1u) {
+          const uint32_t par = ((xi >> 1) & 1u) ^ 1u;
+          if (xi <= i) mbar_wait(xempty_bar((int)(xi & 1u)), par);
+          else if (!mbar_test(xempty_bar((int)(xi & 1u)), par)) break;
+          issue_x(xi);
+          xi++;
+        }
+        const int tap = (int)(t - i * 9u);
+        const int tl = (int)(i / (uint32_t)kcn), kc = (int)i - tl * kcn;
+        const int tile = cluster_id + tl * n_clusters;
+        const int nt = tile % n_tiles;
+        const int n0 = nt * BN + (int)rank * (BN / 2);
+        const int s = (int)(t % NBST);
+        mbar_wait(wempty_bar(s), ((t / NBST) & 1u) ^ 1u);
+        const uint32_t sb = w_smem + s * BST_BYTES;
+        const uint32_t lbar = wfull_bar(s) & PEER_MASK;
+        mbar_expect_tx_cluster(lbar, BST_BYTES);
+        const int kcol = tap * a.cin + kc * BK;
+        tma2_load_2d(sb, &tmB16, lbar, kcol, n0);
+        tma2_load_2d(sb + T16, &tmBh8, lbar, kcol, n0);
+        tma2_load_2d(sb + T16 + T8, &tmBl8, lbar, kcol, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer: the leader CTA's single thread drives both SMs =====
+      constexpr uint32_t idesc16 = make_idesc(2 * BM, BN);
+      constexpr uint32_t idesc8 = idesc16 | (1u << 7);  // kind::f8f6f4: A = E5M2 (1), B = E4M3 (0)
+      uint32_t xi = 0, t = 0, tcount = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
+        const int acc = tcount & 1;
+        mbar_wait(tempty_bar(acc), ((tcount >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kc = 0; kc < kcn; kc++, xi++) {
+          mbar_wait(xfull_bar((int)(xi & 1u)), (xi >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_base + (xi & 1u) * AST_BYTES;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; tap++, t++) {
+            const int s = (int)(t % NBST);
+            mbar_wait(wfull_bar(s), (t / NBST) & 1u);
+            tc_fence_after();
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            const uint32_t j0 = (uint32_t)(af.halo + dy * a.Wp + dx);  // first row of this tap's view of the halo tile
+            const uint32_t sb = w_smem + s * BST_BYTES;
+            const uint64_t dA16 = make_desc_sw<64>(sa + j0 * 128u);
+            const uint64_t dAh8 = make_desc_sw<32>(sa + A16_BYTES + j0 * 64u);
+            const uint64_t dAl8 = make_desc_sw<32>(sa + A16_BYTES + A8_BYTES + j0 * 64u);
+            const uint64_t dB16 = make_desc_sw<64>(sb), dBh8 = make_desc_sw<32>(sb + T16), dBl8 = make_desc_sw<32>(sb + T16 + T8);
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)  // 16 fp16 = 32 B per step
+              umma2_f16(d_tmem, dA16 + (uint64_t)(ks * 2), dB16 + (uint64_t)(ks * 2), idesc16, (kc | tap | ks) ? 1u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {  // 32 fp8 = 32 B per step
+              umma2_f8(d_tmem, dAh8 + (uint64_t)(ks * 2), dBl8 + (uint64_t)(ks * 2), idesc8, 1u);
+              umma2_f8(d_tmem, dAl8 + (uint64_t)(ks * 2), dBh8 + (uint64_t)(ks * 2), idesc8, 1u);
+            }
+            umma2_commit_mc(wempty_bar(s));
+          }
+          umma2_commit_mc(xempty_bar((int)(xi & 1u)));
+        }
+        umma2_commit_mc(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5 of either CTA: own 128 TMEM lanes =====
+    const int quad = warp & 3;
+    uint32_t tcount = 0;
+    constexpr int CH = OUTC / 8;
+    const uint32_t aff_buf = aff_smem + quad * 8192;
+    auto aff_issue = [&](uint32_t qq) {
+      const int tile = cluster_id + (int)(qq / CH) * n_clusters;
+      if (tile >= total_tiles) return;
+      const int j = qq % CH;
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int prow = a.mode3d ? (mt % a.tps) * BM + quad * 32 : (mt * BM + quad * 32) % a.S;
+      if (lane == 0) {
+        const uint32_t bar = afull_bar(quad, qq & 1);
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d(aff_buf + (qq & 1) * 4096, &tmAff, bar, (nt * OUTC + j * 8) * 4, prow);
+      }
+    };
+    aff_issue(0);
+    aff_issue(1);
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, tcount++) {
+      const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+      const int mt = 2 * mp + (int)rank;
+      const int m0 = mt * BM;
+      const int acc = tcount & 1;
+      mbar_wait(tfull_bar(acc), (tcount >> 1) & 1u);
+      tc_fence_after();
+      int r, p;
+      bool inb;
+      if (a.mode3d) {
+        const int b = mt / a.tps;
+        p = (mt - b * a.tps) * BM + quad * 32 + lane;
+        r = b * a.S + p;
+        inb = p < a.S && mt < m_tiles;
+      } else {
+        r = m0 + quad * 32 + lane;
+        p = r % a.S;
+        inb = r < rows;
+      }
+      const int y = p / a.Wp, x = p - y * a.Wp;
+      const bool valid = inb && y < a.H && x < a.W;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      const size_t orow = (size_t)(a.guard + r) * a.cout + nt * OUTC;
+      bool overflow = false;
+#pragma unroll 1
+      for (int c0 = 0; c0 < OUTC; c0 += 32) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row + c0, ra);
+        tmem_ld32(t_row + BN / 2 + c0, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < 4; sub++) {
+          const uint32_t qq = tcount * CH + (c0 >> 3) + sub;
+          mbar_wait(afull_bar(quad, qq & 1), (qq >> 1) & 1);
+          const uint8_t* box = smem_al + (aff_buf - smem_base) + (qq & 1) * 4096 + lane * 128;
+          __align__(16) __half hi[8];
+          __align__(16) __half lo[8];
+          __align__(8) uint8_t h8[8];
+          __align__(8) uint8_t l8[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const float4 f = *reinterpret_cast<const float4*>(box + ((k ^ (lane & 7)) << 4));
+            const int i = sub * 8 + k;
+            float v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+            v *= a.act_scale;
+            const __half h = __float2half_rn(v);
+            const float hf = __half2float(h);
+            overflow |= valid && !(fabsf(hf) <= 65504.0f);
+            const float res = v - hf;
+            hi[k] = h;
+            lo[k] = __float2half_rn(res);
+            h8[k] = to_e5m2(hf);
+            l8[k] = to_e5m2(res * af.scale_l8);
           }
           if (valid) {
             *(uint4*)(a.out_hi + orow + c0 + sub * 8) = *(const uint4*)hi;
@@ -524,8 +810,8 @@ __global__ void k_split_fp8(const __half* __restrict__ hi, const __half* __restr
                             uint8_t* h8, uint8_t* l8) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  h8[i] = to_e4m3(__half2float(hi[i]) * scale_h8);
-  l8[i] = to_e4m3(__half2float(lo[i]) * scale_l8);
+  h8[i] = to_e5m2(__half2float(hi[i]) * scale_h8);
+  l8[i] = to_e5m2(__half2float(lo[i]) * scale_l8);
 }
 
 // fp32 NCHW planes -> zero-bordered NHWC fp16 hi/lo (channels padded to cpad)
@@ -605,6 +891,7 @@ void tower_configure_device() {
   set_conv_attr<64, false, 32>();
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_f8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_f8h, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
 }
 
 // e4m3 operands (AZ_TC_FP8 experiment): [rows][cols] bytes, box {64 bytes, box_rows}, SWIZZLE_64B
@@ -619,11 +906,11 @@ CUtensorMap make_map_u8(void* base, uint64_t rows, uint64_t cols, uint32_t box_r
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(u8) failed: " + std::to_string((int)r));
   return m;
 }
-CUtensorMap make_map3d_u8(void* base, uint64_t n, uint64_t S, uint64_t cols) {
+CUtensorMap make_map3d_u8(void* base, uint64_t n, uint64_t S, uint64_t cols, uint32_t box_rows = BM) {
   CUtensorMap m;
   cuuint64_t dims[3] = {cols, S, n};
   cuuint64_t strides[2] = {cols, S * cols};
-  cuuint32_t box[3] = {64, BM, 1};
+  cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -649,8 +936,10 @@ struct Impl {
   int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1, bk = 64;
   int pair_clusters = 0;  // > 0: fused layers run on k_conv3x3_tc2 with this many co-resident CTA pairs
   // AZ_TC_FP8=1 (experiment): correction passes on the FP8 tensor path; activations also travel as e4m3 h8 / l8
-  bool fp8 = false;
-  int pa = 0, q = 10;  // h8 = e4m3(hi16 * 2^pa), l8 = e4m3(lo * 2^q); weights carry the inverse factors
+  int fp8 = 0;         // 0: three fp16 passes; 1: per-tap FP8-correction kernel (A/B); 2: halo FP8-correction kernel (default)
+  int pa = 0, q = 11;  // h8 = e5m2(hi16 * 2^pa), l8 = e5m2(lo * 2^q); filters (e4m3) carry the inverse factors
+  int hrows = 0, halo = 0;                     // halo kernel: rows per activation stage, Wp + 1
+  CUtensorMap mXh_hi[2], mXh_h8[2], mXh_l8[2];  // halo boxes {64 channels, hrows positions}
   uint8_t *x_h8[2] = {nullptr, nullptr}, *x_l8[2] = {nullptr, nullptr};
   CUtensorMap mX_h8[2], mX_l8[2];
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
@@ -721,6 +1010,23 @@ void launch_conv_pair2_f8(const Impl& I, const Layer& L, int in, int out, const 
   k_conv3x3_tc2_f8<<<2 * clusters, NTHREADS, smem_bytes2(), st>>>(I.mX_hi[in], I.mX_h8[in], I.mX_l8[in], L.mB2_hi, L.mB2_h8,
                                                                   L.mB2_l8, L.mAff, af); LAUNCH_CHECK();
 }
+void launch_conv_pair2_f8h(const Impl& I, const Layer& L, int in, int out, const int* n_dev, int* err, cudaStream_t st) {
+  ConvArgsF8H af;
+  ConvArgs& a = af.c;
+  a.n_dev = n_dev; a.n_max = I.n_max; a.S = I.S; a.Wp = I.d.W + 1; a.H = I.d.H; a.W = I.d.W; a.guard = I.guard;
+  a.mode3d = I.mode3d; a.tps = I.tps;
+  a.cin = L.cin; a.n_total = L.n_total; a.cout = I.d.K; a.aff = L.aff; a.out_hi = I.x_hi[out]; a.out_lo = I.x_lo[out];
+  a.act_scale = ldexpf(1.0f, I.ea); a.err = err; a.passes = 3;
+  a.out_raw = nullptr; a.exp_a = nullptr; a.exp_b = nullptr;
+  af.out_h8 = I.x_h8[out]; af.out_l8 = I.x_l8[out];
+  af.scale_l8 = ldexpf(1.0f, I.q);
+  af.hrows = I.hrows; af.halo = I.halo;
+  const int m_tiles = I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM;
+  const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
+  const int clusters = std::min(I.pair_clusters, pair_tiles);
+  k_conv3x3_tc2_f8h<<<2 * clusters, NTHREADS, smem_bytes_f8h(I.hrows), st>>>(I.mXh_hi[in], I.mXh_h8[in], I.mXh_l8[in], L.mB2_hi,
+                                                                           L.mB2_h8, L.mB2_l8, L.mAff, af); LAUNCH_CHECK();
+}
 void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                    const int* n_dev, int* err, cudaStream_t st) {
   if (I.pair_clusters > 0 && L.pair && L.bn == 256) launch_conv_pair2(I, L, ah, al, ohi, olo, n_dev, err, st);
@@ -776,15 +1082,30 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
       I->pair_clusters = std::min(nc, I->num_sms / 2);
     }
   }
-  if (const char* f8 = getenv("AZ_TC_FP8")) I->fp8 = f8[0] == '1' && I->pair_clusters > 0 && 2 * d.K >= 256;
+  // fused layers: hi*hi on kind::f16 + the two correction passes on kind::f8f6f4 (2 tensor passes per MAC instead of 3).
+  // Default = the halo kernel; AZ_TC_FP8=0: three fp16 passes (k_conv3x3_tc2), =1: per-tap FP8 kernel (A/B checks).
+  I->halo = d.W + 2;
+  I->hrows = (BM + 2 * I->halo + 15) & ~15;
+  const int fp8_best = (I->pair_clusters > 0 && 2 * d.K >= 256) ? (I->hrows <= F8H_MAX_HROWS ? 2 : 1) : 0;
+  I->fp8 = fp8_best;
+  if (const char* f8 = getenv("AZ_TC_FP8")) { const int v = atoi(f8); if (v >= 0 && v <= 2) I->fp8 = std::min(v, fp8_best); }
   if (I->fp8) {
-    I->pa = 2 - I->ea;  // an activation of 1.0 lands at 2^2 in e4m3 (representable up to 112, saturating above)
-    I->q = 10;          // weights' hi parts (max in [2^13, 2^14)) land at 2^3..2^4
+    I->pa = 0;   // h8 = e5m2(hi16): the fp16 operand's own scale and range
+    I->q = 11;   // l8 = e5m2(lo * 2^11): |lo| <= 2^-11 |hi|; filters' hi parts (max in [2^13, 2^14)) land at 2^2..2^3 in e4m3
     for (int i = 0; i < 2; i++) {
       CUDA_CHECK(cudaMalloc(&I->x_h8[i], (size_t)I->rows_alloc * d.K)); CUDA_CHECK(cudaMemset(I->x_h8[i], 0, (size_t)I->rows_alloc * d.K));
       CUDA_CHECK(cudaMalloc(&I->x_l8[i], (size_t)I->rows_alloc * d.K)); CUDA_CHECK(cudaMemset(I->x_l8[i], 0, (size_t)I->rows_alloc * d.K));
       if (I->mode3d) { I->mX_h8[i] = make_map3d_u8(I->x_h8[i], n_max, I->S, d.K); I->mX_l8[i] = make_map3d_u8(I->x_l8[i], n_max, I->S, d.K); }
       else { I->mX_h8[i] = make_map_u8(I->x_h8[i], I->rows_alloc, d.K, BM); I->mX_l8[i] = make_map_u8(I->x_l8[i], I->rows_alloc, d.K, BM); }
+      if (I->fp8 == 2) {
+        if (I->mode3d) {
+          I->mXh_hi[i] = make_map3d(I->x_hi[i], n_max, I->S, d.K, 64, I->hrows);
+          I->mXh_h8[i] = make_map3d_u8(I->x_h8[i], n_max, I->S, d.K, I->hrows); I->mXh_l8[i] = make_map3d_u8(I->x_l8[i], n_max, I->S, d.K, I->hrows);
+        } else {
+          I->mXh_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, I->hrows, 64);
+          I->mXh_h8[i] = make_map_u8(I->x_h8[i], I->rows_alloc, d.K, I->hrows); I->mXh_l8[i] = make_map_u8(I->x_l8[i], I->rows_alloc, d.K, I->hrows);
+        }
+      }
     }
   }
   // layers: init (single), then SharedLayers fused pairs
@@ -935,7 +1256,8 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   }
   for (size_t l = 1; l < I->layers.size(); l++) {
     size_t e0 = I->profile ? I->ev_get(st) : 0;
-    if (I->fp8 && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
+    if (I->fp8 == 2 && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8h(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
+    else if (I->fp8 && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
     else
     dispatch_conv(*I, I->layers[l], I->mX_hi[cur], I->mX_lo[cur], I->x_hi[cur ^ 1], I->x_lo[cur ^ 1], n_dev, err_flag, st);
     if (I->profile) I->conv_spans.push_back({e0, I->ev_get(st)});

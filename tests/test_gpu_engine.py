@@ -388,43 +388,64 @@ def test_learn_loop_go_on_tensor_cores(engine_lib):
         assert sum(l["a"]) == 6 and sum(l["b"]) == 6
 
 
-def test_tc_tower_full_depth_c3(oracle, engine_lib):
-    """The headline net (20 blocks x 256, 19x19, FC 512) end to end against the oracle: the fp16 hi/lo
-    3-pass tower must hold 1e-4 through all 41 conv layers."""
-    size, A1 = 19, 362
-    def desc(flags):
-        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4, flags=flags,
-                           nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=A1))
-    eo, etc = oracle.create(desc(0)), engine_lib.create(desc(0))
-    H.tame_gammas([eo, etc], 0, 99)
-    for e in (eo, etc):
-        e.set_inferer(0, K.INF_DUAL)
-    planes = _wq_planes(np.random.default_rng(8), 3, size)
-    po, vo = eo.infer(0, planes)
+_C3_ORACLE = {}
+
+
+def _c3_oracle_outputs(oracle, init, seed):
+    """Oracle forward of the headline net (20 blocks x 256, 19x19, FC 512) on three positions, cached per weight set."""
+    key = (init, seed)
+    if key not in _C3_ORACLE:
+        d = K.make_desc(K.GAME_WQ, 19, 19, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4,
+                        nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=362))
+        eo = oracle.create(d)
+        # "reference": BN scales with the spread the reference's own init has at DefaultConf's batch 256 (GlorotN over
+        # [B,C,H,W] = sigma sqrt(2/((256+256)*361)), x 316 in test mode = 1.0396 per layer): the distribution the bench
+        # nets have, without materialising 7.9 GB of batch-shaped parameters in the CPU oracle
+        params = H.tame_gammas([eo], 0, seed, target=0.9 if init == "tamed" else 1.0396)
+        eo.set_inferer(0, K.INF_DUAL)
+        planes = _wq_planes(np.random.default_rng(8), 3, 19)
+        po, vo = eo.infer(0, planes)
+        _C3_ORACLE[key] = (params, planes, po, vo)
+        eo.close()
+    return _C3_ORACLE[key]
+
+
+@pytest.mark.parametrize("init,seed", [("tamed", 99), ("tamed", 7), ("reference", 5), ("reference", 11)])
+@pytest.mark.parametrize("mode", ["halo-f8", "tap-f8", "fp16x3"])
+def test_tc_tower_full_depth_c3(oracle, engine_lib, monkeypatch, mode, init, seed):
+    """The headline net (20 blocks x 256, 19x19, FC 512) end to end against the oracle, 1e-4 on policy and value through
+    all 41 conv layers, for the three numeric schemes of the fused layers: the product (hi*hi on kind::f16 + E5M2 x E4M3
+    correction passes on kind::f8f6f4, halo kernel), the same arithmetic in the per-tap kernel, and three fp16 passes —
+    on four weight sets, two of them the reference's own untamed init (heavy-tailed activations)."""
+    monkeypatch.setenv("AZ_TC_FP8", {"halo-f8": "2", "tap-f8": "1", "fp16x3": "0"}[mode])
+    params, planes, po, vo = _c3_oracle_outputs(oracle, init, seed)
+    d = K.make_desc(K.GAME_WQ, 19, 19, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4,
+                    nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=362))
+    etc = engine_lib.create(d)
+    etc.net_set(0, params)
+    etc.set_inferer(0, K.INF_DUAL)
     ptc, vtc = etc.infer(0, planes)
-    print("C3 depth: dp=%.3g dv=%.3g pmax=%.3g |v|max=%.3g" % (np.abs(ptc - po).max(), np.abs(vtc - vo).max(), po.max(), np.abs(vo).max()))
-    assert np.isfinite(po).all() and np.abs(vo).max() < 0.9999
+    etc.close()
+    print("C3 depth %s %s/%d: dp=%.3g dv=%.3g pmax=%.3g |v|max=%.3g" % (mode, init, seed, np.abs(ptc - po).max(), np.abs(vtc - vo).max(), po.max(), np.abs(vo).max()))
+    assert np.isfinite(po).all() and np.isfinite(vo).all()
     assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
 
 
-@pytest.mark.skipif(__import__("os").environ.get("AZ_RUN_EXPERIMENTS") != "1",
-                    reason="unvalidated experiment kernels only run on request (AZ_RUN_EXPERIMENTS=1)")
-def test_fp8_correction_passes_experiment(oracle, engine_lib, monkeypatch):
-    """AZ_TC_FP8=1: the fused layers with E4M3 correction passes, full C3 depth, against the oracle at
-    the north star's 1e-4 — the gate this variant has to pass before it can replace the 3 x fp16 kernel."""
-    monkeypatch.setenv("AZ_TC_FP8", "1")
-    size, A1 = 19, 362
+@pytest.mark.parametrize("mode", ["2", "0"])
+def test_tc_tower_modes_small_nets(oracle, engine_lib, monkeypatch, mode):
+    """9x9, K = 128 (2C = 256: the CTA-pair kernels in the flat 2-D layout): FP8-correction halo kernel and the three-pass
+    kernel against the oracle."""
+    monkeypatch.setenv("AZ_TC_FP8", mode)
     def desc():
-        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4,
-                           nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=A1))
+        return K.make_desc(K.GAME_WQ, 9, 9, 0, komi=7.5, sims=2, n_games=8, seed=2, max_moves=4,
+                           nn=dict(k=128, shared_layers=4, fc=64, batch_size=2, features=18, action_space=82))
     eo, etc = oracle.create(desc()), engine_lib.create(desc())
-    H.tame_gammas([eo, etc], 0, 99)
+    H.tame_gammas([eo, etc], 0, 13)
     for e in (eo, etc):
         e.set_inferer(0, K.INF_DUAL)
-    planes = _wq_planes(np.random.default_rng(8), 3, size)
-    po, vo = eo.infer(0, planes)
-    ptc, vtc = etc.infer(0, planes)
-    print("fp8 corrections: dp=%.3g dv=%.3g" % (np.abs(ptc - po).max(), np.abs(vtc - vo).max()))
+    planes = _wq_planes(np.random.default_rng(6), 11, 9)
+    (po, vo), (ptc, vtc) = eo.infer(0, planes), etc.infer(0, planes)
+    print("9x9 K=128 mode %s: dp=%.3g dv=%.3g" % (mode, np.abs(ptc - po).max(), np.abs(vtc - vo).max()))
     assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
 
 

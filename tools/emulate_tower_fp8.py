@@ -29,6 +29,14 @@ def e4m3(x):
     return (sign * np.minimum(np.round(a / qn) * qn, 448.0)).astype(np.float32)
 
 
+def e5m2(x):
+    x = x.astype(np.float64)
+    sign, a = np.sign(x), np.abs(x)
+    e = np.clip(np.floor(np.log2(np.where(a > 0, a, 1.0))), -14, 15)
+    qn = 2.0 ** (e - 2)
+    return (sign * np.minimum(np.round(a / qn) * qn, 57344.0)).astype(np.float32)
+
+
 def f16(x):
     return x.astype(np.float16).astype(np.float32)
 
@@ -45,7 +53,7 @@ def conv_emulated(x, w, mode):
     N = x.shape[0]
     mx = np.abs(w).max()
     e2 = int(np.floor(np.log2(mx))) + 1                      # frexp exponent: mx = m * 2^e2, m in [0.5, 1)
-    ew = (14 if mode == "fp8" else 7) - e2
+    ew = (14 if mode.startswith("fp8") else 7) - e2
     xs = (x * np.float32(2.0 ** EA)).astype(np.float32)      # x16 units
     xh = f16(xs); xl = f16(xs - xh)
     ws = (w * np.float32(2.0 ** ew)).astype(np.float32)
@@ -57,6 +65,10 @@ def conv_emulated(x, w, mode):
         acc = acc + A_h @ Bm(wl) + A_l @ Bm(wh)
     elif mode == "fp16x2":  # calibration: the two-pass tower measured 6.5e-5 worst-case |dvalue| on hardware
         acc = acc + A_h @ Bm(wl)
+    elif mode == "fp8e5":  # activations as E5M2 at the fp16 operand's own scale (range-safe), weights E4M3
+        xh8 = e5m2(xh); wl8 = e4m3(wl_exact)
+        xl8 = e5m2((xs - xh) * np.float32(2.0 ** 11)); wh8 = e4m3(wh * np.float32(2.0 ** -11))
+        acc = acc + im2col(xh8) @ Bm(wl8) + im2col(xl8) @ Bm(wh8)
     else:
         xh8 = e4m3(xh * np.float32(2.0 ** PA)); wl8 = e4m3(wl_exact * np.float32(2.0 ** -PA))
         xl8 = e4m3((xs - xh) * np.float32(2.0 ** QW)); wh8 = e4m3(wh * np.float32(2.0 ** -QW))
@@ -99,7 +111,7 @@ net = D.Net(D.unpack(e, 0), blocks)
 rng = np.random.default_rng(8)
 X = (rng.random((NB, 18, size, size)) < 0.25).astype(np.float64) * rng.choice([1.0, -1.0], (NB, 18, size, size))
 p_ref, v_ref = net.infer(X)
-for mode in ("fp16x3", "fp16x2", "fp8"):
+for mode in ("fp16x3", "fp16x2", "fp8", "fp8e5"):
     cur = tower(net, X.astype(np.float32), mode)
     p, v = heads(net, cur.astype(np.float64))
     print("%-7s blocks %d: max|dpolicy| %.3e  max|dvalue| %.3e   (tolerance 1e-4)" % (mode, blocks, np.abs(p - p_ref).max(), np.abs(v - v_ref).max()), flush=True)
