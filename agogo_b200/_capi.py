@@ -16,7 +16,7 @@ PASS, RESIGN = -1, -2
 GAME_MNK, GAME_C4, GAME_WQ = 0, 1, 2
 ENC_TWO_PLANE, ENC_WQ18 = 0, 1
 INF_DUAL, INF_DUMMY, INF_TABLE = 0, 1, 2
-FLAG_SHARED_TREE, FLAG_FP32_TOWER = 1, 2
+FLAG_SHARED_TREE, FLAG_FP32_TOWER, FLAG_FAST_TOWER = 1, 2, 4
 DONT_PREFER_PASS, PREFER_PASS, DONT_RESIGN = 0, 1, 2
 
 
@@ -330,7 +330,8 @@ class Engine:
     def profile(self, enable):
         out = (C.c_double * 8)()
         self._ck(self.lib.dll.az_profile(self.h, int(enable), out))
-        return dict(conv_ms=out[0], conv_launches=out[1], forward_ms=out[2], forward_calls=out[3], region_ms=out[4])
+        return dict(conv_ms=out[0], conv_launches=out[1], forward_ms=out[2], forward_calls=out[3], region_ms=out[4],
+                    kernel_kind=int(out[5]))
 
     def comm_bench(self, net=1, iters=10):
         ms, nbytes = C.c_double(), C.c_double()

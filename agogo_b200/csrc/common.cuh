@@ -21,6 +21,7 @@ enum {
   ERR_NAN_PRIOR = 16,        // NaN prior reached the sort (Go's sort order is unspecified there)
   ERR_PATH_OVERFLOW = 32,
   ERR_RESIGN_APPLIED = 64,   // Arena applies Resign: every game.State.Apply indexes board[-2] and panics
+  ERR_COMM_TIMEOUT = 128,    // K8: a peer never published its epoch flag (rank died / different batch count / not called collectively)
 };
 
 // Game + search parameters, passed by value to every kernel.

@@ -21,7 +21,7 @@
 // kernels (mcts.cu)
 size_t mcts_ws_bytes(const GameP& P, int cellsP);
 void mcts_set_smem_limits(const GameP& P, int cellsP);
-void launch_arena_begin(const GameP& P, const EngineDev& E, int n_games, const int* coins, cudaStream_t s);
+void launch_arena_begin(const GameP& P, const EngineDev& E, int n_games, const int* coins, unsigned long long game_base, cudaStream_t s);
 void launch_assign_slots(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s);
 void launch_search_begin(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s);
 void launch_encode_roots(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s);
@@ -69,6 +69,7 @@ struct az_engine {
   float* table_val_dev[2] = {nullptr, nullptr};
   int* coins_dev = nullptr;
   uint64_t coin_state = 0;
+  uint64_t games_started = 0;  // per-tree RNG streams: tree t of the c-th game = stream 2c + t of the tree seed
   // play state
   bool in_play = false, record = false;
   int n_play = 0;
@@ -103,6 +104,7 @@ struct az_engine {
   int* my_flags = nullptr;
   unsigned int* done_counter = nullptr;
   int epoch = 0, num_sms = 148;
+  int32_t* d_agree = nullptr;  // step-count agreement of the data-parallel ranks (az_train)
   mutable std::string err;
 
   template <class T>
@@ -153,6 +155,13 @@ static void nccl_allreduce_sum(az_engine* e, float* buf, size_t n) {
   }                                                                    \
   catch (const CudaError& ce) { (e)->err = ce.msg; return AZ_ERR_CUDA; } \
   catch (const std::exception& ex) { (e)->err = ex.what(); return AZ_ERR_PANIC; }
+// entry points that run inside an arena / search: any failure also leaves the "in play" state, so that the next call
+// reports its own error instead of "during a running arena"
+#define PLAY_ABORT(e) do { (e)->in_play = false; (e)->ex_by_game.clear(); } while (0)
+#define GUARD_END_PLAY(e)                                                                  \
+  }                                                                                        \
+  catch (const CudaError& ce) { (e)->err = ce.msg; PLAY_ABORT(e); return AZ_ERR_CUDA; }     \
+  catch (const std::exception& ex) { (e)->err = ex.what(); PLAY_ABORT(e); return AZ_ERR_PANIC; }
 
 static int device_error_to_rc(az_engine* e, int bits) {
   if (!bits) return AZ_OK;
@@ -164,6 +173,7 @@ static int device_error_to_rc(az_engine* e, int bits) {
   if (bits & ERR_NAN_PRIOR) m += " NaN prior";
   if (bits & ERR_PATH_OVERFLOW) m += " per-game move capacity exceeded (set game.max_moves)";
   if (bits & ERR_RESIGN_APPLIED) m += " index out of range (Arena applied Resign: State.Apply indexes board[-2])";
+  if (bits & ERR_COMM_TIMEOUT) m += " gradient all-reduce: a peer rank never arrived (rank died, different batch count, or the call was not collective)";
   e->err = m;
   return AZ_ERR_PANIC;
 }
@@ -177,6 +187,16 @@ void az_engine_destroy(az_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
+  if (e->comm && e->p2p) {  // peers have this rank's gradient / parameter / flag buffers IPC-mapped: nobody frees before everybody is done
+    try {
+      if (!e->d_agree) e->d_agree = e->dalloc<int32_t>(2);
+      int32_t* d1 = e->d_agree;
+      nccl_api().AllReduce(d1, d1, 1, ncclInt32, ncclSum, (ncclComm_t)e->comm, e->stream);
+      cudaStreamSynchronize(e->stream);
+    } catch (...) {}
+  }
+  for (void* p : e->ipc_opened) cudaIpcCloseMemHandle(p);
+  e->ipc_opened.clear();
   for (void* p : e->allocs) cudaFree(p);
   for (int a = 0; a < 2; a++) { tc_tower_free(e->tc[a]); }
   train_ws_free(e->train);
@@ -209,6 +229,10 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
   if (desc->encoder == AZ_ENC_WQ18 && gd.kind != AZ_GAME_WQ) { g_create_error = "WQEncoder needs State.Historical, which only wq provides on clones"; return AZ_ERR_UNSUPPORTED; }
   if (m.random_count > 0 && !(m.random_temperature > 0)) { g_create_error = "RandomCount > 0 needs RandomTemperature > 0"; return AZ_ERR_INVALID; }
   if (n.width != gd.n || n.height != gd.m) { g_create_error = "nn width/height must match the board"; return AZ_ERR_INVALID; }
+  {  // expandAndSimulate reads policy[i] for i < ActionSpace and policy[len-1] (search.go:285-296): a narrower net panics
+    const int A = gd.kind == AZ_GAME_C4 ? gd.n : gd.m * gd.n;
+    if (n.action_space < A) { g_create_error = "index out of range: dual.Config.ActionSpace is smaller than the game's ActionSpace()"; return AZ_ERR_INVALID; }
+  }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev <= desc->device) {
@@ -304,7 +328,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     fp32_scratch_alloc(e->fp32, nd, E.GS);
     e->use_tc = !(desc->flags & AZ_FLAG_FP32_TOWER) && tc_tower_supported(nd);
     if (e->use_tc)
-      for (int a = 0; a < 2; a++) tc_tower_alloc(e->tc[a], nd, E.GS, desc->act_scale_log2 ? desc->act_scale_log2 : -2);
+      for (int a = 0; a < 2; a++) tc_tower_alloc(e->tc[a], nd, E.GS, desc->act_scale_log2 ? desc->act_scale_log2 : -2, (desc->flags & AZ_FLAG_FAST_TOWER) != 0);
 
     CUDA_CHECK(cudaMallocHost(&e->h_ex_board, (size_t)G * P.plane * 4));
     CUDA_CHECK(cudaMallocHost(&e->h_ex_policy, (size_t)G * (P.A + 1) * 4));
@@ -406,8 +430,12 @@ int az_agent_set_table(az_engine* e, int32_t agent, int32_t n_rows, int32_t row_
   if (row_len > e->E.Lmax || row_len < e->P.A) { e->err = "table row length must be in [ActionSpace, ActionSpace+1]"; return AZ_ERR_INVALID; }
   GUARD_BEGIN
   CUDA_CHECK(cudaSetDevice(e->device));
+  // a table replaces the agent's previous one: free that first (dalloc keeps every allocation until destroy)
+  for (float* old : {e->table_dev[agent], e->table_val_dev[agent]})
+    if (old) { auto it = std::find(e->allocs.begin(), e->allocs.end(), (void*)old); if (it != e->allocs.end()) e->allocs.erase(it); CUDA_CHECK(cudaStreamSynchronize(e->stream)); cudaFree(old); }
   float* t = e->dalloc<float>((size_t)n_rows * row_len);
   float* v = e->dalloc<float>(n_rows);
+  e->table_dev[agent] = t; e->table_val_dev[agent] = v;
   CUDA_CHECK(cudaMemcpy(t, policy_rows, (size_t)n_rows * row_len * 4, cudaMemcpyHostToDevice));
   CUDA_CHECK(cudaMemcpy(v, values, (size_t)n_rows * 4, cudaMemcpyHostToDevice));
   InfererDev& I = e->E.inf[agent];
@@ -487,7 +515,8 @@ int az_arena_begin(az_engine* e, int32_t n_games, int32_t record) {
   std::vector<int> coins(n_games);
   for (int g = 0; g < n_games; g++) coins[g] = (int)(splitmix64(&e->coin_state) % 2);  // arena.go:81 a.r.Intn(2)
   CUDA_CHECK(cudaMemcpyAsync(e->coins_dev, coins.data(), (size_t)n_games * 4, cudaMemcpyHostToDevice, e->stream));
-  launch_arena_begin(e->P, e->E, n_games, e->coins_dev, e->stream); e->launches++;
+  launch_arena_begin(e->P, e->E, n_games, e->coins_dev, e->games_started, e->stream); e->launches++;
+  e->games_started += (uint64_t)n_games;
   launch_assign_slots(e->P, e->E, n_games, e->stream); e->launches++;
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   e->in_play = true; e->record = record != 0; e->n_play = n_games;
@@ -512,7 +541,7 @@ int az_search_begin(az_engine* e) {
   launch_search_begin(e->P, e->E, e->n_play, e->stream); e->launches++;
   launch_encode_roots(e->P, e->E, e->n_play, e->stream); e->launches++;
   eval_pending(e);
-  GUARD_END(e)
+  GUARD_END_PLAY(e)
   return AZ_OK;
 }
 // n pipeline iterations = ceil(n / workers) rounds; the device reads how many workers the round starts
@@ -550,7 +579,7 @@ int az_search_run(az_engine* e, int32_t n) {
   } else {
     for (int left = n; left > 0; left -= e->E.V) { set_round_workers(e, std::min(left, e->E.V)); run_wave(e); }
   }
-  GUARD_END(e)
+  GUARD_END_PLAY(e)
   return AZ_OK;
 }
 int az_search_end(az_engine* e) {
@@ -569,7 +598,7 @@ int az_search_end(az_engine* e) {
     CUDA_CHECK(cudaMemcpyAsync(e->h_ex_board, E.ex_board, (size_t)n * P.plane * 4, cudaMemcpyDeviceToHost, e->stream));
   }
   int rc = sync_small(e, nullptr);
-  if (rc) return rc;
+  if (rc) { PLAY_ABORT(e); return rc; }
   if (e->record) {
     for (int g = 0; g < n; g++) {
       if (!e->h_ex_valid[g]) continue;
@@ -580,7 +609,7 @@ int az_search_end(az_engine* e) {
       e->ex_by_game[g].push_back(std::move(ex));
     }
   }
-  GUARD_END(e)
+  GUARD_END_PLAY(e)
   return AZ_OK;
 }
 int az_arena_step(az_engine* e, int32_t* n_active) {
@@ -629,7 +658,7 @@ int az_arena_finish(az_engine* e) {
   }
   e->ex_by_game.clear();
   e->in_play = false;
-  GUARD_END(e)
+  GUARD_END_PLAY(e)
   return AZ_OK;
 }
 int az_arena_play(az_engine* e, int32_t n_games, int32_t record) {
@@ -651,7 +680,7 @@ int az_arena_play(az_engine* e, int32_t n_games, int32_t record) {
 }
 
 int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, int32_t* best, float* child_visits) {
-  if (agent < 0 || agent > 1 || !st || !st->board || st->n_hist < 0 || st->n_hist > 8) return AZ_ERR_INVALID;
+  if (agent < 0 || agent > 1 || !st || !st->board || st->n_hist < 0 || st->n_hist > 8 || (st->n_hist > 0 && !st->hist)) return AZ_ERR_INVALID;
   if (e->in_play) { e->err = "az_search during a running arena"; return AZ_ERR_STATE; }
   if (e->E.inf[agent].kind < 0) { e->err = "agent has no inferer"; return AZ_ERR_STATE; }
   GUARD_BEGIN
@@ -661,7 +690,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   // fresh slot 0 (board, scalars, trees), then overwrite it with the caller's position
   int coin = 0;
   CUDA_CHECK(cudaMemcpyAsync(e->coins_dev, &coin, 4, cudaMemcpyHostToDevice, e->stream));
-  launch_arena_begin(P, E, 1, e->coins_dev, e->stream); e->launches++;
+  launch_arena_begin(P, E, 1, e->coins_dev, 0ull, e->stream); e->launches++;  // external position: streams 0 / 1 of the tree seed
   std::vector<uint8_t> b(E.cellsP, 0);
   for (int i = 0; i < P.cells; i++) b[i] = (uint8_t)st->board[i];
   std::vector<uint8_t> ring(P.hist_len ? (size_t)8 * E.cellsP : 1, 0);
@@ -727,7 +756,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   e->in_play = false;
   e->ex_by_game.clear();
   if (rc) return rc;
-  GUARD_END(e)
+  GUARD_END_PLAY(e)
   return AZ_OK;
 }
 
@@ -912,7 +941,7 @@ static void train_one(az_engine* e, int net, float lr) {
   train_step_grads(e->train, e->L, e->net_params[net], e->stream, &e->launches);
   if (e->p2p) {  // K8: reduce-scatter + SGD + all-gather in one kernel over NVLink peer memory
     train_allreduce_sgd_p2p(e->d_peer_grads, e->d_peer_params[net], e->d_peer_flags, e->my_flags, e->rank, e->world, e->L.total,
-                            lr, ++e->epoch, e->done_counter, e->num_sms, e->stream, &e->launches);
+                            lr, ++e->epoch, e->done_counter, e->num_sms, e->E.err, e->stream, &e->launches);
     return;
   }
   float gscale = 1.0f;
@@ -937,6 +966,19 @@ int az_train(az_engine* e, int32_t net, float* Xs, float* Pi, float* V, int32_t 
   train_ws_inputs(e->train, &dX, &dPi, &dV);
   std::vector<float> costs((size_t)batches * iterations);
   uint64_t rs = shuffle_seed;
+  if (e->comm && e->world > 1) {  // every rank must run the same number of collective steps: agree before the first one
+    if (!e->d_agree) e->d_agree = e->dalloc<int32_t>(2);
+    int32_t* d2 = e->d_agree;
+    const int32_t mine[2] = {batches * iterations, -(batches * iterations)};
+    CUDA_CHECK(cudaMemcpyAsync(d2, mine, 8, cudaMemcpyHostToDevice, e->stream));
+    NcclApi& na = nccl_api();
+    ncclResult_t r = na.AllReduce(d2, d2, 2, ncclInt32, ncclMax, (ncclComm_t)e->comm, e->stream);
+    if (r != ncclSuccess) throw std::runtime_error(std::string("ncclAllReduce(step count): ") + na.GetErrorString(r));
+    int32_t got[2];
+    CUDA_CHECK(cudaMemcpyAsync(got, d2, 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (got[0] != mine[0] || got[1] != mine[1]) throw std::runtime_error("az_train: ranks disagree on batches x iterations (data-parallel steps are collective)");
+  }
   for (int it = 0; it < iterations; it++) {
     for (int bat = 0; bat < batches; bat++) {
       const size_t s0 = (size_t)bat * d.B;
@@ -946,6 +988,11 @@ int az_train(az_engine* e, int32_t net, float* Xs, float* Pi, float* V, int32_t 
       train_one(e, net, lr);
       CUDA_CHECK(cudaMemcpyAsync(&costs[(size_t)it * batches + bat], train_ws_cost(e->train), 4, cudaMemcpyDeviceToHost, e->stream));
       CUDA_CHECK(cudaStreamSynchronize(e->stream));  // pageable staging buffers are reused next batch
+      if (e->p2p) {
+        int bits = 0;
+        CUDA_CHECK(cudaMemcpy(&bits, e->E.err, 4, cudaMemcpyDeviceToHost));
+        if (bits) { CUDA_CHECK(cudaMemset(e->E.err, 0, 4)); CUDA_CHECK(cudaMemset(e->done_counter, 0, 4)); return device_error_to_rc(e, bits); }
+      }
     }
     shuffle_rows(x, p, v, rows, &rs);
   }
@@ -1058,7 +1105,7 @@ int az_comm_bench(az_engine* e, int32_t net, int32_t iters, double* ms_out, doub
   CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
   auto step = [&]() {
     if (e->p2p) train_allreduce_sgd_p2p(e->d_peer_grads, e->d_peer_params[net], e->d_peer_flags, e->my_flags, e->rank, e->world,
-                                        e->L.total, 0.0f, ++e->epoch, e->done_counter, e->num_sms, e->stream, &e->launches);
+                                        e->L.total, 0.0f, ++e->epoch, e->done_counter, e->num_sms, e->E.err, e->stream, &e->launches);
     else { nccl_allreduce_sum(e, train_ws_grads(e->train), e->L.total); train_sgd(e->train, e->L, e->net_params[net], 0.0f, 1.0f, e->stream, &e->launches); }
   };
   for (int i = 0; i < 2; i++) step();  // warm-up
@@ -1071,6 +1118,11 @@ int az_comm_bench(az_engine* e, int32_t net, int32_t iters, double* ms_out, doub
   cudaEventDestroy(a); cudaEventDestroy(b);
   if (ms_out) *ms_out = ms / iters;
   if (bytes_out) *bytes_out = 2.0 * (e->world - 1) / e->world * (double)e->L.total * 4.0;
+  if (e->p2p) {
+    int bits = 0;
+    CUDA_CHECK(cudaMemcpy(&bits, e->E.err, 4, cudaMemcpyDeviceToHost));
+    if (bits) { CUDA_CHECK(cudaMemset(e->E.err, 0, 4)); CUDA_CHECK(cudaMemset(e->done_counter, 0, 4)); return device_error_to_rc(e, bits); }
+  }
   GUARD_END(e)
   return AZ_OK;
 }
@@ -1082,6 +1134,7 @@ int az_profile(az_engine* e, int32_t enable, double out[8]) {
   if (out) {
     for (int i = 0; i < 8; i++) out[i] = 0;
     if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile_collect(e->tc[a], e->stream, &out[0], &out[1], &out[2], &out[3]);
+    out[5] = e->use_tc ? (double)tc_tower_kernel_kind(e->tc[0]) : -1.0;  // which kernel runs the fused layers
     if (e->profiling && !enable) {  // whole region on the engine's stream, device-timed
       CUDA_CHECK(cudaEventRecord(e->prof_stop, e->stream));
       CUDA_CHECK(cudaEventSynchronize(e->prof_stop));

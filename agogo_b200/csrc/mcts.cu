@@ -173,7 +173,19 @@ __device__ inline int alloc_nodes(const EngineDev& E, const GameP& P, int* ti, i
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __restrict__ coins) {
+__device__ inline unsigned long long dev_splitmix64(unsigned long long* s) {
+  unsigned long long z = (*s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ inline unsigned long long dev_derive_seed(unsigned long long seed, unsigned long long stream) {
+  unsigned long long s = seed ^ (0xD1B54A32D192ED03ull * (stream + 1));
+  return dev_splitmix64(&s);
+}
+// game_base: games this engine started before this call — tree t of the c-th game draws from stream 2c + t of the
+// engine's tree seed (the reference seeds every MCTS.rand from the clock, tree.go:84: all trees differ)
+__global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __restrict__ coins, unsigned long long game_base) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -184,8 +196,9 @@ __global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __re
   if (P.hist_len) for (int i = lane; i < 8 * E.cellsP; i += 32) E.hist[(size_t)g * 8 * E.cellsP + i] = 0;
   for (int t = 0; t < E.T; t++) {
     int* ti = E.ti + ((size_t)g * E.T + t) * TI_COUNT;
+    const unsigned long long ts = dev_derive_seed(E.tree_seed, 2ull * (game_base + (unsigned long long)g) + (unsigned long long)t);
     if (lane < TI_COUNT)
-      ti[lane] = lane == TI_ROOT ? -1 : (lane == TI_RNG_LO ? (int)(unsigned)(E.tree_seed & 0xffffffffu) : (lane == TI_RNG_HI ? (int)(unsigned)(E.tree_seed >> 32) : 0));
+      ti[lane] = lane == TI_ROOT ? -1 : (lane == TI_RNG_LO ? (int)(unsigned)(ts & 0xffffffffu) : (lane == TI_RNG_HI ? (int)(unsigned)(ts >> 32) : 0));
   }
   for (int i = lane; i < E.V * WV_COUNT; i += 32) WV_OF(E, g, 0)[i] = 0;
   __syncwarp();
@@ -884,15 +897,17 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   const int n_moves = gi[GI_N_MOVES];
   int winner = gi[GI_WINNER];
   bool active = true;
-  if (n_moves + 1 >= P.max_plies) active = false;  // record capacity (engine limit)
   if (arena_pass >= 2) active = false;             // arena.go:135-137
   else if (P.max_moves > 0 && n_moves + 1 >= P.max_moves) active = false;  // COMPLETION: move cap
-  else if (active) {
+  else {
     int wn;
     bool ended = game_ended(P, w.board, P.kind == KIND_C4 ? c4pass : s.passes, lane, &wn);
     winner = wn;
     active = !ended;
   }
+  // the per-game move list is full but the reference would keep playing (no move cap set): an engine limit, reported —
+  // silently ending the game here would count it as a draw and label its examples 0
+  if (active && n_moves + 1 >= P.max_plies) { raise(E, ERR_PATH_OVERFLOW, lane); active = false; }
   if (lane == 0) {
     E.moves[(size_t)g * P.max_plies + n_moves] = (int16_t)best;
     gi[GI_N_MOVES] = n_moves + 1;
@@ -981,8 +996,8 @@ void mcts_set_smem_limits(const GameP& P, int cellsP) {
   CUDA_CHECK(cudaFuncSetAttribute(k_rules_status, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
 }
 #define SMEM(P, E) (ws_bytes(P, (E).cellsP) * WPB)
-void launch_arena_begin(const GameP& P, const EngineDev& E, int n_games, const int* coins, cudaStream_t s) {
-  k_arena_begin<<<grid_for(E.G, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games, coins); LAUNCH_CHECK();
+void launch_arena_begin(const GameP& P, const EngineDev& E, int n_games, const int* coins, unsigned long long game_base, cudaStream_t s) {
+  k_arena_begin<<<grid_for(E.G, WPB), WPB * 32, SMEM(P, E), s>>>(P, E, n_games, coins, game_base); LAUNCH_CHECK();
 }
 void launch_assign_slots(const GameP& P, const EngineDev& E, int n_games, cudaStream_t s) {
   k_assign_slots<<<1, 32, 0, s>>>(E, n_games, P.shared_tree); LAUNCH_CHECK();

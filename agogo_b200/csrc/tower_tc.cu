@@ -561,11 +561,15 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
+// F8 = true: hi*hi (kind::f16) + two FP8 correction passes.  F8 = false: the fp32-faithful three fp16 passes
+// (hi*hi + hi*lo + lo*hi) on the same halo pipeline — the stages then hold hi16 | lo16 of the activations
+// (tmAh8 = the lo16 halo map, tmAl8 unused) and hi16 | lo16 of the filters (tmBh8 = the lo16 map, tmBl8 unused).
+template <bool F8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
-k_conv3x3_tc2_f8h(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmAh8,
-                  const __grid_constant__ CUtensorMap tmAl8, const __grid_constant__ CUtensorMap tmB16,
-                  const __grid_constant__ CUtensorMap tmBh8, const __grid_constant__ CUtensorMap tmBl8,
-                  const __grid_constant__ CUtensorMap tmAff, ConvArgsF8H af) {
+k_conv3x3_tc2_halo(const __grid_constant__ CUtensorMap tmA16, const __grid_constant__ CUtensorMap tmAh8,
+                   const __grid_constant__ CUtensorMap tmAl8, const __grid_constant__ CUtensorMap tmB16,
+                   const __grid_constant__ CUtensorMap tmBh8, const __grid_constant__ CUtensorMap tmBl8,
+                   const __grid_constant__ CUtensorMap tmAff, ConvArgsF8H af) {
   const ConvArgs& a = af.c;
   constexpr int BK = 64, BN = 256, OUTC = 128;
   constexpr int T16 = BM * BK * 2, T8 = BM * BK;  // filter tiles: 16 KB / 8 KB (128 rows each)
@@ -631,12 +635,12 @@ k_conv3x3_tc2_f8h(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
           const int b = mt / a.tps, p0 = (mt - b * a.tps) * BM - af.halo;  // <0 / >=S / b>=n: TMA zero fill
           tma2_load_3d(sa, &tmA16, lbar, kc * BK, p0, b);
           tma2_load_3d(sa + A16_BYTES, &tmAh8, lbar, kc * BK, p0, b);
-          tma2_load_3d(sa + A16_BYTES + A8_BYTES, &tmAl8, lbar, kc * BK, p0, b);
+          if (F8) tma2_load_3d(sa + A16_BYTES + A8_BYTES, &tmAl8, lbar, kc * BK, p0, b);
         } else {
           const int arow = a.guard + mt * BM - af.halo;
           tma2_load_2d(sa, &tmA16, lbar, kc * BK, arow);
           tma2_load_2d(sa + A16_BYTES, &tmAh8, lbar, kc * BK, arow);
-          tma2_load_2d(sa + A16_BYTES + A8_BYTES, &tmAl8, lbar, kc * BK, arow);
+          if (F8) tma2_load_2d(sa + A16_BYTES + A8_BYTES, &tmAl8, lbar, kc * BK, arow);
         }
       };
       for (uint32_t t = 0; t < total_w; t++) {
@@ -662,7 +666,7 @@ k_conv3x3_tc2_f8h(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
         const int kcol = tap * a.cin + kc * BK;
         tma2_load_2d(sb, &tmB16, lbar, kcol, n0);
         tma2_load_2d(sb + T16, &tmBh8, lbar, kcol, n0);
-        tma2_load_2d(sb + T16 + T8, &tmBl8, lbar, kcol, n0);
+        if (F8) tma2_load_2d(sb + T16 + T8, &tmBl8, lbar, kcol, n0);
       }
     }
   } else if (warp == 1) {
@@ -689,16 +693,28 @@ k_conv3x3_tc2_f8h(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
             const uint32_t j0 = (uint32_t)(af.halo + dy * a.Wp + dx);  // first row of this tap's view of the halo tile
             const uint32_t sb = w_smem + s * BST_BYTES;
             const uint64_t dA16 = make_desc_sw<64>(sa + j0 * 128u);
-            const uint64_t dAh8 = make_desc_sw<32>(sa + A16_BYTES + j0 * 64u);
-            const uint64_t dAl8 = make_desc_sw<32>(sa + A16_BYTES + A8_BYTES + j0 * 64u);
-            const uint64_t dB16 = make_desc_sw<64>(sb), dBh8 = make_desc_sw<32>(sb + T16), dBl8 = make_desc_sw<32>(sb + T16 + T8);
+            const uint64_t dB16 = make_desc_sw<64>(sb);
+            if (F8) {
+              const uint64_t dAh8 = make_desc_sw<32>(sa + A16_BYTES + j0 * 64u);
+              const uint64_t dAl8 = make_desc_sw<32>(sa + A16_BYTES + A8_BYTES + j0 * 64u);
+              const uint64_t dBh8 = make_desc_sw<32>(sb + T16), dBl8 = make_desc_sw<32>(sb + T16 + T8);
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)  // 16 fp16 = 32 B per step
-              umma2_f16(d_tmem, dA16 + (uint64_t)(ks * 2), dB16 + (uint64_t)(ks * 2), idesc16, (kc | tap | ks) ? 1u : 0u);
+              for (int ks = 0; ks < 4; ks++)  // 16 fp16 = 32 B per step
+                umma2_f16(d_tmem, dA16 + (uint64_t)(ks * 2), dB16 + (uint64_t)(ks * 2), idesc16, (kc | tap | ks) ? 1u : 0u);
 #pragma unroll
-            for (int ks = 0; ks < 2; ks++) {  // 32 fp8 = 32 B per step
-              umma2_f8(d_tmem, dAh8 + (uint64_t)(ks * 2), dBl8 + (uint64_t)(ks * 2), idesc8, 1u);
-              umma2_f8(d_tmem, dAl8 + (uint64_t)(ks * 2), dBh8 + (uint64_t)(ks * 2), idesc8, 1u);
+              for (int ks = 0; ks < 2; ks++) {  // 32 fp8 = 32 B per step
+                umma2_f8(d_tmem, dAh8 + (uint64_t)(ks * 2), dBl8 + (uint64_t)(ks * 2), idesc8, 1u);
+                umma2_f8(d_tmem, dAl8 + (uint64_t)(ks * 2), dBh8 + (uint64_t)(ks * 2), idesc8, 1u);
+              }
+            } else {
+              const uint64_t dAlo = make_desc_sw<64>(sa + A16_BYTES + j0 * 128u), dBlo = make_desc_sw<64>(sb + T16);
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                umma2_f16(d_tmem, dA16 + adv, dB16 + adv, idesc16, (kc | tap | ks) ? 1u : 0u);
+                umma2_f16(d_tmem, dA16 + adv, dBlo + adv, idesc16, 1u);
+                umma2_f16(d_tmem, dAlo + adv, dB16 + adv, idesc16, 1u);
+              }
             }
             umma2_commit_mc(wempty_bar(s));
           }
@@ -779,14 +795,18 @@ k_conv3x3_tc2_f8h(const __grid_constant__ CUtensorMap tmA16, const __grid_consta
             const float res = v - hf;
             hi[k] = h;
             lo[k] = __float2half_rn(res);
-            h8[k] = to_e5m2(hf);
-            l8[k] = to_e5m2(res * af.scale_l8);
+            if (F8) {
+              h8[k] = to_e5m2(hf);
+              l8[k] = to_e5m2(res * af.scale_l8);
+            }
           }
           if (valid) {
             *(uint4*)(a.out_hi + orow + c0 + sub * 8) = *(const uint4*)hi;
             *(uint4*)(a.out_lo + orow + c0 + sub * 8) = *(const uint4*)lo;
-            *(uint2*)(af.out_h8 + orow + c0 + sub * 8) = *(const uint2*)h8;
-            *(uint2*)(af.out_l8 + orow + c0 + sub * 8) = *(const uint2*)l8;
+            if (F8) {
+              *(uint2*)(af.out_h8 + orow + c0 + sub * 8) = *(const uint2*)h8;
+              *(uint2*)(af.out_l8 + orow + c0 + sub * 8) = *(const uint2*)l8;
+            }
           }
           __syncwarp();
           aff_issue(qq + 2);
@@ -891,7 +911,8 @@ void tower_configure_device() {
   set_conv_attr<64, false, 32>();
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_f8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
-  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_f8h, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_halo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
+  CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
 }
 
 // e4m3 operands (AZ_TC_FP8 experiment): [rows][cols] bytes, box {64 bytes, box_rows}, SWIZZLE_64B
@@ -939,7 +960,8 @@ struct Impl {
   int fp8 = 0;         // 0: three fp16 passes; 1: per-tap FP8-correction kernel (A/B); 2: halo FP8-correction kernel (default)
   int pa = 0, q = 11;  // h8 = e5m2(hi16 * 2^pa), l8 = e5m2(lo * 2^q); filters (e4m3) carry the inverse factors
   int hrows = 0, halo = 0;                     // halo kernel: rows per activation stage, Wp + 1
-  CUtensorMap mXh_hi[2], mXh_h8[2], mXh_l8[2];  // halo boxes {64 channels, hrows positions}
+  bool halo3 = false;                          // three fp16 passes on the halo pipeline (the fp32-faithful default)
+  CUtensorMap mXh_hi[2], mXh_lo[2], mXh_h8[2], mXh_l8[2];  // halo boxes {64 channels, hrows positions}
   uint8_t *x_h8[2] = {nullptr, nullptr}, *x_l8[2] = {nullptr, nullptr};
   CUtensorMap mX_h8[2], mX_l8[2];
   __half *xin_hi = nullptr, *xin_lo = nullptr;  // [(guard+rows+guard)][64]
@@ -1024,8 +1046,13 @@ void launch_conv_pair2_f8h(const Impl& I, const Layer& L, int in, int out, const
   const int m_tiles = I.mode3d ? I.n_max * I.tps : (I.n_max * I.S + BM - 1) / BM;
   const int pair_tiles = ((m_tiles + 1) / 2) * (L.n_total / 256);
   const int clusters = std::min(I.pair_clusters, pair_tiles);
-  k_conv3x3_tc2_f8h<<<2 * clusters, NTHREADS, smem_bytes_f8h(I.hrows), st>>>(I.mXh_hi[in], I.mXh_h8[in], I.mXh_l8[in], L.mB2_hi,
-                                                                           L.mB2_h8, L.mB2_l8, L.mAff, af); LAUNCH_CHECK();
+  if (I.fp8 == 2)
+    k_conv3x3_tc2_halo<true><<<2 * clusters, NTHREADS, smem_bytes_f8h(I.hrows), st>>>(I.mXh_hi[in], I.mXh_h8[in], I.mXh_l8[in], L.mB2_hi,
+                                                                                   L.mB2_h8, L.mB2_l8, L.mAff, af);
+  else  // three fp16 passes on the halo pipeline
+    k_conv3x3_tc2_halo<false><<<2 * clusters, NTHREADS, smem_bytes_f8h(I.hrows), st>>>(I.mXh_hi[in], I.mXh_lo[in], I.mXh_lo[in], L.mB2_hi,
+                                                                                    L.mB2_lo, L.mB2_lo, L.mAff, af);
+  LAUNCH_CHECK();
 }
 void dispatch_conv(const Impl& I, const Layer& L, const CUtensorMap& ah, const CUtensorMap& al, __half* ohi, __half* olo,
                    const int* n_dev, int* err, cudaStream_t st) {
@@ -1041,7 +1068,7 @@ bool tc_tower_supported(const NetDims& d) {
   return (d.K == 64 || d.K == 128 || d.K == 256) && d.F <= 64 && d.SharedLayers >= 0;
 }
 
-void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2) {
+void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2, bool fast) {
   tower_configure_device();
   Impl* I = new Impl;
   t.impl = I;
@@ -1086,9 +1113,17 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
   // Default = the halo kernel; AZ_TC_FP8=0: three fp16 passes (k_conv3x3_tc2), =1: per-tap FP8 kernel (A/B checks).
   I->halo = d.W + 2;
   I->hrows = (BM + 2 * I->halo + 15) & ~15;
-  const int fp8_best = (I->pair_clusters > 0 && 2 * d.K >= 256) ? (I->hrows <= F8H_MAX_HROWS ? 2 : 1) : 0;
-  I->fp8 = fp8_best;
-  if (const char* f8 = getenv("AZ_TC_FP8")) { const int v = atoi(f8); if (v >= 0 && v <= 2) I->fp8 = std::min(v, fp8_best); }
+  const bool pair_ok = I->pair_clusters > 0 && 2 * d.K >= 256, halo_ok = pair_ok && I->hrows <= F8H_MAX_HROWS;
+  const int fp8_best = pair_ok ? (halo_ok ? 2 : 1) : 0;
+  I->fp8 = fast ? fp8_best : 0;
+  if (const char* f8 = getenv("AZ_TC_FP8")) { const int v = atoi(f8); if (v >= 0 && v <= 2) I->fp8 = std::min(v, fp8_best); }  // tests / A-B runs
+  I->halo3 = I->fp8 == 0 && halo_ok;
+  if (const char* h3 = getenv("AZ_TC_HALO")) { if (h3[0] == '0') I->halo3 = false; }  // A/B: per-tap three-pass kernel
+  if (I->halo3)
+    for (int i = 0; i < 2; i++) {
+      if (I->mode3d) { I->mXh_hi[i] = make_map3d(I->x_hi[i], n_max, I->S, d.K, 64, I->hrows); I->mXh_lo[i] = make_map3d(I->x_lo[i], n_max, I->S, d.K, 64, I->hrows); }
+      else { I->mXh_hi[i] = make_map(I->x_hi[i], I->rows_alloc, d.K, I->hrows, 64); I->mXh_lo[i] = make_map(I->x_lo[i], I->rows_alloc, d.K, I->hrows, 64); }
+    }
   if (I->fp8) {
     I->pa = 0;   // h8 = e5m2(hi16): the fp16 operand's own scale and range
     I->q = 11;   // l8 = e5m2(lo * 2^11): |lo| <= 2^-11 |hi|; filters' hi parts (max in [2^13, 2^14)) land at 2^2..2^3 in e4m3
@@ -1135,6 +1170,15 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2)
     I->layers.push_back(L);
   }
   CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+int tc_tower_kernel_kind(const TcTower& t) {
+  const Impl* I = (const Impl*)t.impl;
+  if (!I) return -1;
+  if (I->fp8 == 2) return 3;
+  if (I->fp8 == 1) return 2;
+  if (I->halo3) return 4;
+  return I->pair_clusters > 0 && 2 * I->d.K >= 256 ? 1 : 0;
 }
 
 void tc_tower_free(TcTower& t) {
@@ -1256,7 +1300,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   }
   for (size_t l = 1; l < I->layers.size(); l++) {
     size_t e0 = I->profile ? I->ev_get(st) : 0;
-    if (I->fp8 == 2 && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8h(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
+    if ((I->fp8 == 2 || I->halo3) && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8h(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
     else if (I->fp8 && I->layers[l].pair && I->layers[l].bn == 256) launch_conv_pair2_f8(*I, I->layers[l], cur, cur ^ 1, n_dev, err_flag, st);
     else
     dispatch_conv(*I, I->layers[l], I->mX_hi[cur], I->mX_lo[cur], I->x_hi[cur ^ 1], I->x_lo[cur ^ 1], n_dev, err_flag, st);

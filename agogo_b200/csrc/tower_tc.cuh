@@ -9,7 +9,12 @@ struct TcTower {
 // shapes the tensor-core tower handles (K multiple of 64, board fits the padded tiling); smaller
 // nets (tic-tac-toe K=3, Connect-4 K=16) run on the fp32 CUDA-core kernels.
 bool tc_tower_supported(const NetDims& d);
-void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2);
+// fast = AZ_FLAG_FAST_TOWER: the fused layers' two correction passes on the FP8 tensor path (E5M2 x E4M3, ~14.5-bit
+// operands) instead of fp16 — 2 tensor passes per MAC instead of 3; default false = fp32-faithful three fp16 passes
+void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2, bool fast);
+// 0: single-CTA kernel, 1: CTA-pair per-tap 3 x fp16, 2: CTA-pair per-tap FP8 corrections, 3: halo FP8 corrections,
+// 4: halo 3 x fp16 — which kernel runs the fused layers (bench labels)
+int tc_tower_kernel_kind(const TcTower& t);
 void tc_tower_free(TcTower& t);
 // split/scale/reorder the snapshot's filters and BN affines into the tensor-core operand layout
 void tc_tower_prepare(TcTower& t, const NetLayout& L, const Snapshot& s, cudaStream_t st, unsigned long long* launches);

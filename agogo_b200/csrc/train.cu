@@ -7,6 +7,7 @@
 // => deterministic; the tensor-core version of the conv passes is the next optimisation row.  Semantics are pinned against oracle/dual.hpp
 // (dual_train_step), whose backward is itself pinned by a finite-difference check.
 #include <algorithm>
+#include <cstdlib>
 #include <stdexcept>
 #include <vector>
 
@@ -500,21 +501,41 @@ void train_step_grads(TrainWS& ws, const NetLayout& L, const float* P, cudaStrea
 // w -= lr * g / world to its slice and writes the updated slice into every rank's parameter buffer.
 // Cross-GPU ordering uses epoch flags in peer memory: (A) "my gradients are complete" before anyone
 // reads them, (B) "my slice is written everywhere" before anyone's next kernel may start.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded spin on a peer-written epoch flag: false when the peer has not shown up within timeout_ns
+__device__ __forceinline__ bool wait_epoch(volatile int* flag, int epoch, unsigned long long timeout_ns) {
+  const unsigned long long t0 = global_ns();
+  while (*flag < epoch) {
+    if (global_ns() - t0 > timeout_ns) return false;
+  }
+  return true;
+}
 template <int WORLD>  // compile-time world size (0 = runtime): lets every peer load of a thread be issued up front
 __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float* const* __restrict__ peer_params,
                                     int* const* __restrict__ peer_flags, int* my_flags, int rank, int world_rt, size_t n,
-                                    float lr_over_world, int epoch, unsigned int* done_counter) {
+                                    float lr_over_world, int epoch, unsigned int* done_counter, unsigned long long timeout_ns,
+                                    int* err) {
   const int world = WORLD ? WORLD : world_rt;
-  __shared__ int s_last;
+  __shared__ int s_last, s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
   // (A) publish "gradients ready", then wait for everybody's
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
     ((volatile int*)peer_flags[threadIdx.x])[rank] = epoch;
   }
   if (threadIdx.x < world) {
-    while (((volatile int*)my_flags)[threadIdx.x] < epoch) {}
+    if (!wait_epoch((volatile int*)my_flags + threadIdx.x, epoch, timeout_ns)) s_ok = 0;
   }
   __syncthreads();
+  if (!s_ok) {  // a peer never arrived: report instead of spinning on the GPU forever; parameters are left untouched
+    if (threadIdx.x == 0) atomicOr(err, ERR_COMM_TIMEOUT);
+    return;
+  }
   __threadfence_system();
   const size_t shard = (((n + world - 1) / world) + 3) & ~(size_t)3;
   const size_t lo = (size_t)rank * shard;
@@ -564,7 +585,7 @@ __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float
   if (s_last) {
     if (threadIdx.x < world) {
       ((volatile int*)peer_flags[threadIdx.x])[world + rank] = epoch;
-      while (((volatile int*)my_flags)[world + threadIdx.x] < epoch) {}
+      if (!wait_epoch((volatile int*)my_flags + world + threadIdx.x, epoch, timeout_ns)) atomicOr(err, ERR_COMM_TIMEOUT);
     }
     if (threadIdx.x == 0) *done_counter = 0;
   }
@@ -572,13 +593,19 @@ __global__ void k_allreduce_sgd_p2p(float* const* __restrict__ peer_grads, float
 
 void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params, int* const* peer_flags, int* my_flags,
                              int rank, int world, size_t n, float lr, int epoch, unsigned int* done_counter, int num_sms,
-                             cudaStream_t st, unsigned long long* launches) {
+                             int* err, cudaStream_t st, unsigned long long* launches) {
+  static unsigned long long timeout_ns = 0;
+  if (!timeout_ns) {
+    const char* t = getenv("AZ_COMM_TIMEOUT_S");
+    const double sec = t ? atof(t) : 60.0;
+    timeout_ns = (unsigned long long)((sec > 0 ? sec : 60.0) * 1e9);
+  }
   const size_t shard = (((n + world - 1) / world) + 3) & ~(size_t)3;
   int blocks = (int)std::min<size_t>((shard / 4 + 255) / 256, (size_t)num_sms * 8);
   if (blocks < 1) blocks = 1;
   if (world > 16) throw std::runtime_error("k_allreduce_sgd_p2p: world > 16");
 #define AZ_LAUNCH_K8(W) k_allreduce_sgd_p2p<W><<<blocks, 256, 0, st>>>(peer_grads, peer_params, peer_flags, my_flags, rank, world, n, \
-                                                                       lr / (float)world, epoch, done_counter)
+                                                                       lr / (float)world, epoch, done_counter, timeout_ns, err)
   if (world == 2) AZ_LAUNCH_K8(2);
   else if (world == 4) AZ_LAUNCH_K8(4);
   else if (world == 8) AZ_LAUNCH_K8(8);

@@ -13,4 +13,4 @@ void train_sgd(TrainWS& ws, const NetLayout& L, float* params, float lr, float g
 // K8: one kernel = reduce-scatter over peer memory + SGD on the owned slice + all-gather into every peer
 void train_allreduce_sgd_p2p(float* const* peer_grads, float* const* peer_params, int* const* peer_flags, int* my_flags,
                              int rank, int world, size_t n, float lr, int epoch, unsigned int* done_counter, int num_sms,
-                             cudaStream_t st, unsigned long long* launches);
+                             int* err, cudaStream_t st, unsigned long long* launches);

@@ -97,6 +97,13 @@ typedef struct az_dual_config {
 
 #define AZ_FLAG_SHARED_TREE 1u /* one MCTS searched by both colours (mcts/example_test.go:74-156) */
 #define AZ_FLAG_FP32_TOWER 2u  /* force the fp32 CUDA-core tower (validation kernel) instead of tcgen05 */
+/* Precision policy of the tcgen05 tower.  Default: fp32-faithful — fp16 hi/lo operand split, three tensor passes per MAC,
+ * policy/value within 1e-4 of the fp32 forward on every net measured (incl. the reference's own random init, whose
+ * per-layer gain > 1 leaves a 1.5x margin).  AZ_FLAG_FAST_TOWER: the two correction passes run on the FP8 tensor path
+ * (E5M2 activations x E4M3 filters, ~14.5-bit effective operands, two tensor passes per MAC): +26 % simulations/s, outputs
+ * within 1.3e-5 on well-conditioned nets but up to 1.4e-4 on the reference's untamed init — outside the 1e-4 bar, hence
+ * opt-in. */
+#define AZ_FLAG_FAST_TOWER 4u
 
 typedef struct az_engine_desc {
   az_game_desc game;
@@ -243,8 +250,10 @@ int az_counters_reset(az_engine* e);
 /* Kernel timing for bench.py's roofline line: CUDA events on the engine's own stream around every
  * launch of the dominant kernel (the fused 3x3 conv of a residual block).  enable=1 starts a fresh
  * measurement, enable=0 stops; out (may be NULL) receives {conv_ms_total, conv_launches,
- * forward_ms_total, forward_calls, region_ms, 0...} accumulated since the last enable=1; region_ms is the device
- * time between the enable=1 and the enable=0 call on the engine's stream. */
+ * forward_ms_total, forward_calls, region_ms, kernel_kind, 0...} accumulated since the last enable=1; region_ms is the
+ * device time between the enable=1 and the enable=0 call on the engine's stream; kernel_kind names the kernel that runs
+ * the fused layers (0 single-CTA, 1 CTA-pair per-tap 3 x fp16, 2 per-tap FP8 corrections, 3 halo FP8 corrections,
+ * 4 halo 3 x fp16; -1 fp32 tower). */
 int az_profile(az_engine* e, int32_t enable, double out[8]);
 
 const char* az_build_info(void); /* "agogo_b200 <ver> sm_100a ..." or "oracle ..." */

@@ -127,6 +127,7 @@ struct Arena {
   Agent* currentPlayer = nullptr;
   MCTSConfig conf;
   uint64_t tree_seed;
+  uint64_t games = 0;  // games this Arena has started: every tree gets its own MCTS.rand stream (tree.go:84 seeds each from the clock)
   int max_moves = 0;  // COMPLETION: 0 = unlimited (reference has no cap; wq games need one to end)
   bool shared_tree = false;  // mcts/example_test.go:74-156 usage: ONE MCTS searched by both colours
   std::vector<GameRecord> records;
@@ -137,10 +138,10 @@ struct Arena {
     newTrees();
   }
   ~Arena() { delete game; }
-  void newTrees() {
-    A.mcts.reset(new MCTS(game, conf, &A, tree_seed));
+  void newTrees() {  // tree t of game g: stream derive_seed(tree_seed, 2 g + t)
+    A.mcts.reset(new MCTS(game, conf, &A, derive_seed(tree_seed, 2 * games)));
     if (shared_tree) B.mcts = A.mcts;
-    else B.mcts.reset(new MCTS(game, conf, &B, tree_seed));
+    else B.mcts.reset(new MCTS(game, conf, &B, derive_seed(tree_seed, 2 * games + 1)));
   }
 
   void switchPlayer() { currentPlayer = currentPlayer == &A ? &B : &A; }
@@ -196,6 +197,7 @@ struct Arena {
     else if (winner == B.player) { B.Wins++; A.Loss++; }
     rec.winner = winner; rec.n_examples = (int)examples.size();
     records.push_back(rec);
+    games++;
     newTrees();
     return examples;
   }

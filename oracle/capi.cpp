@@ -24,6 +24,7 @@ struct az_engine {
   std::shared_ptr<Inferer> inferers[2];
   float wins[2] = {0, 0}, loss[2] = {0, 0}, draw[2] = {0, 0};
   Rng coin{0};
+  uint64_t games_started = 0;
   std::vector<std::unique_ptr<Arena>> slots;
   int n_active_games = 0;  // games in the current begin..finish
   bool in_play = false, record = false;
@@ -183,6 +184,7 @@ int az_arena_begin(az_engine* e, int32_t n_games, int32_t record) {
     std::unique_ptr<Arena> a(new Arena(make_state(e->d.game), e->nets[0], e->nets[1], e->mc, e->d.encoder, e->d.seed));
     a->max_moves = e->d.game.max_moves;
     a->shared_tree = (e->d.flags & AZ_FLAG_SHARED_TREE) != 0;
+    a->games = e->games_started++;
     a->newTrees();
     a->A.inferer = e->inferers[0];
     a->B.inferer = e->inferers[1] ? e->inferers[1] : e->inferers[0];
@@ -283,7 +285,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   }
   Agent ag;
   ag.NN = e->nets[agent]; ag.enc = e->d.encoder; ag.player = player; ag.inferer = e->inferers[agent];
-  ag.mcts.reset(new MCTS(state.get(), e->mc, &ag, derive_seed(e->d.seed, 1)));
+  ag.mcts.reset(new MCTS(state.get(), e->mc, &ag, derive_seed(derive_seed(e->d.seed, 1), (e->d.flags & AZ_FLAG_SHARED_TREE) ? 0 : agent)));
   Single b = ag.Search(state.get());
   add_counters(e->base, ag.mcts->cnt);
   if (best) *best = b;

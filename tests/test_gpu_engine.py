@@ -411,33 +411,42 @@ def _c3_oracle_outputs(oracle, init, seed):
 
 
 @pytest.mark.parametrize("init,seed", [("tamed", 99), ("tamed", 7), ("reference", 5), ("reference", 11)])
-@pytest.mark.parametrize("mode", ["halo-f8", "tap-f8", "fp16x3"])
+@pytest.mark.parametrize("mode", ["fp16x3-halo", "fp16x3-tap", "f8-halo", "f8-tap"])
 def test_tc_tower_full_depth_c3(oracle, engine_lib, monkeypatch, mode, init, seed):
-    """The headline net (20 blocks x 256, 19x19, FC 512) end to end against the oracle, 1e-4 on policy and value through
-    all 41 conv layers, for the three numeric schemes of the fused layers: the product (hi*hi on kind::f16 + E5M2 x E4M3
-    correction passes on kind::f8f6f4, halo kernel), the same arithmetic in the per-tap kernel, and three fp16 passes —
-    on four weight sets, two of them the reference's own untamed init (heavy-tailed activations)."""
-    monkeypatch.setenv("AZ_TC_FP8", {"halo-f8": "2", "tap-f8": "1", "fp16x3": "0"}[mode])
+    """The headline net (20 blocks x 256, 19x19, FC 512) end to end against the oracle through all 41 conv layers, on four
+    weight sets (two with the BN-scale spread of the reference's own init at batch 256: per-layer gain > 1, the nets
+    bench.py runs).  The default precision (three fp16 passes, halo kernel — and the per-tap kernel it replaced) holds
+    the north star's 1e-4 on all of them.  AZ_FLAG_FAST_TOWER (FP8 correction passes, ~14.5-bit operands) holds it with
+    >= 5x margin on the well-conditioned nets but not on the reference-init ones (measured up to 1.4e-4 on the value
+    head): that is why it is opt-in; its bound here is what was measured, stated, not the north star's."""
+    env = {"fp16x3-halo": {}, "fp16x3-tap": {"AZ_TC_HALO": "0"}, "f8-halo": {}, "f8-tap": {"AZ_TC_FP8": "1"}}[mode]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fast = mode.startswith("f8")
     params, planes, po, vo = _c3_oracle_outputs(oracle, init, seed)
-    d = K.make_desc(K.GAME_WQ, 19, 19, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4,
+    d = K.make_desc(K.GAME_WQ, 19, 19, 0, komi=7.5, sims=2, n_games=4, seed=2, max_moves=4, flags=K.FLAG_FAST_TOWER if fast else 0,
                     nn=dict(k=256, shared_layers=20, fc=512, batch_size=2, features=18, action_space=362))
     etc = engine_lib.create(d)
     etc.net_set(0, params)
     etc.set_inferer(0, K.INF_DUAL)
     ptc, vtc = etc.infer(0, planes)
     etc.close()
-    print("C3 depth %s %s/%d: dp=%.3g dv=%.3g pmax=%.3g |v|max=%.3g" % (mode, init, seed, np.abs(ptc - po).max(), np.abs(vtc - vo).max(), po.max(), np.abs(vo).max()))
+    dp, dv = np.abs(ptc - po).max(), np.abs(vtc - vo).max()
+    print("C3 depth %s %s/%d: dp=%.3g dv=%.3g pmax=%.3g |v|max=%.3g" % (mode, init, seed, dp, dv, po.max(), np.abs(vo).max()))
     assert np.isfinite(po).all() and np.isfinite(vo).all()
-    assert np.abs(ptc - po).max() < 1e-4 and np.abs(vtc - vo).max() < 1e-4
+    tol = 1e-4 if not fast else (2e-5 if init == "tamed" else 3e-4)
+    assert dp < tol and dv < tol, (mode, init, seed, dp, dv, tol)
 
 
-@pytest.mark.parametrize("mode", ["2", "0"])
+@pytest.mark.parametrize("mode", ["fp16x3-halo", "fp16x3-tap", "f8-halo"])
 def test_tc_tower_modes_small_nets(oracle, engine_lib, monkeypatch, mode):
-    """9x9, K = 128 (2C = 256: the CTA-pair kernels in the flat 2-D layout): FP8-correction halo kernel and the three-pass
-    kernel against the oracle."""
-    monkeypatch.setenv("AZ_TC_FP8", mode)
+    """9x9, K = 128 (2C = 256: the CTA-pair kernels in the flat 2-D layout, halo of 150 -> 160 rows): the three-pass halo
+    kernel (default), the per-tap kernel and the FP8-correction halo kernel against the oracle."""
+    if mode == "fp16x3-tap":
+        monkeypatch.setenv("AZ_TC_HALO", "0")
     def desc():
         return K.make_desc(K.GAME_WQ, 9, 9, 0, komi=7.5, sims=2, n_games=8, seed=2, max_moves=4,
+                           flags=K.FLAG_FAST_TOWER if mode == "f8-halo" else 0,
                            nn=dict(k=128, shared_layers=4, fc=64, batch_size=2, features=18, action_space=82))
     eo, etc = oracle.create(desc()), engine_lib.create(desc())
     H.tame_gammas([eo, etc], 0, 13)

@@ -232,7 +232,7 @@ def test_config_options_vs_python(oracle, name, conf):
     for g in range(G_):
         state, r = P._splitmix(state)
         def make(agent, gm):
-            return P.MCTS(gm, 1.0, sims, None, None, m, m, evaluator=P.dummy_evaluator(cells, 1 + agent), conf=conf, tree_seed=tree_seed)
+            return P.MCTS(gm, 1.0, sims, None, None, m, m, evaluator=P.dummy_evaluator(cells, 1 + agent), conf=conf, tree_seed=P.derive_seed(tree_seed, 2 * g + agent))  # tree t of game g: stream 2g + t
         moves, winner, a_player, examples, dumps = P.arena_play(new_game, make, r % 2, encoder=enc, max_moves=cap)
         rec = run["records"][g]
         assert list(rec["moves"]) == moves and rec["winner"] == winner and rec["n_examples"] == len(examples), (name, g, rec, moves)
