@@ -230,11 +230,34 @@ class AZ:
         return len(range(self.rank, n, self.world))
 
     def _gather_examples(self, ex):
+        """Every rank ends up with all ranks' examples, rank-major (tensor all-gather of padded arrays: boards of a 19x19
+        epoch are gigabytes, too much for pickled objects)."""
         if self.world == 1:
             return ex
-        out = [None] * self.world
-        self.dist.all_gather_object(out, [(x.Board, x.Policy, x.Value) for x in ex])
-        return [Example(b, p, v) for part in out for (b, p, v) in part]
+        import torch
+        dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
+        n = len(ex)
+        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        self.dist.all_gather(counts, cnt)
+        counts = [int(c.item()) for c in counts]
+        mx = max(counts)
+        if mx == 0:
+            return []
+        plane = self.engine.plane
+        A1 = self.engine.action_space + 1
+        B = np.zeros((mx, plane), np.float32)
+        P = np.zeros((mx, A1), np.float32)
+        V = np.zeros(mx, np.float32)
+        for i, x in enumerate(ex):
+            B[i], P[i], V[i] = x.Board, x.Policy, x.Value
+        out = []
+        for arr in (B, P, V):
+            t = torch.from_numpy(arr).to(dev)
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            self.dist.all_gather(parts, t)
+            out.append([p.cpu().numpy() for p in parts])
+        return [Example(out[0][r][i], out[1][r][i], float(out[2][r][i])) for r in range(self.world) for i in range(counts[r])]
 
     def _train(self, Xs, Pi, V, batches, nniters, seed):
         """dual.Train (meta.go:16-54) on this rank's share of the batches, gradients averaged over ranks."""
@@ -326,23 +349,31 @@ class AZ:
 
     # ---- AZ.Learn (agogo.go:100-172) ----------------------------------------------------------
     def Learn(self, iters, episodes, nniters, arenaGames, on_epoch=None):
+        import time
         e = self.engine
         for self.epoch in range(iters):
             ep = self.epoch
+            t0 = time.perf_counter()
             self.setupSelfPlay(ep)
-            ex = self._gather_examples(self._play(self._share(episodes), True))
+            mine = self._play(self._share(episodes), True)
+            t1 = time.perf_counter()
+            ex = self._gather_examples(mine)
+            t2 = time.perf_counter()
             if self.conf.MaxExamples > 0 and len(ex) > self.conf.MaxExamples:
                 self.shuffleExamples(ex, derive_seed(self.seed, 1000 + 10 * ep))
                 ex = ex[:self.conf.MaxExamples]
             Xs, Pi, V, batches = self.prepareExamples(ex, derive_seed(self.seed, 1001 + 10 * ep))
             if batches == 0:
                 raise RuntimeError("batches is nil, probably too few examples regarding the batchsize")
+            t3 = time.perf_counter()
             costs = self._train(Xs, Pi, V, batches, nniters, derive_seed(self.seed, 1002 + 10 * ep))
+            t4 = time.perf_counter()
             self.B.SwitchToInference()
             self.A.resetStats()
             self.B.resetStats()
             self._play(self._share(arenaGames), False)
             aw, al, ad, bw, bl, bd = self._global_stats()
+            t5 = time.perf_counter()
             with np.errstate(invalid="ignore", divide="ignore"):
                 ratio = np.float32(bw) / (np.float32(bw) + np.float32(aw))
             promoted = bool(ratio > np.float32(self.conf.UpdateThreshold))  # NaN (0/0) never promotes
@@ -350,7 +381,10 @@ class AZ:
                 e.net_copy(0, 1)  # A.NN = B.NN (agogo.go:161)
             e.net_init(1, derive_seed(self.seed, 200 + ep))  # newB (arena.go:205-224)
             self.log.append(dict(a=(float(aw), float(al), float(ad)), b=(float(bw), float(bl), float(bd)), n_examples=len(ex), batches=batches, promoted=promoted,
-                                 first_cost=float(costs[0]), last_cost=float(costs[-1])))
+                                 first_cost=float(costs[0]), last_cost=float(costs[-1]),
+                                 phase_seconds=dict(selfplay=round(t1 - t0, 3), gather=round(t2 - t1, 3), prepare=round(t3 - t2, 3),
+                                                    train=round(t4 - t3, 3), arena=round(t5 - t4, 3),
+                                                    train_steps=int(len(costs)))))
             if on_epoch is not None:
                 on_epoch(ep, self.log[-1])
         return None

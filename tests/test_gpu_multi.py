@@ -25,29 +25,34 @@ def _worker(rank, world, port, out_dir, collective):
     conf = host.Config(NNConf=nn, MCTSConf=mc, UpdateThreshold=0.52)
     az = host.AZ(host.Game(K.GAME_C4, 6, 7, 4), conf, n_games=8, seed=5, dist=dist, device=rank, flags=K.FLAG_FP32_TOWER)
     assert az.engine_comm
-    az.Learn(2, 8, 2, 6)
+    az.Learn(2, 4 * world, 2, 6)
     np.save(os.path.join(out_dir, "params_%s_%d.npy" % (collective, rank)),
             np.concatenate([az.engine.net_get(0), az.engine.net_get(1)]))
     dist.destroy_process_group()
 
 
-def test_two_gpu_learn_nccl(tmp_path):
+def _ngpu():
     import subprocess
     try:
-        ngpu = len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.strip().splitlines())
+        return len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout.strip().splitlines())
     except Exception:
-        ngpu = 0
-    if ngpu < 2:
-        pytest.skip("needs 2 GPUs")  # (decided without importing torch: a cold import costs minutes on a fresh box)
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_learn_nccl(tmp_path, world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)  # (decided without importing torch: a cold import costs minutes on a fresh box)
     import torch.multiprocessing as mp
-    port = 29700 + (os.getpid() % 2000)
+    port = 29700 + (os.getpid() % 2000) + 10 * world
     res = {}
     for i, collective in enumerate(("p2p", "nccl")):  # the fused peer-memory kernel, and plain ncclAllReduce + SGD
-        mp.spawn(_worker, args=(2, port + i, str(tmp_path), collective), nprocs=2, join=True)
+        mp.spawn(_worker, args=(world, port + i, str(tmp_path), collective), nprocs=world, join=True)
         p0 = np.load(tmp_path / ("params_%s_0.npy" % collective))
-        p1 = np.load(tmp_path / ("params_%s_1.npy" % collective))
         assert np.isfinite(p0).all()
-        assert (p0.view(np.uint32) == p1.view(np.uint32)).all(), "replicas diverged (%s)" % collective
+        for r in range(1, world):
+            pr = np.load(tmp_path / ("params_%s_%d.npy" % (collective, r)))
+            assert (p0.view(np.uint32) == pr.view(np.uint32)).all(), "replicas diverged (%s, rank %d)" % (collective, r)
         res[collective] = p0
     # same mathematics, different summation order inside the collective
     assert np.abs(res["p2p"] - res["nccl"]).max() <= 1e-4 * max(1.0, np.abs(res["nccl"]).max())
