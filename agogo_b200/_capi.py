@@ -48,7 +48,8 @@ class EngineDesc(C.Structure):
 
 class State(C.Structure):
     _fields_ = [("board", C.POINTER(C.c_int32)), ("to_move", C.c_int32), ("move_number", C.c_int32), ("passes", C.c_int32),
-                ("last_move", C.c_int32), ("n_hist", C.c_int32), ("hist", C.POINTER(C.c_int32))]
+                ("last_move", C.c_int32), ("n_hist", C.c_int32), ("hist", C.POINTER(C.c_int32)),
+                ("n_moves", C.c_int32), ("moves", C.POINTER(C.c_int32))]
 
 
 class Counters(C.Structure):
@@ -64,7 +65,7 @@ SYMBOLS = [
     "az_arena_step", "az_arena_finish", "az_search_begin", "az_search_run", "az_search_end", "az_game_record",
     "az_game_state", "az_examples_count", "az_examples_read", "az_examples_clear", "az_tree_dump", "az_rules_apply",
     "az_rules_status", "az_train", "az_comm_unique_id", "az_comm_init", "az_counters_get", "az_counters_reset",
-    "az_build_info", "az_profile", "az_train_grads", "az_train_apply", "az_search", "az_comm_bench",
+    "az_build_info", "az_profile", "az_train_grads", "az_train_apply", "az_search", "az_comm_bench", "az_agent_reset_tree",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -223,15 +224,21 @@ class Engine:
     def search_end(self):
         self._ck(self.lib.dll.az_search_end(self.h))
 
-    def search(self, agent, board, to_move, player, move_number=0, passes=0, hist=None, last_move=-1):
-        """Agent.Search on an external position: returns (best move, visit counts by move, Pass last)."""
+    def search(self, agent, board, to_move, player, move_number=0, passes=0, hist=None, last_move=-1, moves=None):
+        """Agent.Search on an external position: returns (best move, visit counts by move, Pass last).  `moves` = the
+        tail of the state's history as (player, move) pairs, oldest first (enables tree reuse across calls)."""
         board = np.ascontiguousarray(board, np.int32)
         hist = np.zeros((0, self.cells), np.int32) if hist is None else np.ascontiguousarray(hist, np.int32).reshape(-1, self.cells)
-        st = State(_p(board, C.c_int32), to_move, move_number, passes, last_move, hist.shape[0], _p(hist, C.c_int32))
+        mv = np.zeros((0, 2), np.int32) if moves is None else np.ascontiguousarray(moves, np.int32).reshape(-1, 2)
+        st = State(_p(board, C.c_int32), to_move, move_number, passes, last_move, hist.shape[0], _p(hist, C.c_int32),
+                   mv.shape[0], _p(mv, C.c_int32))
         best = C.c_int32()
         visits = np.zeros(self.action_space + 1, np.float32)
         self._ck(self.lib.dll.az_search(self.h, agent, C.byref(st), player, C.byref(best), _p(visits, C.c_float)))
         return best.value, visits
+
+    def reset_tree(self, agent):
+        self._ck(self.lib.dll.az_agent_reset_tree(self.h, agent))
 
     def game_record(self, game, cap=4096):
         moves = np.empty(cap, np.int32)

@@ -105,6 +105,8 @@ struct az_engine {
   unsigned int* done_counter = nullptr;
   int epoch = 0, num_sms = 148;
   int32_t* d_agree = nullptr;  // step-count agreement of the data-parallel ranks (az_train)
+  // Agent.Search on external positions: the position each agent's tree (game slot 0) was last searched on = t.prev
+  struct ExtPrev { bool valid = false; int move_number = 0; std::vector<uint8_t> board; } ext_prev[2];
   mutable std::string err;
 
   template <class T>
@@ -520,6 +522,7 @@ int az_arena_begin(az_engine* e, int32_t n_games, int32_t record) {
   launch_assign_slots(e->P, e->E, n_games, e->stream); e->launches++;
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   e->in_play = true; e->record = record != 0; e->n_play = n_games;
+  e->ext_prev[0].valid = e->ext_prev[1].valid = false;  // the arena owns slot 0 now
   e->ex_by_game.assign(n_games, {});
   e->records.clear();
   GUARD_END(e)
@@ -687,12 +690,44 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   CUDA_CHECK(cudaSetDevice(e->device));
   const GameP& P = e->P;
   const EngineDev& E = e->E;
-  // fresh slot 0 (board, scalars, trees), then overwrite it with the caller's position
-  int coin = 0;
-  CUDA_CHECK(cudaMemcpyAsync(e->coins_dev, &coin, 4, cudaMemcpyHostToDevice, e->stream));
-  launch_arena_begin(P, E, 1, e->coins_dev, 0ull, e->stream); e->launches++;  // external position: streams 0 / 1 of the tree seed
+  // ---- newRootState (search.go:424-469) on the host: may the agent's tree be re-rooted on this position?
+  const int t_idx = P.shared_tree ? 0 : agent;
+  az_engine::ExtPrev& prev = e->ext_prev[t_idx];
   std::vector<uint8_t> b(E.cellsP, 0);
   for (int i = 0; i < P.cells; i++) b[i] = (uint8_t)st->board[i];
+  int depth = st->move_number - prev.move_number;
+  bool reuse = P.kind == KIND_MNK && prev.valid && depth >= 0 && (depth == 0 || (st->moves && st->n_moves >= depth)) &&
+               st->move_number < P.max_plies;
+  if (reuse) {  // tmp.UndoLastMove() x depth, then tmp.Eq(prev): mnk's Undo clears the cell of each undone move (mnk.go:184-189)
+    std::vector<uint8_t> tmp = b;
+    for (int i = 0; i < depth && reuse; i++) {
+      const int mv = st->moves[2 * (st->n_moves - 1 - i) + 1];
+      if (mv < 0 || mv >= P.cells) reuse = false; else tmp[mv] = 0;
+    }
+    if (reuse) reuse = memcmp(tmp.data(), prev.board.data(), P.cells) == 0;
+  }
+  if (!reuse) {
+    // fresh tree for this agent (the other agent's tree in slot 0 is untouched): empty pool, no root, RNG stream t of the
+    // engine's tree seed (what k_arena_begin gives tree t of the first game)
+    const uint64_t ts = derive_seed(E.tree_seed, (uint64_t)t_idx);
+    int32_t tiv[TI_COUNT] = {0};
+    tiv[TI_ROOT] = -1; tiv[TI_RNG_LO] = (int32_t)(uint32_t)(ts & 0xffffffffu); tiv[TI_RNG_HI] = (int32_t)(uint32_t)(ts >> 32);
+    CUDA_CHECK(cudaMemcpyAsync(E.ti + (size_t)t_idx * TI_COUNT, tiv, sizeof tiv, cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaMemsetAsync(E.wv, 0, (size_t)E.V * WV_COUNT * 4, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));  // tiv is a stack buffer
+    prev.valid = false;
+  } else {
+    // keep the tree: reset only the per-search worker records of slot 0 and hand the replay (Fwd + findChild per move)
+    // to k_search_begin through the slot's move history
+    CUDA_CHECK(cudaMemsetAsync(E.wv, 0, (size_t)E.V * WV_COUNT * 4, e->stream));
+    std::vector<int16_t> hm(depth > 0 ? depth : 1);
+    for (int i = 0; i < depth; i++) hm[i] = (int16_t)st->moves[2 * (st->n_moves - depth + i) + 1];
+    if (depth > 0) CUDA_CHECK(cudaMemcpyAsync(E.hmoves + prev.move_number, hm.data(), (size_t)depth * 2, cudaMemcpyHostToDevice, e->stream));
+    int32_t pv[3] = {1, prev.move_number, 0};  // TI_PREV_VALID, TI_PREV_MN, TI_NPOL (cachedPolicies only feed Arena examples)
+    static_assert(TI_PREV_MN == TI_PREV_VALID + 1 && TI_NPOL == TI_PREV_VALID + 2, "tree-info layout");
+    CUDA_CHECK(cudaMemcpyAsync(E.ti + (size_t)t_idx * TI_COUNT + TI_PREV_VALID, pv, 12, cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));  // hm / pv are stack buffers
+  }
   std::vector<uint8_t> ring(P.hist_len ? (size_t)8 * E.cellsP : 1, 0);
   if (P.hist_len)
     for (int i = 0; i < st->n_hist; i++) {
@@ -755,8 +790,17 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   }
   e->in_play = false;
   e->ex_by_game.clear();
-  if (rc) return rc;
+  if (rc) { prev.valid = false; return rc; }
+  // t.prev = t.current.Clone() (search.go:152): the position this tree was searched on
+  prev.valid = true; prev.move_number = st->move_number; prev.board.assign(b.begin(), b.begin() + P.cells);
   GUARD_END_PLAY(e)
+  return AZ_OK;
+}
+
+int az_agent_reset_tree(az_engine* e, int32_t agent) {  // MCTS.Reset (tree.go:249-276) for the external-search tree
+  if (agent < 0 || agent > 1) return AZ_ERR_INVALID;
+  if (e->in_play) { e->err = "az_agent_reset_tree during a running arena"; return AZ_ERR_STATE; }
+  e->ext_prev[e->P.shared_tree ? 0 : agent].valid = false;
   return AZ_OK;
 }
 

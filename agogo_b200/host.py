@@ -389,15 +389,37 @@ class AZ:
                 on_epoch(ep, self.log[-1])
         return None
 
-    # ---- checkpoint: Model()-ordered flat payload (the gob container stays on the Go side) ---------
+    # ---- checkpoint (agogo.go:175-209): the reference's gob container of the Model()-ordered tensors (gobfmt.py; the
+    # tensor.Dense layout inside it is restated from memory, unverified), or a flat .npz when the name says so
+
     def Save(self, filename):
         nt, _ = self.engine.param_count()
         descs = [self.engine.param_desc(i) for i in range(nt)]
-        np.savez(filename, params=self.engine.net_get(0), names=np.array([d[0] for d in descs]),
-                 shapes=np.array([list(d[1]) + [1] * (4 - len(d[1])) for d in descs]))
+        params = self.engine.net_get(0)
+        if str(filename).endswith(".npz"):
+            np.savez(filename, params=params, names=np.array([d[0] for d in descs]),
+                     shapes=np.array([list(d[1]) + [1] * (4 - len(d[1])) for d in descs]))
+            return
+        from . import gobfmt
+        with open(filename, "wb") as f:  # os.O_CREATE|os.O_TRUNC|os.O_WRONLY
+            f.write(gobfmt.save_stream([params[off:off + size].reshape(shape) for (_, shape, off, size) in descs]))
 
     def Load(self, filename):  # agogo.go:187-209: both A and B get the stored net, useDummy is cleared
-        z = np.load(filename if str(filename).endswith(".npz") else str(filename) + ".npz")
-        self.engine.net_set(0, z["params"])
-        self.engine.net_set(1, z["params"])
+        if str(filename).endswith(".npz"):
+            flat = np.load(filename)["params"]
+        else:
+            from . import gobfmt
+            nt, nf = self.engine.param_count()
+            descs = [self.engine.param_desc(i) for i in range(nt)]
+            with open(filename, "rb") as f:
+                tensors = gobfmt.load_stream(f.read())
+            if len(tensors) != nt:
+                raise RuntimeError("checkpoint holds %d tensors, the net's Model() has %d" % (len(tensors), nt))
+            flat = np.empty(nf, np.float32)
+            for t, (name, shape, off, size) in zip(tensors, descs):
+                if tuple(t.shape) != tuple(shape):
+                    raise RuntimeError("checkpoint tensor %s has shape %r, expected %r" % (name, t.shape, shape))
+                flat[off:off + size] = t.reshape(-1)
+        self.engine.net_set(0, flat)
+        self.engine.net_set(1, flat)
         self.useDummy = False

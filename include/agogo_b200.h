@@ -166,18 +166,30 @@ int az_search_end(az_engine* e);                     /* bestMove, example, Apply
 
 /* Agent.Search on an EXTERNAL position (agent.go:77-80: MCTS.SetGame(g); MCTS.Search(a.Player)) — the
  * README's inference use.  The Go shim marshals game.State getters into az_state: Board(), ToMove(),
- * MoveNumber(), Passes() and, for the WQEncoder, Historical(MoveNumber-n_hist .. MoveNumber-1).
- * A fresh tree is searched for `mcts.sims` iterations (no reuse across calls).  Returns the chosen move
- * and, optionally, the root children's visit counts indexed by move (Pass at index ActionSpace).
- * Not callable while an arena is running; uses game slot 0. */
+ * MoveNumber(), Passes(), for the WQEncoder Historical(MoveNumber-n_hist .. MoveNumber-1), and the tail of the
+ * state's move history (what UndoLastMove / Fwd walk).  Returns the chosen move and, optionally, the root children's
+ * visit counts indexed by move (Pass at index ActionSpace).  Not callable while an arena is running; uses game slot 0.
+ *
+ * Tree reuse (updateRoot / newRootState, search.go:424-500): the agent's tree survives the call, as the Agent's MCTS
+ * does in the reference.  The next az_search of the same agent re-roots it when the new position continues the one
+ * searched last: d = MoveNumber - prev.MoveNumber >= 0, the last d entries of `moves` undone from the board give the
+ * previous board (State.Eq), and each of those moves is a child of the successive roots (findChild); the siblings'
+ * subtrees become unreachable (cleanup), the pool keeps growing until az_agent_reset_tree.  Anything else — no move
+ * list, a different line of play, a missing child — searches a brand-new root, exactly as the reference falls back to
+ * New(Pass|first legal move).  Reuse can only succeed for mnk: c4's Clone pads its history (c4/game.go:142-160) and
+ * wq has no UndoLastMove (wq/game.go:119), so those games always take the fresh-root path (and their pool is recycled).
+ * az_arena_begin and az_agent_reset_tree (MCTS.Reset, tree.go:249-276) drop the external trees. */
 typedef struct az_state {
   const int32_t* board; /* [m*n] colours */
   int32_t to_move, move_number, passes;
   int32_t last_move;    /* LastMove().Single; AZ_PASS for an empty history (mnk.go:84-89) */
   int32_t n_hist;       /* 0..8 */
   const int32_t* hist;  /* [n_hist][m*n], oldest first */
+  int32_t n_moves;      /* entries of `moves` (0 = history unknown: no reuse across calls) */
+  const int32_t* moves; /* [n_moves][2] = (player, move), oldest first: the tail of the State's history */
 } az_state;
 int az_search(az_engine* e, int32_t agent, const az_state* s, int32_t player, int32_t* best, float* child_visits);
+int az_agent_reset_tree(az_engine* e, int32_t agent);
 
 /* per-game results of the last begin..finish: moves played, winner (AZ_NONE/BLACK/WHITE),
  * colour of agent A, number of examples kept */

@@ -31,6 +31,11 @@ struct az_engine {
   std::vector<Example> examples;
   std::vector<GameRecord> records;
   Counters base;  // counters accumulated from finished slots
+  // Agent.Search on external positions: the Agent and its MCTS persist across az_search calls (agent.go:14-30)
+  std::unique_ptr<Agent> ext_agent[2];
+  bool ext_valid[2] = {false, false};
+  int ext_prev_mn[2] = {0, 0};
+  std::vector<int32_t> ext_prev_board[2];
   mutable std::string err;
 };
 
@@ -179,6 +184,7 @@ int az_arena_begin(az_engine* e, int32_t n_games, int32_t record) {
   if (!e->inferers[0] || (!e->inferers[1] && !(e->d.flags & AZ_FLAG_SHARED_TREE))) { e->err = "agents have no inferer"; return AZ_ERR_STATE; }
   GUARD_BEGIN
   e->slots.clear(); e->records.clear();
+  e->ext_valid[0] = e->ext_valid[1] = false;
   e->n_active_games = n_games; e->record = record != 0; e->in_play = true;
   for (int g = 0; g < n_games; g++) {
     std::unique_ptr<Arena> a(new Arena(make_state(e->d.game), e->nets[0], e->nets[1], e->mc, e->d.encoder, e->d.seed));
@@ -263,6 +269,8 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
     MNK* t = new MNK(g.m, g.n, g.k);
     t->board.assign(st->board, st->board + cells);
     t->history.assign(st->move_number, PlayerMove{None, st->last_move}); t->histPtr = st->move_number; t->nextToMove = st->to_move;
+    for (int i = 0; i < st->n_moves && i < st->move_number; i++)  // the tail of the history the caller knows
+      t->history[st->move_number - 1 - i] = PlayerMove{(Player)st->moves[2 * (st->n_moves - 1 - i)], (Single)st->moves[2 * (st->n_moves - 1 - i) + 1]};
     state.reset(t);
   } else if (g.kind == AZ_GAME_C4) {
     C4* t = new C4(g.m, g.n, g.k);
@@ -283,11 +291,31 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
     }
     state.reset(t);
   }
-  Agent ag;
+  // The agent's MCTS survives the call when the position continues the one it searched last (include/agogo_b200.h,
+  // az_search): same admission rule as the engine's host side — then MCTS.Search's own updateRoot / newRootState
+  // (search.go:424-500) does the re-rooting, findChild failures included.
+  const int ti = (e->d.flags & AZ_FLAG_SHARED_TREE) ? 0 : agent;
+  const int depth = st->move_number - e->ext_prev_mn[ti];
+  bool reuse = g.kind == AZ_GAME_MNK && e->ext_valid[ti] && e->ext_agent[ti] && depth >= 0 &&
+               (depth == 0 || (st->moves && st->n_moves >= depth)) && st->move_number < cells + 2;
+  if (reuse) {
+    std::vector<int32_t> tmp(st->board, st->board + cells);
+    for (int i = 0; i < depth && reuse; i++) {
+      const int mv = st->moves[2 * (st->n_moves - 1 - i) + 1];
+      if (mv < 0 || mv >= cells) reuse = false; else tmp[mv] = None;
+    }
+    if (reuse) reuse = tmp == e->ext_prev_board[ti];
+  }
+  if (!reuse) {
+    e->ext_valid[ti] = false;
+    e->ext_agent[ti].reset(new Agent);
+    e->ext_agent[ti]->mcts.reset(new MCTS(state.get(), e->mc, e->ext_agent[ti].get(), derive_seed(derive_seed(e->d.seed, 1), ti)));
+  }
+  Agent& ag = *e->ext_agent[ti];
   ag.NN = e->nets[agent]; ag.enc = e->d.encoder; ag.player = player; ag.inferer = e->inferers[agent];
-  ag.mcts.reset(new MCTS(state.get(), e->mc, &ag, derive_seed(derive_seed(e->d.seed, 1), (e->d.flags & AZ_FLAG_SHARED_TREE) ? 0 : agent)));
   Single b = ag.Search(state.get());
-  add_counters(e->base, ag.mcts->cnt);
+  e->ext_valid[ti] = true; e->ext_prev_mn[ti] = st->move_number; e->ext_prev_board[ti].assign(st->board, st->board + cells);
+  add_counters(e->base, ag.mcts->cnt); ag.mcts->cnt = Counters();
   if (best) *best = b;
   if (child_visits) {
     int A = state->ActionSpace();
@@ -301,6 +329,13 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
       }
   }
   GUARD_END(e)
+  return AZ_OK;
+}
+
+int az_agent_reset_tree(az_engine* e, int32_t agent) {
+  if (agent < 0 || agent > 1) return AZ_ERR_INVALID;
+  if (e->in_play) { e->err = "az_agent_reset_tree during a running arena"; return AZ_ERR_STATE; }
+  e->ext_valid[(e->d.flags & AZ_FLAG_SHARED_TREE) ? 0 : agent] = false;
   return AZ_OK;
 }
 
