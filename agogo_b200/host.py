@@ -118,7 +118,8 @@ class Config:
     UpdateThreshold: float = 0.0
     MaxExamples: int = 0
     Encoder: int = K.ENC_TWO_PLANE
-    Augmenter: object = None
+    Augmenter: object = None       # Augmenter func(Example) []Example (datatypes.go:44-45), applied to every kept example
+    OutputEncoder: object = None   # OutputEncoder{Encode(MetaState) error; Flush() error} (datatypes.go:36-42)
 
 
 @dataclass
@@ -157,6 +158,32 @@ class Agent:
 
     def resetStats(self):
         self._az.engine.reset_stats(self.idx)
+
+
+class MetaState:
+    """game.MetaState (game/state.go:171-177) as the OutputEncoder sees it after every move of Arena.Play."""
+
+    def __init__(self, az, state, game_number):
+        self._az, self._state, self._game_number = az, state, game_number
+
+    def Name(self):
+        return self._az.conf.Name or "UNKNOWN GAME"  # arena.go:56-58
+
+    def Epoch(self):
+        return self._az.epoch
+
+    def GameNumber(self):
+        return self._game_number
+
+    def Score(self, player):  # arena.go:181-189: the agent's wins
+        if player == self._az.A.Player:
+            return float(self._az.A.Wins)
+        if player == self._az.B.Player:
+            return float(self._az.B.Wins)
+        return 0.0
+
+    def State(self):  # game.State getters of the running game: board, to_move, move_number, passes, ended, winner
+        return self._state
 
 
 def shuffle_rows(Xs, Pi, V, rng):
@@ -327,6 +354,28 @@ class AZ:
 
     def SelfPlay(self, episodes=1):
         return self._play(episodes, True)
+
+    def Play(self, record, enc=None, aug=None, game_number=0):
+        """(*Arena).Play(record, enc, aug) (arena.go:80-179) with the reference's signature: ONE game, stepped ply by ply
+        so that the OutputEncoder is called with the MetaState after every move (arena.go:131-133); the Augmenter is
+        applied to every kept example (arena.go:115-121).  Returns (None, examples) like the reference (arena.go:178)."""
+        e = self.engine
+        e.examples(clear=True)
+        e.arena_begin(1, record)
+        rec = e.game_record(0)
+        self.A.Player = rec["a_player"]
+        self.B.Player = K.WHITE if rec["a_player"] == K.BLACK else K.BLACK
+        active = 1
+        while active:
+            active = e.arena_step()
+            if enc is not None:
+                enc.Encode(MetaState(self, e.game_state(0), game_number))
+        e.arena_finish()
+        boards, pols, vals = e.examples(clear=True)
+        ex = [Example(boards[i], pols[i], float(vals[i])) for i in range(len(vals))]
+        if aug is not None:
+            ex = [y for x in ex for y in aug(x)]
+        return K.NONE, ex
 
     @staticmethod
     def shuffleExamples(ex, seed):  # agogo.go:251-257 with an injected seed

@@ -1,6 +1,8 @@
 // Package b200 is the cgo shim that puts the B200 engine (include/agogo_b200.h) under gorgonia/agogo's
 // Go API.  UNCOMPILED in this repository's image (no Go toolchain); kept as the binding a maintainer
-// would add next to agent.go / arena.go / agogo.go.  No Go pointer is retained by C after a call.
+// would add next to agent.go / arena.go / agogo.go.  No Go pointer is retained by C after a call, and no Go-allocated
+// struct containing Go pointers is passed to C (az_state's arrays are C.malloc copies).  backend_b200.go puts the
+// reference's own method signatures — (*Agent).Search, (*Arena).Play, (*AZ).Learn, Save, Load — on top of this package.
 package b200
 
 /*
@@ -154,20 +156,30 @@ func (e *Engine) ResetStats(agent int) error {
 	return check(e, C.az_agent_reset_stats(e.h, C.int32_t(agent)))
 }
 
+// cInts copies a Go []int32 into C memory (the cgo pointer-passing rule forbids handing C a Go struct that holds Go
+// pointers: az_state's board / hist / moves therefore point at C allocations for the duration of the call).
+func cInts(v []int32) *C.int32_t {
+	if len(v) == 0 {
+		return nil
+	}
+	p := (*C.int32_t)(C.malloc(C.size_t(len(v)) * 4))
+	copy(unsafe.Slice((*int32)(unsafe.Pointer(p)), len(v)), v)
+	return p
+}
+
 // Search replaces Agent.Search (agent.go:77-80) on a caller-owned game.State (GTP / analysis): the position is
-// marshalled into an az_state (board colours, side to move, move number, passes, last move and up to 8 historical
-// boards for the 18-plane encoder) and searched on a fresh device tree for mcts.Config sims iterations (in rounds of
-// `Workers` concurrent descents).  Returns the chosen move and the visit counts of the root's children ([A] + pass).
-func (e *Engine) Search(agent int, s game.State, player game.Player, actionSpace int) (game.Single, []float32, error) {
+// marshalled into an az_state — board colours, side to move, move number, passes, last move, up to 8 historical boards
+// for the 18-plane encoder and the tail of the move history (what UndoLastMove / Fwd walk) — and searched for
+// mcts.Config sims iterations.  The agent's device tree survives the call and is re-rooted on the next position when
+// that continues this one (updateRoot, search.go:424-500); ResetTree is MCTS.Reset.  `history` = the state's
+// (player, move) list, oldest first (mnk: State keeps it; pass nil when unknown: every call then searches a fresh tree).
+// Returns the chosen move and the visit counts of the root's children ([A] + pass).
+func (e *Engine) Search(agent int, s game.State, player game.Player, actionSpace int, history []game.PlayerMove) (game.Single, []float32, error) {
 	raw := s.Board()
 	board := make([]int32, len(raw))
 	for i, c := range raw {
 		board[i] = int32(c)
 	}
-	var st C.az_state
-	st.board = (*C.int32_t)(unsafe.Pointer(&board[0]))
-	st.to_move, st.move_number, st.passes = C.int32_t(s.ToMove()), C.int32_t(s.MoveNumber()), C.int32_t(s.Passes())
-	st.last_move = C.int32_t(s.LastMove().Single)
 	nHist := s.MoveNumber()
 	if nHist > 8 {
 		nHist = 8
@@ -178,13 +190,55 @@ func (e *Engine) Search(agent int, s game.State, player game.Player, actionSpace
 			hist = append(hist, int32(c))
 		}
 	}
+	moves := make([]int32, 0, 2*len(history))
+	for _, pm := range history {
+		moves = append(moves, int32(pm.Player), int32(pm.Single))
+	}
+	var st C.az_state // holds C pointers only
+	st.board = cInts(board)
+	defer C.free(unsafe.Pointer(st.board))
+	st.to_move, st.move_number, st.passes = C.int32_t(s.ToMove()), C.int32_t(s.MoveNumber()), C.int32_t(s.Passes())
+	st.last_move = C.int32_t(s.LastMove().Single)
 	if len(hist) == nHist*len(board) && nHist > 0 {
-		st.n_hist, st.hist = C.int32_t(nHist), (*C.int32_t)(unsafe.Pointer(&hist[0]))
+		st.n_hist, st.hist = C.int32_t(nHist), cInts(hist)
+		defer C.free(unsafe.Pointer(st.hist))
+	}
+	if len(moves) > 0 {
+		st.n_moves, st.moves = C.int32_t(len(history)), cInts(moves)
+		defer C.free(unsafe.Pointer(st.moves))
 	}
 	var best C.int32_t
 	visits := make([]float32, actionSpace+1)
 	err := check(e, C.az_search(e.h, C.int32_t(agent), &st, C.int32_t(player), &best, (*C.float)(unsafe.Pointer(&visits[0]))))
 	return game.Single(best), visits, err
+}
+
+// ResetTree replaces MCTS.Reset (tree.go:249-276) for the agent's external-search tree.
+func (e *Engine) ResetTree(agent int) error { return check(e, C.az_agent_reset_tree(e.h, C.int32_t(agent))) }
+
+// Begin / Step / Finish expose Arena.Play's loop (arena.go:80-179) ply by ply for n concurrent games, so that a Go
+// Arena can run its OutputEncoder between moves; GameRecord returns the moves of one of them.
+func (e *Engine) Begin(nGames int, record bool) error {
+	r := C.int32_t(0)
+	if record {
+		r = 1
+	}
+	return check(e, C.az_arena_begin(e.h, C.int32_t(nGames), r))
+}
+func (e *Engine) Step() (active int, err error) {
+	var n C.int32_t
+	err = check(e, C.az_arena_step(e.h, &n))
+	return int(n), err
+}
+func (e *Engine) Finish() error { return check(e, C.az_arena_finish(e.h)) }
+func (e *Engine) GameRecord(g, maxMoves int) (moves []int32, winner, aPlayer game.Player, err error) {
+	moves = make([]int32, maxMoves)
+	var n, w, ap, ne C.int32_t
+	err = check(e, C.az_game_record(e.h, C.int32_t(g), (*C.int32_t)(unsafe.Pointer(&moves[0])), C.int32_t(maxMoves), &n, &w, &ap, &ne))
+	if int(n) < maxMoves {
+		moves = moves[:int(n)]
+	}
+	return moves, game.Player(w), game.Player(ap), err
 }
 
 // CommInit joins the gradient all-reduce group of a multi-process Learn (one process per GPU): rank 0 obtains the id

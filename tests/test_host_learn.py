@@ -91,3 +91,46 @@ def test_cpp_host_learn_equals_python_host(oracle, tmp_path):
     for byte in p.tobytes():
         h = ((h ^ byte) * 16777619) & 0xFFFFFFFF
     assert out[-1].split()[1] == "%08x" % h
+
+
+def test_arena_play_hooks(oracle):
+    """(*Arena).Play(record, enc, aug): the OutputEncoder sees the MetaState after every move (arena.go:131-133) and the
+    Augmenter multiplies every kept example (arena.go:115-121); Config.Augmenter is applied by Learn's batched self-play."""
+    conf = _c1_conf(batch=20, sims=12)
+    az = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle, n_games=4, seed=8)
+    az.setupSelfPlay(0)
+
+    class Enc:
+        def __init__(self):
+            self.calls = []
+
+        def Encode(self, ms):
+            st = ms.State()
+            self.calls.append((ms.Name(), ms.Epoch(), ms.GameNumber(), st["move_number"], int((st["board"] != 0).sum())))
+
+        def Flush(self):
+            return None
+
+    def mirror(ex):  # a board symmetry: the kind of Augmenter the reference's README shows
+        b = ex.Board.reshape(2, 3, 3)[:, :, ::-1].reshape(-1).copy()
+        p = np.concatenate([ex.Policy[:9].reshape(3, 3)[:, ::-1].reshape(-1), ex.Policy[9:]])
+        return [ex, host.Example(b, p, ex.Value)]
+
+    enc = Enc()
+    winner, plain = az.Play(True, None, None)
+    az2 = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle, n_games=4, seed=8)
+    az2.setupSelfPlay(0)
+    winner2, aug = az2.Play(True, enc, mirror, game_number=3)
+    assert winner == K.NONE and winner2 == K.NONE                      # arena.go:178
+    n_moves = len(az2.engine.game_record(0)["moves"])
+    assert len(enc.calls) == n_moves and [c[3] for c in enc.calls] == list(range(1, n_moves + 1))
+    assert all(c[0] == "Tic Tac Toe" and c[2] == 3 for c in enc.calls) and [c[4] for c in enc.calls] == list(range(1, n_moves + 1))
+    assert len(aug) == 2 * len(plain) and len(plain) > 0
+    for i, x in enumerate(plain):
+        assert (aug[2 * i].Board == x.Board).all() and aug[2 * i].Value == x.Value
+        assert (aug[2 * i + 1].Board.reshape(2, 3, 3) == x.Board.reshape(2, 3, 3)[:, :, ::-1]).all()
+    # Config.Augmenter inside Learn's batched self-play
+    conf.Augmenter = mirror
+    az3 = host.AZ(host.Game(K.GAME_MNK, 3, 3, 3), conf, lib=oracle, n_games=4, seed=8)
+    az3.setupSelfPlay(0)
+    assert len(az3._play(1, True)) == len(aug)
