@@ -16,7 +16,7 @@ PASS, RESIGN = -1, -2
 GAME_MNK, GAME_C4, GAME_WQ = 0, 1, 2
 ENC_TWO_PLANE, ENC_WQ18 = 0, 1
 INF_DUAL, INF_DUMMY, INF_TABLE = 0, 1, 2
-FLAG_SHARED_TREE, FLAG_FP32_TOWER, FLAG_FAST_TOWER = 1, 2, 4
+FLAG_SHARED_TREE, FLAG_FP32_TOWER, FLAG_FAST_TOWER, FLAG_WQ_COMPLETE = 1, 2, 4, 8
 DONT_PREFER_PASS, PREFER_PASS, DONT_RESIGN = 0, 1, 2
 
 

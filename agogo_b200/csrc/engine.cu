@@ -253,6 +253,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     P.komi = gd.komi; P.max_moves = gd.max_moves; P.maxDepth = m.m * m.n; P.puct = m.puct; P.sims = m.sims;
     P.dont_prefer_pass = m.pass_preference == 0; P.dumb_pass = m.dumb_pass != 0; P.dont_resign = m.pass_preference == 2;
     P.resign_pct = m.resign_percentage;
+    P.wq_complete = (gd.kind == AZ_GAME_WQ && (desc->flags & AZ_FLAG_WQ_COMPLETE)) ? 1 : 0;
     P.random_count = m.random_count; P.random_min_visits = m.random_min_visits; P.random_temperature = m.random_temperature; P.shared_tree = (desc->flags & AZ_FLAG_SHARED_TREE) ? 1 : 0;
     P.encoder = desc->encoder; P.F = n.features; P.plane = n.features * P.cells;
     P.hist_len = desc->encoder == AZ_ENC_WQ18 ? 8 : 0;
@@ -741,6 +742,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : (P.kind == KIND_WQ ? st->passes : 0);
   gi[GI_C4_PASS] = P.kind == KIND_C4 ? st->passes : 0;
   gi[GI_ACTIVE] = 1; gi[GI_CUR_AGENT] = P.shared_tree ? 0 : agent; gi[GI_LAST_MOVE] = st->last_move;
+  gi[GI_KO] = -1;  // an external position carries no ko point
   gi[GI_A_PLAYER] = (P.shared_tree || agent == 0) ? player : opp_player;
   if (P.kind == KIND_WQ) {  // clean Zobrist hash of the position (wq/zobrist.go:44-56)
     std::vector<int32_t> zt((size_t)P.cells * 2);

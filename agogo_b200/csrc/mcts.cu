@@ -97,22 +97,23 @@ __device__ inline void encode_planes(const GameP& P, const uint8_t* board, const
 
 // ---------------------------------------------------------------------------------------------
 // State.Check / State.Apply on the warp's working state (board + ring in shared memory).
-struct St { int to_move, move_number, passes; };
+struct St { int to_move, move_number, passes; int ko = -1; };  // ko: AZ_FLAG_WQ_COMPLETE only (-1 = none)
 
 // warp-uniform move.  For wq the board analysis must be current when `analyzed` is true.
-__device__ inline bool state_check(const GameP& P, WS& w, int player, int move, int lane, bool* analyzed) {
+__device__ inline bool state_check(const GameP& P, WS& w, int player, int move, int lane, bool* analyzed, int ko = -1) {
   if (P.kind != KIND_WQ) return simple_check(P, w.board, move);
   if (move == MV_RESIGN || move == MV_PASS) return true;  // wq/game.go:66-71
   if (move >= P.cells || move < 0) return false;
   if (!*analyzed) { wq_analyze(P, w.board, w.wq, lane); *analyzed = true; }
   bool cap;
-  return wq_check_pt(P, w.board, w.wq, move, player, &cap);
+  return wq_check_pt(P, w.board, w.wq, move, player, &cap, ko);
 }
 
 // In-tree / root Apply of a move already known to pass Check (mnk.go:117-137, c4/game.go:55-72,
 // wq/game.go:81-92 + COMPLETION for pass/passes/historical).  zhash may be null (in-tree).
 __device__ inline void state_apply(const GameP& P, WS& w, int cellsP, St& s, int player, int move, int lane,
                                    bool* analyzed, int* zhash, const int* ztable) {
+  __syncwarp();  // every lane's State.Check read of the board is done before one lane writes the move (racecheck: WAR)
   if (P.kind == KIND_MNK) {
     if (lane == 0) w.board[move] = (uint8_t)player;
     s.to_move = opp(player);
@@ -133,10 +134,12 @@ __device__ inline void state_apply(const GameP& P, WS& w, int cellsP, St& s, int
     }
     if (move == MV_PASS) {
       s.passes++;
+      s.ko = -1;
     } else {
       if (!*analyzed) { wq_analyze(P, w.board, w.wq, lane); *analyzed = true; }
-      int taken;
-      wq_board_apply(P, w.board, w.wq, move, player, lane, &taken, zhash, ztable);  // error ignored (game.go:84)
+      int taken, nko = -1;
+      wq_board_apply(P, w.board, w.wq, move, player, lane, &taken, zhash, ztable, s.ko, &nko);  // error ignored (game.go:84)
+      s.ko = nko;
       s.passes = 0;
     }
     s.to_move = opp(player);
@@ -212,6 +215,7 @@ __global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __re
       gi[GI_TO_MOVE] = C_BLACK;  // SetToMove(currentPlayer.Player), arena.go:91
       gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : 0;
       gi[GI_LAST_MOVE] = MV_PASS;  // State.LastMove() of an empty history (mnk.go:84-89)
+      gi[GI_KO] = -1;
     }
   }
   __syncwarp();
@@ -353,6 +357,7 @@ __global__ void k_search_begin(GameP P, EngineDev E, int n_games) {
     for (int i = lane; i < P.cells; i += 32) lb[i] = w.board[i];
     if (lane == 0) {
       wv[WV_STATUS] = ST_LEAF; wv[WV_TO_MOVE] = player; wv[WV_MOVE_NUMBER] = mn; wv[WV_PASSES] = passes;
+      wv[WV_KO] = gi[GI_KO];
     }
     // planes are written after slots are known (k_encode_roots)
   } else {
@@ -422,6 +427,7 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
     s.to_move = gi[GI_TO_MOVE];
     s.move_number = gi[GI_MOVE_NUMBER];
     s.passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
+    s.ko = gi[GI_KO];
     int node = ti[TI_ROOT];
     int depth = 0, path_len = 0;
     int status = ST_DONE;
@@ -438,8 +444,9 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
       const uint32_t meta = E.meta[tb + node];
       if (!META_EXPANDED(meta)) {
         if (s.passes >= 2) {  // search.go:226-228: terminal by passes -> combinedScore (utils.go:62-67)
-          float ws_ = game_score(P, w.board, C_WHITE, lane);
-          float bs_ = game_score(P, w.board, C_BLACK, lane);
+          float ws_ = game_score(P, w.board, C_WHITE, lane, &w.wq);
+          float bs_ = game_score(P, w.board, C_BLACK, lane, &w.wq);
+          analyzed = false;
           float v = __fsub_rn(__fsub_rn(bs_, ws_), P.komi);
           __syncwarp();
           backup(E, tb, path, path_len, v, lane);
@@ -452,7 +459,7 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
             float* out = E.nn_in + ((size_t)agent * E.GS + slot0 + (size_t)wk * slot_stride) * P.plane;
             encode_planes(P, w.board, w.hist, E.cellsP, s.to_move, s.move_number, out, lane);
           }
-          if (lane == 0) { wv[WV_TO_MOVE] = s.to_move; wv[WV_MOVE_NUMBER] = s.move_number; wv[WV_PASSES] = s.passes; }
+          if (lane == 0) { wv[WV_TO_MOVE] = s.to_move; wv[WV_MOVE_NUMBER] = s.move_number; wv[WV_PASSES] = s.passes; wv[WV_KO] = s.ko; }
           status = ST_LEAF;
           is_null = false;
         }
@@ -513,7 +520,7 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
       if (besti == 0x7fffffff) { raise(E, ERR_NO_ACTIVE_CHILD, lane); break; }
       const int next = first + besti;
       const int move = META_MOVE(E.meta[tb + next]);
-      if (!state_check(P, w, player, move, lane, &analyzed)) break;  // illegal: null result, no retry
+      if (!state_check(P, w, player, move, lane, &analyzed, s.ko)) break;  // illegal: null result, no retry
       state_apply(P, w, E.cellsP, s, player, move, lane, &analyzed, nullptr, nullptr);
       node = next;
     }
@@ -598,7 +605,7 @@ __global__ void k_expand_backup(GameP P, EngineDev E, int n_games) {
     int i = base + lane;
     bool legal = false;
     if (i < P.A) {
-      if (P.kind == KIND_WQ) { bool cap; legal = wq_check_pt(P, w.board, w.wq, i, player, &cap); }
+      if (P.kind == KIND_WQ) { bool cap; legal = wq_check_pt(P, w.board, w.wq, i, player, &cap, wv[WV_KO]); }
       else legal = simple_check(P, w.board, i);
     }
     unsigned m = __ballot_sync(FULL, legal);
@@ -804,7 +811,7 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
         if (j < nc) {
           int mv = w.ib[j];
           if (mv != MV_PASS) {
-            if (P.kind == KIND_WQ) { bool cap; ok = (mv == MV_RESIGN) || (mv < P.cells && wq_check_pt(P, w.board, w.wq, mv, player, &cap)); }
+            if (P.kind == KIND_WQ) { bool cap; ok = (mv == MV_RESIGN) || (mv < P.cells && wq_check_pt(P, w.board, w.wq, mv, player, &cap, gi[GI_KO])); }
             else ok = simple_check(P, w.board, mv);
           }
         }
@@ -869,6 +876,7 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   St s;
   s.to_move = gi[GI_TO_MOVE]; s.move_number = gi[GI_MOVE_NUMBER];
   s.passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
+  s.ko = gi[GI_KO];
   int zhash = gi[GI_ZHASH];
   int c4pass = gi[GI_C4_PASS];
   int last_move = gi[GI_LAST_MOVE];  // State.LastMove(): the last entry State.Apply appended to history
@@ -901,7 +909,7 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   else if (P.max_moves > 0 && n_moves + 1 >= P.max_moves) active = false;  // COMPLETION: move cap
   else {
     int wn;
-    bool ended = game_ended(P, w.board, P.kind == KIND_C4 ? c4pass : s.passes, lane, &wn);
+    bool ended = game_ended(P, w.board, P.kind == KIND_C4 ? c4pass : s.passes, lane, &wn, &w.wq);
     winner = wn;
     active = !ended;
   }
@@ -912,7 +920,7 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
     E.moves[(size_t)g * P.max_plies + n_moves] = (int16_t)best;
     gi[GI_N_MOVES] = n_moves + 1;
     gi[GI_TO_MOVE] = s.to_move; gi[GI_MOVE_NUMBER] = s.move_number;
-    if (P.kind == KIND_WQ) gi[GI_PASSES] = s.passes;
+    if (P.kind == KIND_WQ) { gi[GI_PASSES] = s.passes; gi[GI_KO] = s.ko; }
     gi[GI_ZHASH] = zhash; gi[GI_C4_PASS] = c4pass; gi[GI_LAST_MOVE] = last_move;
     gi[GI_ARENA_PASS] = arena_pass;
     gi[GI_CUR_AGENT] ^= 1;  // switchPlayer
@@ -970,8 +978,8 @@ __global__ void k_rules_status(GameP P, int cellsP, int n, const int* __restrict
   for (int i = lane; i < P.cells; i += 32) w.board[i] = (uint8_t)boards[(size_t)q * P.cells + i];
   __syncwarp();
   int wn;
-  bool e = game_ended(P, w.board, passes[q], lane, &wn);
-  float b = game_score(P, w.board, C_BLACK, lane), wh = game_score(P, w.board, C_WHITE, lane);
+  bool e = game_ended(P, w.board, passes[q], lane, &wn, &w.wq);
+  float b = game_score(P, w.board, C_BLACK, lane, &w.wq), wh = game_score(P, w.board, C_WHITE, lane, &w.wq);
   if (lane == 0) { ended[q] = e; winner[q] = wn; sb[q] = b; sw[q] = wh; }
 }
 

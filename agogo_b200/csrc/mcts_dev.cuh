@@ -15,10 +15,10 @@
 #include "common.cuh"
 
 enum { GI_TO_MOVE, GI_MOVE_NUMBER, GI_PASSES, GI_ACTIVE, GI_WINNER, GI_ARENA_PASS, GI_A_PLAYER, GI_CUR_AGENT,
-       GI_N_MOVES, GI_ZHASH, GI_N_EX, GI_C4_PASS, GI_N_HMOVES, GI_LAST_MOVE, GI_COUNT = 16 };
+       GI_N_MOVES, GI_ZHASH, GI_N_EX, GI_C4_PASS, GI_N_HMOVES, GI_LAST_MOVE, GI_KO, GI_COUNT = 16 };
 enum { TI_ROOT, TI_ALLOC, TI_PREV_VALID, TI_PREV_MN, TI_NPOL, TI_RNG_LO, TI_RNG_HI, TI_COUNT = 8 };
 enum { WV_STATUS, WV_PATHLEN, WV_TO_MOVE, WV_MOVE_NUMBER, WV_PASSES, WV_SLOT, WV_AGENT, WV_FLAGS, WV_TREE,
-       WV_PLAYER, WV_HASH, WV_COUNT = 16 };
+       WV_PLAYER, WV_HASH, WV_KO, WV_COUNT = 16 };
 enum { ST_IDLE = 0, ST_LEAF = 1, ST_DONE = 2 };
 enum { INF_DUAL = 0, INF_DUMMY = 1, INF_TABLE = 2 };
 enum { CNT_SEARCHES, CNT_SIMS, CNT_NULL, CNT_EVALS, CNT_SEL_CHILDREN, CNT_SEL_LEVELS, CNT_CREATED, CNT_BACKUP,

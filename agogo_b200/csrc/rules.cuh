@@ -152,8 +152,27 @@ __device__ inline void wq_analyze(const GameP& P, const uint8_t* b, WqScratch s,
 // reference (Game.Check does not reject them, wq/game.go:65-79).  *captures_any tells whether
 // any neighbouring opponent group has no liberty other than p.
 __device__ inline bool wq_check_pt(const GameP& P, const uint8_t* b, WqScratch s, int p, int player,
-                                   bool* captures_any) {
+                                   bool* captures_any, int ko = -1) {
   const int size = P.m, o = opp(player);
+  if (P.wq_complete) {
+    // OUR completion (include/agogo_b200.h, AZ_FLAG_WQ_COMPLETE): occupied points, the ko point, suicide and the
+    // mover's own single-point eyes are illegal
+    *captures_any = false;
+    if (b[p] != C_NONE || p == ko) return false;
+    bool cap = false, empty_nbr = false, friend_safe = false, has_opp = false;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      int a = wq_nbr(size, p, d);
+      if (a < 0) continue;
+      if (b[a] == C_NONE) { empty_nbr = true; continue; }
+      const int libs = s.libcnt[s.label[a]];
+      if (b[a] == o) { has_opp = true; if (libs == 1) cap = true; }
+      else if (libs >= 2) friend_safe = true;
+    }
+    *captures_any = cap;
+    if (!empty_nbr && !has_opp) return false;  // own eye
+    return cap || empty_nbr || friend_safe;
+  }
   const int need = b[p] == C_NONE ? 1 : 0;  // p itself is a liberty of its neighbours iff it is empty
   bool cap = false, empty_nbr = false;
 #pragma unroll
@@ -176,21 +195,27 @@ __device__ inline bool wq_check_pt(const GameP& P, const uint8_t* b, WqScratch s
 // duplicates (a group adjacent to p through two neighbours is listed twice); *zhash is updated
 // with one XOR per listing when ztable != nullptr (zobrist.go:44-56).
 __device__ inline bool wq_board_apply(const GameP& P, uint8_t* b, WqScratch s, int p, int player, int lane,
-                                      int* taken, int* zhash, const int* __restrict__ ztable) {
+                                      int* taken, int* zhash, const int* __restrict__ ztable, int ko = -1,
+                                      int* ko_out = nullptr) {
   *taken = 0;
+  if (ko_out) *ko_out = -1;
   if (!(player == C_BLACK || player == C_WHITE)) return false;
   if (p >= P.cells || p < 0) return false;
   if (b[p] != C_NONE) return false;
   bool cap;
-  if (!wq_check_pt(P, b, s, p, player, &cap)) return false;
+  if (!wq_check_pt(P, b, s, p, player, &cap, ko)) return false;
   const int size = P.m, o = opp(player);
   int h = 0, tk = 0;
   if (ztable) h ^= ztable[p * 2 + (player == C_BLACK ? 0 : 1)];
   int groups[4];
+  bool lone = true;  // complete rules: no friendly and no empty neighbour -> after capturing one stone this is a ko
 #pragma unroll
   for (int d = 0; d < 4; d++) {
     int a = wq_nbr(size, p, d);
     groups[d] = (a >= 0 && b[a] == o && s.libcnt[s.label[a]] == 1) ? s.label[a] : -1;
+    if (a >= 0 && b[a] != o) lone = false;
+    if (P.wq_complete)  // each captured group once (the reference lists a group per neighbour through which it touches p)
+      for (int q = 0; q < d; q++) if (groups[q] == groups[d]) groups[d] = -1;
   }
   __syncwarp();
   int lh = 0;
@@ -211,7 +236,61 @@ __device__ inline bool wq_board_apply(const GameP& P, uint8_t* b, WqScratch s, i
   __syncwarp();
   if (zhash) *zhash ^= h ^ lh;
   *taken = tk;
+  if (P.wq_complete && ko_out && tk == 1 && lone) {
+#pragma unroll
+    for (int d = 0; d < 4; d++) if (groups[d] >= 0) *ko_out = groups[d];  // a one-stone group's label is its point
+  }
   return true;
+}
+
+// Area score (AZ_FLAG_WQ_COMPLETE): stones of the colour + empty regions whose border touches that colour only.  Whole
+// warp; clobbers the analysis scratch (label = empty-region ids, libcnt = border colour mask, gsize = region sizes).
+__device__ inline void wq_area_scores(const GameP& P, const uint8_t* b, WqScratch s, int lane, float* black, float* white) {
+  const int cells = P.cells, size = P.m;
+  for (int i = lane; i < cells; i += 32) { s.label[i] = b[i] ? -1 : i; s.libcnt[i] = 0; s.gsize[i] = 0; }
+  __syncwarp();
+  bool changed;
+  do {
+    changed = false;
+    for (int i = lane; i < cells; i += 32) {
+      if (b[i]) continue;
+      int l = s.label[i];
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        int j = wq_nbr(size, i, d);
+        if (j >= 0 && !b[j]) l = min(l, ((volatile int*)s.label)[j]);
+      }
+      l = min(l, ((volatile int*)s.label)[l]);
+      if (l < s.label[i]) { ((volatile int*)s.label)[i] = l; changed = true; }
+    }
+    changed = __any_sync(FULL, changed);
+    __syncwarp();
+  } while (changed);
+  int nb = 0, nw = 0;
+  for (int i = lane; i < cells; i += 32) {
+    if (b[i] == C_BLACK) nb++;
+    else if (b[i] == C_WHITE) nw++;
+    else {
+      int mask = 0;
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        int j = wq_nbr(size, i, d);
+        if (j >= 0 && b[j]) mask |= b[j] == C_BLACK ? 1 : 2;
+      }
+      atomicAdd(&s.gsize[s.label[i]], 1);
+      if (mask) atomicOr(&s.libcnt[s.label[i]], mask);
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < cells; i += 32)
+    if (!b[i] && s.label[i] == i) {
+      if (s.libcnt[i] == 1) nb += s.gsize[i];
+      else if (s.libcnt[i] == 2) nw += s.gsize[i];
+    }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) { nb += __shfl_xor_sync(FULL, nb, off); nw += __shfl_xor_sync(FULL, nw, off); }
+  *black = (float)nb; *white = (float)nw;
+  __syncwarp();
 }
 
 // Board.Score (wq.go:173-202): stones of the colour plus the empties its buggy flood fill reaches
@@ -237,8 +316,17 @@ __device__ inline float wq_score_seq(const GameP& P, const uint8_t* b, int colou
 // ------------------------------------------------------------------------------------------------
 // State.Ended (mnk.go:156-169, c4/game.go:161-179, wq/game.go:94-115).  `passes` is c4's
 // passCount or wq's passes.  Result broadcast to the warp.
-__device__ inline bool game_ended(const GameP& P, const uint8_t* b, int passes, int lane, int* winner) {
+__device__ inline bool game_ended(const GameP& P, const uint8_t* b, int passes, int lane, int* winner,
+                                  const WqScratch* sc = nullptr) {
   int e = 0, w = C_NONE;
+  if (P.kind == KIND_WQ && P.wq_complete) {  // area scores, komi to White (warp-wide; needs the scratch)
+    if (passes < 2) { *winner = C_NONE; return false; }
+    float bs, ws;
+    wq_area_scores(P, b, *sc, lane, &bs, &ws);
+    ws = __fadd_rn(ws, P.komi);
+    *winner = (ws == bs) ? C_NONE : (ws > bs ? C_WHITE : C_BLACK);
+    return true;
+  }
   if (lane == 0) {
     if (P.kind == KIND_MNK) {
       if (mnk_is_winner_seq(P, b, C_BLACK)) { e = 1; w = C_BLACK; }
@@ -269,8 +357,13 @@ __device__ inline bool game_ended(const GameP& P, const uint8_t* b, int passes, 
 }
 
 // State.Score (mnk.go:142-150, c4/game.go:74-83, wq Board.Score); one lane's result broadcast.
-__device__ inline float game_score(const GameP& P, const uint8_t* b, int player, int lane) {
+__device__ inline float game_score(const GameP& P, const uint8_t* b, int player, int lane, const WqScratch* scr = nullptr) {
   float sc = 0;
+  if (P.kind == KIND_WQ && P.wq_complete) {
+    float bs, ws;
+    wq_area_scores(P, b, *scr, lane, &bs, &ws);
+    return player == C_BLACK ? bs : ws;
+  }
   if (lane == 0) {
     if (P.kind == KIND_MNK) {
       if (mnk_is_winner_seq(P, b, player)) sc = 1;

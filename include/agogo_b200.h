@@ -104,6 +104,13 @@ typedef struct az_dual_config {
  * within 1.3e-5 on well-conditioned nets but up to 1.4e-4 on the reference's untamed init — outside the 1e-4 bar, hence
  * opt-in. */
 #define AZ_FLAG_FAST_TOWER 4u
+/* wq only — OUR completion of the reference's unfinished Go rules, off by default (the default
+ * keeps wq.Game exactly as written: occupied points "legal", no ko, the row-0 flood-fill Score).  With the flag:
+ * occupied points and true suicide are illegal, simple ko, own single-point eyes are never filled (the "eye-ish
+ * situations" noPass expects Check to reject, search.go:543), Score = area (stones + empty regions touching one colour
+ * only) and Ended adds komi to White.  Same arithmetic everywhere else; engine and oracle are compared bit for bit under
+ * the flag too. */
+#define AZ_FLAG_WQ_COMPLETE 8u
 
 typedef struct az_engine_desc {
   az_game_desc game;

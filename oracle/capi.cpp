@@ -39,11 +39,11 @@ struct az_engine {
   mutable std::string err;
 };
 
-static State* make_state(const az_game_desc& g) {
+static State* make_state(const az_game_desc& g, uint32_t flags = 0) {
   switch (g.kind) {
     case AZ_GAME_MNK: return new MNK(g.m, g.n, g.k);
     case AZ_GAME_C4: return new C4(g.m, g.n, g.k);
-    case AZ_GAME_WQ: return new WQ(g.m, 0, g.komi, g.zobrist_seed);
+    case AZ_GAME_WQ: { WQ* w = new WQ(g.m, 0, g.komi, g.zobrist_seed); w->complete = (flags & AZ_FLAG_WQ_COMPLETE) != 0; return w; }
   }
   throw std::runtime_error("unknown game kind");
 }
@@ -75,7 +75,7 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     if (!e->dc.IsValid()) { g_create_error = "NNConf is not valid. Unable to proceed"; return AZ_ERR_INVALID; }
     if (!e->mc.IsValid()) { g_create_error = "MCTSConf is not valid. Unable to proceed"; return AZ_ERR_INVALID; }
     if (desc->n_games < 1) { g_create_error = "n_games must be >= 1"; return AZ_ERR_INVALID; }
-    std::unique_ptr<State> probe(make_state(desc->game));
+    std::unique_ptr<State> probe(make_state(desc->game, desc->flags));
     e->nets[0] = std::make_shared<Dual>(e->dc);
     e->nets[1] = std::make_shared<Dual>(e->dc);
     e->coin = Rng(derive_seed(desc->seed, 0));
@@ -131,7 +131,7 @@ int az_net_copy(az_engine* e, int32_t dst, int32_t src) {
 int az_agent_set_inferer(az_engine* e, int32_t agent, int32_t kind, int32_t dummy_player) {
   if (agent < 0 || agent > 1) return AZ_ERR_INVALID;
   GUARD_BEGIN
-  std::unique_ptr<State> probe(make_state(e->d.game));
+  std::unique_ptr<State> probe(make_state(e->d.game, e->d.flags));
   if (kind == AZ_INF_DUAL) e->inferers[agent] = std::make_shared<DualInferer>(*e->nets[agent]);
   else if (kind == AZ_INF_DUMMY) e->inferers[agent] = std::make_shared<DummyInferer>(probe->ActionSpace(), dummy_player);
   else if (kind == AZ_INF_TABLE) { if (!dynamic_cast<TableInferer*>(e->inferers[agent].get())) e->inferers[agent] = std::make_shared<TableInferer>(); }
@@ -187,7 +187,7 @@ int az_arena_begin(az_engine* e, int32_t n_games, int32_t record) {
   e->ext_valid[0] = e->ext_valid[1] = false;
   e->n_active_games = n_games; e->record = record != 0; e->in_play = true;
   for (int g = 0; g < n_games; g++) {
-    std::unique_ptr<Arena> a(new Arena(make_state(e->d.game), e->nets[0], e->nets[1], e->mc, e->d.encoder, e->d.seed));
+    std::unique_ptr<Arena> a(new Arena(make_state(e->d.game, e->d.flags), e->nets[0], e->nets[1], e->mc, e->d.encoder, e->d.seed));
     a->max_moves = e->d.game.max_moves;
     a->shared_tree = (e->d.flags & AZ_FLAG_SHARED_TREE) != 0;
     a->games = e->games_started++;
@@ -279,6 +279,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
     state.reset(t);
   } else {
     WQ* t = new WQ(g.m, 0, g.komi, g.zobrist_seed);
+    t->complete = (e->d.flags & AZ_FLAG_WQ_COMPLETE) != 0;  // (an external position carries no ko point)
     t->board.data.assign(st->board, st->board + cells);
     for (int i = 0; i < cells; i++) if (st->board[i]) t->board.zupdate(PlayerMove{st->board[i], (Single)i});  // clean hash
     t->nextToMove = st->to_move; t->passes = st->passes; t->moveCount = st->move_number;
@@ -416,8 +417,17 @@ int az_rules_apply(az_engine* e, int32_t n, const int32_t* boards, const int32_t
         memcpy(ob, s.data.data(), cells * 4);
       } else {
         WQ s(g.m, 0, g.komi, g.zobrist_seed); s.board.data.assign(b, b + cells);
+        s.complete = (e->d.flags & AZ_FLAG_WQ_COMPLETE) != 0;
         if (pm.single == PassMove) { check[i] = 1; applied[i] = 1; continue; }  // COMPLETION: pass is a board no-op
         if (pm.player == Black || pm.player == White) check[i] = s.Check(pm);
+        if (s.complete) {  // stateless: no ko point
+          std::vector<int> captured;
+          const bool ok = (pm.player == Black || pm.player == White) && pm.single >= 0 && pm.single < cells && s.completeCheck(pm, &captured, nullptr);
+          if (ok) { s.board.data[pm.single] = pm.player; for (int st : captured) s.board.data[st] = None; }
+          applied[i] = ok; taken[i] = ok ? (int32_t)captured.size() : 0;
+          memcpy(ob, s.board.data.data(), cells * 4);
+          continue;
+        }
         uint8_t t = 0;
         applied[i] = s.board.Apply(pm, &t);
         taken[i] = t;
@@ -436,7 +446,7 @@ int az_rules_status(az_engine* e, int32_t n, const int32_t* boards, const int32_
     std::unique_ptr<State> s;
     if (g.kind == AZ_GAME_MNK) { MNK* t = new MNK(g.m, g.n, g.k); t->board.assign(b, b + cells); s.reset(t); }
     else if (g.kind == AZ_GAME_C4) { C4* t = new C4(g.m, g.n, g.k); t->data.assign(b, b + cells); t->passCount = passes ? passes[i] : 0; s.reset(t); }
-    else { WQ* t = new WQ(g.m, 0, g.komi, g.zobrist_seed); t->board.data.assign(b, b + cells); t->passes = passes ? passes[i] : 0; s.reset(t); }
+    else { WQ* t = new WQ(g.m, 0, g.komi, g.zobrist_seed); t->complete = (e->d.flags & AZ_FLAG_WQ_COMPLETE) != 0; t->board.data.assign(b, b + cells); t->passes = passes ? passes[i] : 0; s.reset(t); }
     Player w = None;
     ended[i] = s->Ended(&w);
     winner[i] = w;
@@ -520,7 +530,7 @@ int azo_learn(const az_engine_desc* desc, double update_threshold, int32_t max_e
   if (rc) return rc;
   try {
     AZConfig c; c.nn = e->dc; c.mcts = e->mc; c.UpdateThreshold = update_threshold; c.MaxExamples = max_examples; c.enc = desc->encoder;
-    AZ az(make_state(desc->game), c, desc->seed);
+    AZ az(make_state(desc->game, desc->flags), c, desc->seed);
     az.arena->max_moves = desc->game.max_moves;
     az.Learn(iters, episodes, nniters, arena_games);
     for (size_t i = 0; i < az.log.size(); i++) {

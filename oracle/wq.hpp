@@ -8,6 +8,8 @@
 // minimal completion (documented in DESIGN.md §wq-gap), switchable only there; everything else
 // follows the reference line by line.
 #pragma once
+#include <algorithm>
+
 #include "game.hpp"
 #include "rng.hpp"
 
@@ -152,6 +154,12 @@ struct WQ : State {
   int moveCount = 0, passes = 0, histPtr = 0, handicap = 0;
   uint8_t captures[2] = {0, 0};
   bool ends = false;
+  // AZ_FLAG_WQ_COMPLETE (OURS, not the reference's: SURVEY §8f row 4): real Go rules instead of the reference's unfinished
+  // ones — occupied points and true suicide are illegal, simple ko (the point of a single stone just captured by a lone
+  // stone left with that single liberty may not be retaken immediately), own single-point eyes are never filled (the
+  // "eye-ish situations" noPass expects Check to reject, search.go:543), area scoring with komi decides the winner.
+  bool complete = false;
+  int32_t ko = -1;
 
   WQ(int boardSize, int handicap_, double komi_, uint64_t zseed)
       : board(boardSize, zseed), komi((float)komi_), handicap(handicap_) {}
@@ -179,8 +187,81 @@ struct WQ : State {
     if (m.single == ResignMove) return true;
     if (m.single == PassMove) return true;
     if ((int)m.single >= (int)board.data.size()) return false;
+    if (complete) return completeCheck(m, nullptr, nullptr);
     std::vector<Single> caps;
     return board.check(m, &caps);
+  }
+
+  // ---- complete rules (OURS) ----
+  // the group of the stone at p and the number of its distinct liberties
+  void groupOf(int p, std::vector<int>* stones, int* libs) const {
+    const int size = board.size, colour = board.data[p];
+    std::vector<char> seen(board.data.size(), 0), libseen(board.data.size(), 0);
+    stones->assign(1, p); seen[p] = 1; *libs = 0;
+    for (size_t h = 0; h < stones->size(); h++) {
+      const int q = (*stones)[h], r = q / size, c = q % size;
+      const int nb[4] = {c + 1 < size ? q + 1 : -1, r + 1 < size ? q + size : -1, c > 0 ? q - 1 : -1, r > 0 ? q - size : -1};
+      for (int a : nb) {
+        if (a < 0) continue;
+        if (board.data[a] == None) { if (!libseen[a]) { libseen[a] = 1; (*libs)++; } }
+        else if (board.data[a] == colour && !seen[a]) { seen[a] = 1; stones->push_back(a); }
+      }
+    }
+  }
+  // legality of an on-board point; optionally the opponent stones it would capture (each once) and the ko point it creates
+  bool completeCheck(PlayerMove m, std::vector<int>* captured, int32_t* new_ko) const {
+    const int p = m.single, size = board.size;
+    if (captured) captured->clear();
+    if (new_ko) *new_ko = -1;
+    if (p < 0 || board.data[p] != None || p == ko) return false;
+    const int r = p / size, c = p % size;
+    const int nb[4] = {c + 1 < size ? p + 1 : -1, r + 1 < size ? p + size : -1, c > 0 ? p - 1 : -1, r > 0 ? p - size : -1};
+    const int opp = opponent(m.player);
+    bool cap = false, empty_nbr = false, friend_safe = false, has_opp = false, has_friend = false;
+    std::vector<int> caps;
+    for (int a : nb) {
+      if (a < 0) continue;
+      if (board.data[a] == None) { empty_nbr = true; continue; }
+      std::vector<int> g; int libs;
+      groupOf(a, &g, &libs);
+      if (board.data[a] == opp) {
+        has_opp = true;
+        if (libs == 1) {  // its only liberty is p
+          cap = true;
+          for (int st : g) if (std::find(caps.begin(), caps.end(), st) == caps.end()) caps.push_back(st);
+        }
+      } else {
+        has_friend = true;
+        if (libs >= 2) friend_safe = true;
+      }
+    }
+    if (!empty_nbr && !has_opp) return false;                 // own single-point eye (or a 1x1 board): never filled
+    if (!(cap || empty_nbr || friend_safe)) return false;     // suicide
+    if (captured) *captured = caps;
+    if (new_ko && caps.size() == 1 && !has_friend && !empty_nbr) *new_ko = caps[0];
+    return true;
+  }
+  float areaScore(Player player) const {  // Tromp-Taylor: stones + empty regions that touch only this colour
+    const int size = board.size, n = (int)board.data.size();
+    std::vector<char> seen(n, 0);
+    float total = 0;
+    for (int i = 0; i < n; i++) {
+      if (board.data[i] == player) { total++; continue; }
+      if (board.data[i] != None || seen[i]) continue;
+      std::vector<int> region{i}; seen[i] = 1;
+      int mask = 0;
+      for (size_t h = 0; h < region.size(); h++) {
+        const int q = region[h], r = q / size, c = q % size;
+        const int nb[4] = {c + 1 < size ? q + 1 : -1, r + 1 < size ? q + size : -1, c > 0 ? q - 1 : -1, r > 0 ? q - size : -1};
+        for (int a : nb) {
+          if (a < 0) continue;
+          if (board.data[a] == None) { if (!seen[a]) { seen[a] = 1; region.push_back(a); } }
+          else mask |= board.data[a] == Black ? 1 : 2;
+        }
+      }
+      if (mask == (player == Black ? 1 : 2)) total += (float)region.size();
+    }
+    return total;
   }
 
   State* Apply(PlayerMove m) override {  // game.go:81-92 — clones; Board.Apply's error is ignored
@@ -193,6 +274,17 @@ struct WQ : State {
     uint8_t caps = 0;
     if (m.single == PassMove) {
       ns->passes = passes + 1;  // COMPLETION: reference would panic on data[-1]
+      ns->ko = -1;
+    } else if (complete) {
+      std::vector<int> captured; int32_t nk = -1;
+      if ((int)m.single < (int)board.data.size() && completeCheck(m, &captured, &nk)) {
+        ns->board.data[m.single] = m.player;
+        ns->board.zupdate(m);
+        for (int st : captured) { ns->board.data[st] = None; ns->board.zupdate(PlayerMove{opponent(m.player), (Single)st}); }
+        caps = (uint8_t)captured.size();
+      }
+      ns->ko = nk;
+      ns->passes = 0;
     } else {
       ns->board.Apply(m, &caps);
       ns->passes = 0;           // COMPLETION: passes counts consecutive passes
@@ -212,6 +304,7 @@ struct WQ : State {
     if (ends) ended = true;
     if (!ended) { *winner = None; return false; }
     float whiteScore = Score(White), blackScore = Score(Black);
+    if (complete) whiteScore += komi;  // OURS: the reference compares the raw scores and leaves komi to combinedScore
     if (whiteScore == blackScore) *winner = None;
     else if (whiteScore > blackScore) *winner = White;
     else *winner = Black;
@@ -221,7 +314,7 @@ struct WQ : State {
   void Reset() override {  // COMPLETION (reference panics): back to New()'s state
     for (auto& c : board.data) c = None;
     board.hash = 0;  // wq.go:132-137
-    history.clear(); hist.reset();
+    history.clear(); hist.reset(); ko = -1;
     nextToMove = Black; moveCount = 0; passes = 0; histPtr = 0;
     captures[0] = captures[1] = 0; ends = false;
   }
@@ -248,7 +341,7 @@ struct WQ : State {
     return ns;
   }
 
-  float Score(Player p) const override { return board.Score(p); }  // COMPLETION: Board.Score as implemented
+  float Score(Player p) const override { return complete ? areaScore(p) : board.Score(p); }  // COMPLETION: Board.Score as implemented
   float AdditionalScore() const override { return komi; }
 };
 

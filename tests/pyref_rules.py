@@ -220,3 +220,74 @@ def wq_score(board, size, player):  # wq.go:173-202, as implemented
                 bd[a] = True
                 q.append(a)
     return reachable
+
+
+# ---- wq under AZ_FLAG_WQ_COMPLETE (OUR completion: include/agogo_b200.h) — a naive second statement of the rules ----
+def _adj4(size, p):
+    r, c = divmod(p, size)
+    return [p + 1 if c + 1 < size else None, p + size if r + 1 < size else None, p - 1 if c > 0 else None,
+            p - size if r > 0 else None]
+
+
+def _wq_group(board, size, p):
+    colour = board[p]
+    seen, stack, libs = {p}, [p], set()
+    while stack:
+        q = stack.pop()
+        for a in _adj4(size, q):
+            if a is None:
+                continue
+            if board[a] == 0:
+                libs.add(a)
+            elif board[a] == colour and a not in seen:
+                seen.add(a); stack.append(a)
+    return seen, libs
+
+
+def wq_complete_check(board, size, player, move, ko=-1):
+    """-> (legal, captured points (set), ko point the move creates or -1)"""
+    if move < 0 or move >= size * size or board[move] != 0 or move == ko:
+        return False, set(), -1
+    opp = 3 - player
+    nbrs = [a for a in _adj4(size, move) if a is not None]
+    captured = set()
+    for a in nbrs:
+        if board[a] == opp:
+            g, libs = _wq_group(board, size, a)
+            if libs == {move}:
+                captured |= g
+    trial = list(board)
+    trial[move] = player
+    for q in captured:
+        trial[q] = 0
+    _, libs = _wq_group(trial, size, move)
+    if not libs:
+        return False, set(), -1  # suicide
+    if all(board[a] == player for a in nbrs):
+        return False, set(), -1  # own single-point eye: never filled
+    mine, _ = _wq_group(trial, size, move)
+    new_ko = next(iter(captured)) if (len(captured) == 1 and len(mine) == 1 and len(libs) == 1) else -1
+    return True, captured, new_ko
+
+
+def wq_area_score(board, size, player):
+    total, seen = 0, set()
+    for i in range(size * size):
+        if board[i] == player:
+            total += 1
+        elif board[i] == 0 and i not in seen:
+            region, stack, colours = {i}, [i], set()
+            while stack:
+                q = stack.pop()
+                for a in _adj4(size, q):
+                    if a is None:
+                        continue
+                    if board[a] == 0:
+                        if a not in region:
+                            region.add(a); stack.append(a)
+                    else:
+                        colours.add(board[a])
+            seen |= region
+            if colours == {player}:
+                total += len(region)
+    return float(total)

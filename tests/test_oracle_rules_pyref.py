@@ -63,3 +63,40 @@ def test_wq_rules_vs_python(oracle, size):
     _, _, sb, sw = e.rules_status(base)
     for i, b in enumerate(base.tolist()):
         assert (float(sb[i]), float(sw[i])) == (R.wq_score(b, size, 1), R.wq_score(b, size, 2)), i
+
+
+def test_wq_complete_rules_oracle_vs_pyref(oracle):
+    """AZ_FLAG_WQ_COMPLETE (our completion of the reference's unfinished Go rules): legality of every point (occupied,
+    suicide, own-eye fill), captures and area scores of random 5x5 / 7x7 positions — oracle (group/liberty BFS) against
+    the naive trial-move restatement in pyref_rules.py."""
+    rng = np.random.default_rng(11)
+    for size in (5, 7):
+        d = K.make_desc(K.GAME_WQ, size, size, 0, komi=5.5, sims=1, n_games=1, flags=K.FLAG_WQ_COMPLETE,
+                        nn=H.tiny_nn(size, size, size * size + 1, features=2), encoder=K.ENC_TWO_PLANE)
+        e = oracle.create(d)
+        cells = size * size
+        for _ in range(40):
+            b = rng.choice([0, 1, 2], size=cells, p=[0.35, 0.33, 0.32]).astype(np.int32)
+            # drop dead groups so that the position is a possible Go position
+            for p in range(cells):
+                if b[p] and not R._wq_group(list(b), size, p)[1]:
+                    for q in R._wq_group(list(b), size, p)[0]:
+                        b[q] = 0
+            boards = np.repeat(b[None], 2 * cells, axis=0)
+            players = [1] * cells + [2] * cells
+            moves = list(range(cells)) * 2
+            check, applied, out, taken = e.rules_apply(boards, players, moves)
+            for i, (pl, mv) in enumerate(zip(players, moves)):
+                legal, captured, _ = R.wq_complete_check(list(b), size, pl, mv)
+                assert bool(check[i]) == legal and bool(applied[i]) == legal, (size, b.tolist(), pl, mv, check[i], legal)
+                if legal:
+                    want = list(b)
+                    want[mv] = pl
+                    for q in captured:
+                        want[q] = 0
+                    assert out[i].tolist() == want and taken[i] == len(captured)
+                else:
+                    assert out[i].tolist() == b.tolist()
+            _, _, sb, sw = e.rules_status(b[None], passes=[2])
+            assert sb[0] == R.wq_area_score(list(b), size, 1) and sw[0] == R.wq_area_score(list(b), size, 2)
+        e.close()
