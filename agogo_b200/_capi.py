@@ -49,7 +49,7 @@ class EngineDesc(C.Structure):
 class State(C.Structure):
     _fields_ = [("board", C.POINTER(C.c_int32)), ("to_move", C.c_int32), ("move_number", C.c_int32), ("passes", C.c_int32),
                 ("last_move", C.c_int32), ("n_hist", C.c_int32), ("hist", C.POINTER(C.c_int32)),
-                ("n_moves", C.c_int32), ("moves", C.POINTER(C.c_int32))]
+                ("n_moves", C.c_int32), ("moves", C.POINTER(C.c_int32)), ("ko", C.c_int32)]
 
 
 class Counters(C.Structure):
@@ -224,14 +224,14 @@ class Engine:
     def search_end(self):
         self._ck(self.lib.dll.az_search_end(self.h))
 
-    def search(self, agent, board, to_move, player, move_number=0, passes=0, hist=None, last_move=-1, moves=None):
+    def search(self, agent, board, to_move, player, move_number=0, passes=0, hist=None, last_move=-1, moves=None, ko=-1):
         """Agent.Search on an external position: returns (best move, visit counts by move, Pass last).  `moves` = the
         tail of the state's history as (player, move) pairs, oldest first (enables tree reuse across calls)."""
         board = np.ascontiguousarray(board, np.int32)
         hist = np.zeros((0, self.cells), np.int32) if hist is None else np.ascontiguousarray(hist, np.int32).reshape(-1, self.cells)
         mv = np.zeros((0, 2), np.int32) if moves is None else np.ascontiguousarray(moves, np.int32).reshape(-1, 2)
         st = State(_p(board, C.c_int32), to_move, move_number, passes, last_move, hist.shape[0], _p(hist, C.c_int32),
-                   mv.shape[0], _p(mv, C.c_int32))
+                   mv.shape[0], _p(mv, C.c_int32), ko)
         best = C.c_int32()
         visits = np.zeros(self.action_space + 1, np.float32)
         self._ck(self.lib.dll.az_search(self.h, agent, C.byref(st), player, C.byref(best), _p(visits, C.c_float)))

@@ -742,7 +742,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : (P.kind == KIND_WQ ? st->passes : 0);
   gi[GI_C4_PASS] = P.kind == KIND_C4 ? st->passes : 0;
   gi[GI_ACTIVE] = 1; gi[GI_CUR_AGENT] = P.shared_tree ? 0 : agent; gi[GI_LAST_MOVE] = st->last_move;
-  gi[GI_KO] = -1;  // an external position carries no ko point
+  gi[GI_KO] = P.wq_complete ? st->ko : -1;
   gi[GI_A_PLAYER] = (P.shared_tree || agent == 0) ? player : opp_player;
   if (P.kind == KIND_WQ) {  // clean Zobrist hash of the position (wq/zobrist.go:44-56)
     std::vector<int32_t> zt((size_t)P.cells * 2);
@@ -853,6 +853,7 @@ int az_game_state(const az_engine* ce, int32_t game, int32_t* board, int32_t cap
   if (passes) *passes = G[GI_PASSES];
   // Ended(): what Arena.Play's loop condition last saw
   if (ended) *ended = (!G[GI_ACTIVE] && G[GI_ARENA_PASS] < 2 && !(e->P.max_moves > 0 && G[GI_N_MOVES] >= e->P.max_moves)) ? 1 : 0;
+  if (ended && e->P.wq_complete && !G[GI_ACTIVE] && G[GI_ARENA_PASS] >= 2) *ended = 1;  // complete rules: two passes are scored
   if (winner) *winner = G[GI_WINNER];
   GUARD_END(e)
   return AZ_OK;

@@ -905,7 +905,10 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   const int n_moves = gi[GI_N_MOVES];
   int winner = gi[GI_WINNER];
   bool active = true;
-  if (arena_pass >= 2) active = false;             // arena.go:135-137
+  if (arena_pass >= 2) {                           // arena.go:135-137: break before Ended() is re-evaluated (winner stays None)
+    active = false;
+    if (P.wq_complete) { int wn; game_ended(P, w.board, 2, lane, &wn, &w.wq); winner = wn; }  // OUR complete rules: score it
+  }
   else if (P.max_moves > 0 && n_moves + 1 >= P.max_moves) active = false;  // COMPLETION: move cap
   else {
     int wn;

@@ -207,6 +207,7 @@ func (e *Engine) Search(agent int, s game.State, player game.Player, actionSpace
 		st.n_moves, st.moves = C.int32_t(len(history)), cInts(moves)
 		defer C.free(unsafe.Pointer(st.moves))
 	}
+	st.ko = -1 // simple ko is a property of OUR complete-rules mode; a reference game.State has none
 	var best C.int32_t
 	visits := make([]float32, actionSpace+1)
 	err := check(e, C.az_search(e.h, C.int32_t(agent), &st, C.int32_t(player), &best, (*C.float)(unsafe.Pointer(&visits[0]))))

@@ -194,6 +194,7 @@ typedef struct az_state {
   const int32_t* hist;  /* [n_hist][m*n], oldest first */
   int32_t n_moves;      /* entries of `moves` (0 = history unknown: no reuse across calls) */
   const int32_t* moves; /* [n_moves][2] = (player, move), oldest first: the tail of the State's history */
+  int32_t ko;           /* AZ_FLAG_WQ_COMPLETE only: the point barred by simple ko for the side to move, or -1 (0 is a point: set it) */
 } az_state;
 int az_search(az_engine* e, int32_t agent, const az_state* s, int32_t player, int32_t* best, float* child_visits);
 int az_agent_reset_tree(az_engine* e, int32_t agent);

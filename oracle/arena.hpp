@@ -179,7 +179,11 @@ struct Arena {
     game = apply_replace(game, PlayerMove{currentPlayer->player, best}, true);
     rec.moves.push_back(best);
     switchPlayer();
-    if (passCount >= 2) { active = false; lastEnded = false; return; }
+    if (passCount >= 2) {  // arena.go:135-137 breaks before the loop condition re-evaluates Ended(): the winner stays None
+      active = false; lastEnded = false;
+      if (game->CompleteRules()) lastEnded = game->Ended(&winner);  // OUR complete-rules mode: two passes end the game, score it
+      return;
+    }
     if (max_moves > 0 && (int)rec.moves.size() >= max_moves) { active = false; lastEnded = false; return; }  // COMPLETION
     lastEnded = game->Ended(&winner);
     active = !lastEnded;

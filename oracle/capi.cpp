@@ -279,7 +279,8 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
     state.reset(t);
   } else {
     WQ* t = new WQ(g.m, 0, g.komi, g.zobrist_seed);
-    t->complete = (e->d.flags & AZ_FLAG_WQ_COMPLETE) != 0;  // (an external position carries no ko point)
+    t->complete = (e->d.flags & AZ_FLAG_WQ_COMPLETE) != 0;
+    t->ko = t->complete ? st->ko : -1;
     t->board.data.assign(st->board, st->board + cells);
     for (int i = 0; i < cells; i++) if (st->board[i]) t->board.zupdate(PlayerMove{st->board[i], (Single)i});  // clean hash
     t->nextToMove = st->to_move; t->passes = st->passes; t->moveCount = st->move_number;

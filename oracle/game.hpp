@@ -59,6 +59,7 @@ struct State {
   virtual State* Clone() const = 0;
   // not part of the Go interface: true iff UndoLastMove/Fwd are usable (wq's panic).
   virtual bool SupportsUndo() const { return true; }
+  virtual bool CompleteRules() const { return false; }  // wq under AZ_FLAG_WQ_COMPLETE (OUR mode)
 };
 
 // Helper mirroring Go's `x = x.Apply(m).(game.State)`: returns the new pointer and frees the

@@ -319,6 +319,7 @@ struct WQ : State {
     captures[0] = captures[1] = 0; ends = false;
   }
   bool SupportsUndo() const override { return false; }
+  bool CompleteRules() const override { return complete; }
   void UndoLastMove() override { throw std::runtime_error("not implemented"); }  // game.go:119
   void Fwd() override { throw std::runtime_error("not implemented"); }           // game.go:121
 

@@ -722,3 +722,59 @@ def test_parity_wq_full_board_search(oracle, engine_lib, size, inferer, workers,
     assert c["select_children"] > 128 * c["select_levels"]  # the strided path really ran
     if temp:
         assert len({tuple(r["moves"]) for r in a["records"]}) >= 4
+
+
+def test_wq_complete_rules_vs_oracle(oracle, engine_lib):
+    """AZ_FLAG_WQ_COMPLETE (our completion of the Go rules): legality / captures of every point and area scores of random
+    7x7 positions, engine against oracle (the oracle is pinned against the naive Python restatement on CPU)."""
+    rng = np.random.default_rng(4)
+    def eng(lib):
+        d = K.make_desc(K.GAME_WQ, 7, 7, 0, komi=5.5, sims=1, n_games=1, flags=K.FLAG_WQ_COMPLETE,
+                        nn=H.tiny_nn(7, 7, 50, features=2), encoder=K.ENC_TWO_PLANE)
+        return lib.create(d)
+    eo, eg = eng(oracle), eng(engine_lib)
+    boards, players, moves = [], [], []
+    for _ in range(50):
+        b = rng.choice([0, 1, 2], size=49, p=[0.35, 0.33, 0.32]).astype(np.int32)
+        for mv in range(49):
+            boards.append(b); players.append(1 + (mv + len(boards)) % 2); moves.append(mv)
+    boards = np.array(boards, np.int32)
+    for x, y, name in zip(eo.rules_apply(boards, players, moves), eg.rules_apply(boards, players, moves), ("check", "applied", "boards", "taken")):
+        assert (x == y).all(), name
+    for x, y in zip(eo.rules_status(boards[::49], passes=[2] * 50), eg.rules_status(boards[::49], passes=[2] * 50)):
+        assert (x == y).all()
+
+
+@pytest.mark.parametrize("size,sims,plies,inferer,workers", [(5, 20, 90, "dummy", 1), (5, 24, 90, "table", 1), (9, 16, 60, "table", 1), (5, 24, 60, "table", 4)])
+def test_parity_wq_complete_arena(oracle, engine_lib, size, sims, plies, inferer, workers):
+    """Whole games under AZ_FLAG_WQ_COMPLETE with sampled play (captures, kos, eye-only endgames, two-pass endings scored
+    by area + komi): trees after every ply, moves, examples, labels and statistics bit-identical to the oracle."""
+    A1 = size * size + 1
+    def desc():
+        d = K.make_desc(K.GAME_WQ, size, size, 0, komi=5.5, sims=sims, n_games=8, seed=17, max_moves=plies, workers=workers,
+                        flags=K.FLAG_WQ_COMPLETE, nn=H.tiny_nn(size, size, A1, features=18))
+        d.mcts.random_count, d.mcts.random_temperature = plies, 1.0
+        return d
+    eo, eg = _pair(oracle, engine_lib, desc)
+    rng = np.random.default_rng(size)
+    table = rng.random((128, A1)).astype(np.float32)
+    table /= table.sum(axis=1, keepdims=True)
+    values = rng.uniform(0.05, 0.95, 128).astype(np.float32)
+    for e in (eo, eg):
+        if inferer == "dummy":
+            e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+        else:
+            e.set_table(0, table, values); e.set_table(1, table[::-1].copy(), values[::-1].copy())
+    a, b = H.play_and_collect(eo, 8), H.play_and_collect(eg, 8)
+    H.assert_same_run(a, b, "wq-complete-%d-%s" % (size, inferer))
+    assert len({tuple(r["moves"]) for r in a["records"]}) >= 4
+    assert any(r["winner"] != 0 for r in a["records"]) or size == 9
+
+
+def test_wq_complete_game_engine_vs_pyref(engine_lib):
+    from tests.test_oracle_rules_pyref import _complete_game_vs_pyref
+    kos = caps = 0
+    for seed in range(1, 6):
+        k, c, _ = _complete_game_vs_pyref(engine_lib, 5, 20, seed, 90)
+        kos += k; caps += c
+    assert caps > 10

@@ -100,3 +100,56 @@ def test_wq_complete_rules_oracle_vs_pyref(oracle):
             _, _, sb, sw = e.rules_status(b[None], passes=[2])
             assert sb[0] == R.wq_area_score(list(b), size, 1) and sw[0] == R.wq_area_score(list(b), size, 2)
         e.close()
+
+
+def _complete_game_vs_pyref(lib, size, sims, seed, max_moves):
+    """One Arena game under AZ_FLAG_WQ_COMPLETE: after every search the root's children must be exactly the legal moves
+    (+ Pass) of the Python restatement with its own ko tracking; returns how many kos and captures occurred."""
+    d = K.make_desc(K.GAME_WQ, size, size, 0, komi=5.5, sims=sims, n_games=1, seed=seed, max_moves=max_moves,
+                    flags=K.FLAG_WQ_COMPLETE, nn=H.tiny_nn(size, size, size * size + 1, features=18))
+    d.mcts.random_count, d.mcts.random_temperature = max_moves, 1.0   # sampled play: varied games with fights
+    e = lib.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    e.arena_begin(1, False)
+    board, ko, kos, caps = [0] * (size * size), -1, 0, 0
+    player = 1
+    n_act, ply = 1, 0
+    while n_act:
+        n_act = e.arena_step()
+        rec = e.game_record(0)
+        a_black = rec["a_player"] == 1
+        agent = 0 if (ply % 2 == 0) == a_black else 1
+        dump = e.tree_dump(0, agent)
+        kids = {int(r[1]) for r in dump if r[0] == 1}
+        legal = {p for p in range(size * size) if R.wq_complete_check(board, size, player, p, ko)[0]} | {K.PASS}
+        assert kids == legal, (ply, sorted(kids ^ legal), ko)
+        mv = int(rec["moves"][ply])
+        if mv == K.PASS:
+            ko = -1
+        else:
+            ok, captured, ko = R.wq_complete_check(board, size, player, mv, ko)
+            assert ok, (ply, mv)
+            board[mv] = player
+            for q in captured:
+                board[q] = 0
+            caps += len(captured)
+            kos += ko >= 0
+        assert e.game_state(0)["board"].tolist() == board, ply
+        player = 3 - player
+        ply += 1
+    st = e.game_state(0)
+    rec = e.game_record(0)
+    e.arena_finish()
+    if rec["moves"][-2:].tolist() == [K.PASS, K.PASS]:  # ended by two passes: area score + komi decides
+        sb, sw = R.wq_area_score(board, size, 1), R.wq_area_score(board, size, 2) + 5.5
+        assert e.game_record(0)["winner"] == (0 if sb == sw else (1 if sb > sw else 2))
+    e.close()
+    return kos, caps, ply
+
+
+def test_wq_complete_games_oracle_vs_pyref(oracle):
+    kos = caps = 0
+    for seed in range(1, 9):
+        k, c, plies = _complete_game_vs_pyref(oracle, 5, 20, seed, 90)
+        kos += k; caps += c
+    assert caps > 20 and kos > 0, (kos, caps)   # the games really fought (captures, at least one ko shape)
