@@ -825,6 +825,306 @@ k_conv3x3_tc2_halo(const __grid_constant__ CUtensorMap tmA16, const __grid_const
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
+// -------------------------------------------------------------------------------------------------
+// Small nets (K = 64, boards up to 10x10: BASELINE config C2): the WHOLE network of one leaf in one CTA, one launch per
+// agent per MCTS wave instead of pack + init conv + one launch per block + head convs + heads (12+ launches of ~17 us:
+// the C2 wave was launch-bound, profiles/r01_bench_c2.json).  A 3x3 convolution mixes board points of ONE sample only, so
+// a CTA can carry a sample through every layer without any grid-wide step:
+//   * the sample's activations (128 + 2*(Wp+1) zero-bordered positions x 64 channels, fp16 hi/lo planes, SWIZZLE_128B
+//     rows) live in shared memory for the whole network; the epilogue of layer l writes layer l+1's operand in place,
+//     in the layout TMA would have produced (16-byte chunk index XOR row & 7), and the nine taps are row-shifted
+//     descriptor views of that one tile (see the halo kernel above);
+//   * only the filters stream (TMA, 2-stage ring that runs ahead across layer boundaries); tcgen05.mma cta_group::1,
+//     M = 128 (all positions of the sample), N = 64 (init conv) / 128 (both branches of a block), three fp16 passes in
+//     the same order as the layered kernels — the accumulators are bit-identical to the per-layer path;
+//   * the last block's epilogue feeds the two 1x1 head convolutions straight from registers; policy / value linears,
+//     softmax and tanh run on the CTA's epilogue warps (same summation order as k_head_convs_nhwc / k_heads_tiled).
+// 40 KB of activations + a 3-stage filter ring (96 KB, runs ahead across layers and samples) + 64 KB of staging for the
+// per-(point, channel) BN affine: 128 KB per layer and sample, four times the activations themselves — each epilogue warp
+// streams its 32 KB share in 8 KB chunks (cp.async.bulk, issued while the tensor core still works on the layer), so the
+// epilogue reads shared memory instead of stalling on L2 (ncu of the first version: 70 % of samples in long-scoreboard stalls).
+constexpr int SN_HR = 160;                       // activation rows: halo + 128 + halo, halo = Wp + 1 <= 16
+constexpr int SN_ACT_BYTES = 2 * SN_HR * 128;    // hi + lo planes
+constexpr int SN_NST = 3;                        // filter stages (96 KB in flight)
+constexpr int SN_WST_BYTES = 2 * 128 * 64 * 2;   // filter stage: hi + lo tiles of 128 rows x 64 K
+constexpr int SN_EPI_WARPS = 8;                  // two epilogue warps per TMEM lane quadrant: 32 channels each
+constexpr int SN_THREADS = 64 + 32 * SN_EPI_WARPS;
+constexpr int SN_AFF_BYTES = SN_EPI_WARPS * 2 * 4096;  // per epilogue warp two 4 KB chunks of the layer's affine (8 channels x 32 rows x float4)
+constexpr int SN_SCRATCH = 16384;                // head-conv partial sums [128 rows][8 groups][3] + head vectors
+constexpr int SN_MAXL = 8;                       // init conv + up to 7 blocks
+__host__ __device__ constexpr int smem_bytes_small() { return SN_ACT_BYTES + SN_NST * SN_WST_BYTES + SN_AFF_BYTES + SN_SCRATCH + 1024 + 512; }
+
+struct SmallMaps { CUtensorMap hi[SN_MAXL], lo[SN_MAXL]; };
+struct SmallNetArgs {
+  const float* planes; const int* n_dev; int n_max;
+  int F, H, W, Wp, S, HW, A1, FC, nlayers /* init + blocks */, ldp;
+  float act_scale, inv_scale;
+  const float2* aff0;            // init layer {A', B}, laid out [row / 32][channel][row % 32] over the tile's 128 rows
+  const float* affq[SN_MAXL];    // blocks: {A'a, Ba, A'b, Bb}, same layout — a warp's load of one channel is 512 contiguous bytes
+  const float *wp, *gp, *bp, *wv, *gv, *bv;        // head convs (snapshot): filters [2][64] / [1][64], per-point gamma / beta
+  const float *pW, *pB, *vW, *vB, *voW, *voB;      // linears
+  float* policy; float* value; int* err;
+};
+__device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(32 * SN_EPI_WARPS) : "memory"); }
+
+__global__ void __launch_bounds__(SN_THREADS, 1)
+k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t act_hi = smem_base, act_lo = smem_base + SN_HR * 128;
+  const uint32_t w_smem = smem_base + SN_ACT_BYTES;
+  constexpr int AFF_OFF = SN_ACT_BYTES + SN_NST * SN_WST_BYTES;
+  float* scratch = (float*)(smem_al + AFF_OFF + SN_AFF_BYTES);
+  const uint32_t bars = smem_base + AFF_OFF + SN_AFF_BYTES + SN_SCRATCH;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + AFF_OFF + SN_AFF_BYTES + SN_SCRATCH + 448);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto wfull = [&](int s) { return bars + 8u * s; };
+  auto wempty = [&](int s) { return bars + 8u * (SN_NST + s); };
+  const uint32_t act_ready = bars + 8u * (2 * SN_NST), acc_full = bars + 8u * (2 * SN_NST + 1);
+  auto aff_bar = [&](int ew, int buf) { return bars + 8u * (2 * SN_NST + 2 + ew * 2 + buf); };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SN_NST; s++) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+    mbar_init(act_ready, 32 * SN_EPI_WARPS); mbar_init(acc_full, 1);
+    for (int i = 0; i < 2 * SN_EPI_WARPS; i++) mbar_init(aff_bar(i >> 1, i & 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  // zero the activation tile once: halo rows and the border positions stay zero for every sample and layer
+  for (int i = threadIdx.x; i < SN_ACT_BYTES / 16; i += SN_THREADS) reinterpret_cast<uint4*>(smem_al)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int n = min(*a.n_dev, a.n_max);
+  const int halo = a.Wp + 1;
+  const uint32_t my_samples = (int)blockIdx.x < n ? (uint32_t)((n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== filter producer: streams every layer's nine K blocks, ahead of the activations =====
+      uint32_t it = 0;
+      for (uint32_t sm = 0; sm < my_samples; sm++)
+        for (int l = 0; l < a.nlayers; l++) {
+          const uint32_t bytes = l == 0 ? 2u * 64u * 64u * 2u : (uint32_t)SN_WST_BYTES;  // init conv: 64 filter rows
+          for (int tap = 0; tap < 9; tap++, it++) {
+            const int s = (int)(it % SN_NST);
+            mbar_wait(wempty(s), ((it / SN_NST) & 1u) ^ 1u);
+            const uint32_t sb = w_smem + s * SN_WST_BYTES;
+            mbar_expect_tx(wfull(s), bytes);
+            tma_load_2d(sb, &maps.hi[l], wfull(s), tap * 64, 0);
+            tma_load_2d(sb + 128 * 64 * 2, &maps.lo[l], wfull(s), tap * 64, 0);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      uint32_t it = 0, lcount = 0;
+      for (uint32_t sm = 0; sm < my_samples; sm++)
+        for (int l = 0; l < a.nlayers; l++, lcount++) {
+          mbar_wait(act_ready, lcount & 1u);
+          tc_fence_after();
+          const uint32_t idesc = l == 0 ? make_idesc(BM, 64) : make_idesc(BM, 128);
+          for (int tap = 0; tap < 9; tap++, it++) {
+            const int s = (int)(it % SN_NST);
+            mbar_wait(wfull(s), (it / SN_NST) & 1u);
+            tc_fence_after();
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            const uint32_t j0 = (uint32_t)(halo + dy * a.Wp + dx);
+            const uint32_t sb = w_smem + s * SN_WST_BYTES;
+            const uint64_t dAh = make_desc_sw<64>(act_hi + j0 * 128u), dAl = make_desc_sw<64>(act_lo + j0 * 128u);
+            const uint64_t dBh = make_desc_sw<64>(sb), dBl = make_desc_sw<64>(sb + 128 * 64 * 2);
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              umma_f16(tmem_base, dAh + adv, dBh + adv, idesc, (tap | ks) ? 1u : 0u);
+              umma_f16(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
+              umma_f16(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
+            }
+            umma_commit(wempty(s));
+          }
+          umma_commit(acc_full);
+        }
+    }
+  } else {
+    // ===== epilogue warps: thread = (board position = TMEM lane, half of the channels) =====
+    const int ew = warp - 2;                        // 0..7
+    const int quad = warp & 3, half = ew >> 2;      // TMEM lane quadrant = warp % 4; channels [32 half, 32 half + 32)
+    const int r = quad * 32 + lane;                 // position inside the sample's tile
+    const int y = r / a.Wp, x = r - y * a.Wp;
+    const bool valid = r < a.S && y < a.H && x < a.W;
+    const int hw = y * a.W + x;
+    const uint32_t brow = (uint32_t)(halo + r);
+    uint8_t* row_hi = smem_al + (size_t)brow * 128;
+    uint8_t* row_lo = smem_al + (size_t)SN_HR * 128 + (size_t)brow * 128;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 32;
+    const int epi_tid = threadIdx.x - 64;           // 0..255
+    float* s_part = scratch;                        // [128 rows][8 channel groups][3]: head-conv partial sums
+    float* s_ph = scratch + 128 * 8 * 3;            // [2*HW]
+    float* s_vh = s_ph + 2 * a.HW;                  // [HW]
+    float* s_lg = s_vh + a.HW;                      // [A1]
+    float* s_hh = s_lg + a.A1;                      // [FC]
+    uint32_t lcount = 0, qq_issue = 0, qq_use = 0;  // affine chunks issued / consumed by this warp (4 per layer, 8 channels each)
+    bool overflow = false;
+    const uint32_t aff_buf = smem_base + AFF_OFF + ew * 8192;
+    const uint8_t* aff_ptr = smem_al + AFF_OFF + ew * 8192;
+    const uint32_t total_chunks = my_samples * (uint32_t)a.nlayers * 4u;
+    auto aff_issue = [&]() {  // next chunk of this warp's share: layer (qq / 4) % nlayers, channels 32 half + 8 (qq % 4) ...
+      if (qq_issue >= total_chunks) return;
+      const int l = (int)((qq_issue >> 2) % (uint32_t)a.nlayers), part = (int)(qq_issue & 3u);
+      const uint32_t bytes = l == 0 ? 2048u : 4096u;  // float2 / float4 per (channel, row)
+      if (lane == 0) {
+        const uint8_t* src = l == 0 ? reinterpret_cast<const uint8_t*>(a.aff0) : reinterpret_cast<const uint8_t*>(a.affq[l]);
+        src += ((size_t)quad * 64 + half * 32 + part * 8) * 32 * (l == 0 ? 8 : 16);
+        const uint32_t bar = aff_bar(ew, (int)(qq_issue & 1u));
+        mbar_expect_tx(bar, bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(aff_buf + (qq_issue & 1u) * 4096u), "l"(src), "r"(bytes), "r"(bar) : "memory");
+      }
+      qq_issue++;
+    };
+    aff_issue();
+    aff_issue();
+    for (uint32_t sm = 0; sm < my_samples; sm++) {
+      const int b = (int)blockIdx.x + (int)sm * (int)gridDim.x;
+      // ---- the encoder's planes -> first operand (k_pack_planes' arithmetic), channels F..63 zero
+      {
+#pragma unroll 1
+        for (int cc = half * 4; cc < half * 4 + 4; cc++) {
+          __align__(16) __half hi[8];
+          __align__(16) __half lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int c = cc * 8 + k;
+            const float v = (valid && c < a.F) ? a.planes[((size_t)b * a.F + c) * a.HW + hw] * a.act_scale : 0.0f;
+            const __half h = __float2half_rn(v);
+            hi[k] = h;
+            lo[k] = __float2half_rn(v - __half2float(h));
+          }
+          const uint32_t off = (uint32_t)((cc ^ (int)(brow & 7u)) << 4);
+          *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(act_ready);
+      }
+      for (int l = 0; l < a.nlayers; l++, lcount++) {
+        const bool last = l == a.nlayers - 1;
+        mbar_wait(acc_full, lcount & 1u);
+        tc_fence_after();
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row, ra);
+        if (l > 0) tmem_ld32(t_row + 64, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int sub = 0; sub < 4; sub++) {  // 8 channels = one affine chunk = one 16-byte operand chunk
+          __align__(16) __half hi[8];
+          __align__(16) __half lo[8];
+          const int cbase = half * 32 + sub * 8;
+          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+          mbar_wait(aff_bar(ew, (int)(qq_use & 1u)), (qq_use >> 1) & 1u);
+          const uint8_t* chunk = aff_ptr + (qq_use & 1u) * 4096u;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int i = sub * 8 + k, ch = cbase + k;
+            float v = 0.0f;
+            if (l == 0) {
+              const float2 fa = reinterpret_cast<const float2*>(chunk)[k * 32 + lane];
+              v = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
+            } else {
+              const float4 f = reinterpret_cast<const float4*>(chunk)[k * 32 + lane];
+              v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+            }
+            v = valid ? v * a.act_scale : 0.0f;
+            const __half h = __float2half_rn(v);
+            const float hf = __half2float(h);
+            overflow |= valid && !(fabsf(hf) <= 65504.0f);
+            const __half lw = __float2half_rn(v - hf);
+            hi[k] = h; lo[k] = lw;
+            if (last) {  // the 1x1 head convolutions read what the layered path would have stored: (hi + lo) / scale
+              const float vv = (hf + __half2float(lw)) * a.inv_scale;
+              a0 = fmaf(vv, __ldg(a.wp + ch), a0);
+              a1 = fmaf(vv, __ldg(a.wp + 64 + ch), a1);
+              a2 = fmaf(vv, __ldg(a.wv + ch), a2);
+            }
+          }
+          if (last) {
+            float* o = s_part + ((size_t)r * 8 + (cbase >> 3)) * 3;
+            o[0] = a0; o[1] = a1; o[2] = a2;
+          } else {
+            const uint32_t off = (uint32_t)(((cbase >> 3) ^ (int)(brow & 7u)) << 4);
+            *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
+          }
+          qq_use++;
+          __syncwarp();  // chunk consumed by every lane: refill its buffer with the chunk after next
+          aff_issue();
+        }
+        tc_fence_before();
+        if (!last) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(act_ready);
+        } else {
+          // ---- heads.  Head convs: the xor-shuffle tree of k_head_convs_nhwc over its lanes 0..7 (8 channels each)
+          bar_epi();
+          if (valid && half == 0) {
+            const float* q = s_part + (size_t)r * 24;
+            const float isd = 1.0f / sqrtf(1e-5f);
+            const float q0 = ((q[0] + q[12]) + (q[6] + q[18])) + ((q[3] + q[15]) + (q[9] + q[21]));
+            const float q1 = ((q[1] + q[13]) + (q[7] + q[19])) + ((q[4] + q[16]) + (q[10] + q[22]));
+            const float q2 = ((q[2] + q[14]) + (q[8] + q[20])) + ((q[5] + q[17]) + (q[11] + q[23]));
+            const float p0 = a.gp[hw] * (q0 * isd) + a.bp[hw];
+            const float p1 = a.gp[a.HW + hw] * (q1 * isd) + a.bp[a.HW + hw];
+            const float v0 = a.gv[hw] * (q2 * isd) + a.bv[hw];
+            s_ph[hw] = p0 > 0.0f ? p0 : 0.0f;
+            s_ph[a.HW + hw] = p1 > 0.0f ? p1 : 0.0f;
+            s_vh[hw] = v0 > 0.0f ? v0 : 0.0f;
+          }
+          bar_epi();
+          const int J2 = 2 * a.HW;
+          for (int o = epi_tid; o < a.A1 + a.FC; o += 32 * SN_EPI_WARPS) {   // k_heads_tiled: ascending-j fma chains
+            if (o < a.A1) {
+              float acc = 0.0f;
+#pragma unroll 27
+              for (int j = 0; j < J2; j++) acc = fmaf(s_ph[j], __ldg(a.pW + (size_t)j * a.A1 + o), acc);
+              s_lg[o] = expf(acc + a.pB[o]);
+            } else {
+              const int f = o - a.A1;
+              float acc = 0.0f;
+#pragma unroll 27
+              for (int j = 0; j < a.HW; j++) acc = fmaf(s_vh[j], __ldg(a.vW + (size_t)j * a.FC + f), acc);
+              const float v = acc + a.vB[f];
+              s_hh[f] = v > 0.0f ? v : 0.0f;
+            }
+          }
+          bar_epi();
+          if (epi_tid < 32) {
+            float sum = 0.0f, dot = 0.0f;
+            for (int o = lane; o < a.A1; o += 32) sum += s_lg[o];
+            for (int f = lane; f < a.FC; f += 32) dot = fmaf(s_hh[f], a.voW[f], dot);
+#pragma unroll
+            for (int off = 16; off; off >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, off); dot += __shfl_xor_sync(0xffffffffu, dot, off); }
+            for (int o = lane; o < a.A1; o += 32) a.policy[(size_t)b * a.ldp + o] = s_lg[o] / sum;
+            if (lane == 0) a.value[b] = tanhf(dot + a.voB[0]);
+          }
+          bar_epi();  // the scratch (and the activation tile) are free for the next sample
+        }
+      }
+    }
+    if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
 // (hi16, lo16) -> (e4m3(hi * 2^pa), e4m3(lo * 2^q)) for the rows a non-fp8 kernel produced (the init conv's output)
 __global__ void k_split_fp8(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t n, float scale_h8, float scale_l8,
                             uint8_t* h8, uint8_t* l8) {
@@ -911,6 +1211,7 @@ void tower_configure_device() {
   set_conv_attr<64, false, 32>();
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_f8, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes2()));
+  CUDA_CHECK(cudaFuncSetAttribute(k_net_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_small()));
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_halo<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
 }
@@ -948,6 +1249,7 @@ struct Layer {
   int aff_rows = 0;
   CUtensorMap mB_hi, mB_lo, mAff;
   CUtensorMap mB2_hi, mB2_lo;               // CTA-pair kernel: 128-row boxes (each CTA of the pair loads half of the N tile)
+  float* affs = nullptr;                    // k_net_small: the layer's affine as [4][64][32] x (float2 | float4), rows = tile positions
   // AZ_TC_FP8 experiment: e4m3(w_hi * 2^-q), e4m3(w_lo * 2^-pa), 64-byte-row boxes
   uint8_t *w_h8 = nullptr, *w_l8 = nullptr;
   CUtensorMap mB2_h8, mB2_l8;
@@ -961,6 +1263,7 @@ struct Impl {
   int pa = 0, q = 11;  // h8 = e5m2(hi16 * 2^pa), l8 = e5m2(lo * 2^q); filters (e4m3) carry the inverse factors
   int hrows = 0, halo = 0;                     // halo kernel: rows per activation stage, Wp + 1
   bool halo3 = false;                          // three fp16 passes on the halo pipeline (the fp32-faithful default)
+  bool small = false;                          // K = 64, board <= 10x10: the whole network in one kernel (k_net_small)
   CUtensorMap mXh_hi[2], mXh_lo[2], mXh_h8[2], mXh_l8[2];  // halo boxes {64 channels, hrows positions}
   uint8_t *x_h8[2] = {nullptr, nullptr}, *x_l8[2] = {nullptr, nullptr};
   CUtensorMap mX_h8[2], mX_l8[2];
@@ -1169,12 +1472,16 @@ void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2,
     }
     I->layers.push_back(L);
   }
+  I->small = d.K == 64 && !I->mode3d && I->S <= BM && d.W + 2 <= 16 && (int)I->layers.size() <= SN_MAXL && d.F <= 64 &&
+             128 * 8 * 3 + 3 * HW + d.A1 + d.FC <= SN_SCRATCH / 4;
+  if (const char* sn = getenv("AZ_TC_SMALLNET")) { if (sn[0] == '0') I->small = false; }  // A/B: the per-layer kernels
   CUDA_CHECK(cudaDeviceSynchronize());
 }
 
 int tc_tower_kernel_kind(const TcTower& t) {
   const Impl* I = (const Impl*)t.impl;
   if (!I) return -1;
+  if (I->small) return 5;
   if (I->fp8 == 2) return 3;
   if (I->fp8 == 1) return 2;
   if (I->halo3) return 4;
@@ -1186,7 +1493,7 @@ void tc_tower_free(TcTower& t) {
   if (!I) return;
   cudaFree(I->xin_hi); cudaFree(I->xin_lo);
   for (int i = 0; i < 2; i++) { cudaFree(I->x_hi[i]); cudaFree(I->x_lo[i]); }
-  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); cudaFree(L.affq); cudaFree(L.w_h8); cudaFree(L.w_l8); }
+  for (Layer& L : I->layers) { cudaFree(L.w_hi); cudaFree(L.w_lo); cudaFree(L.aff); cudaFree(L.affq); cudaFree(L.affs); cudaFree(L.w_h8); cudaFree(L.w_l8); }
   for (int i = 0; i < 2; i++) { cudaFree(I->x_h8[i]); cudaFree(I->x_l8[i]); }
   for (cudaEvent_t e : I->ev_pool) cudaEventDestroy(e);
   delete I;
@@ -1270,6 +1577,24 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
       }
       CUDA_CHECK(cudaMemcpy(L.affq, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
     }
+    if (I->small) {  // k_net_small: rows = the 128 positions of a sample's tile, [row / 32][channel][row % 32]
+      const int per = L.pair ? 4 : 2, Wp = d.W + 1;
+      std::vector<float> q((size_t)128 * 64 * per, 0.0f);
+      for (int r = 0; r < 128 && r < I->S; r++) {
+        const int y = r / Wp, x = r - y * Wp;
+        if (y >= d.H || x >= d.W) continue;
+        const int hw = y * d.W + x;
+        for (int ch = 0; ch < 64; ch++) {
+          float* o = q.data() + (((size_t)(r / 32) * 64 + ch) * 32 + (r % 32)) * per;
+          for (int br = 0; br < (L.pair ? 2 : 1); br++) {
+            o[2 * br] = h[u[br]->gamma + (size_t)ch * HW + hw] * fold;
+            o[2 * br + 1] = h[u[br]->beta + (size_t)ch * HW + hw];
+          }
+        }
+      }
+      if (!L.affs) CUDA_CHECK(cudaMalloc(&L.affs, q.size() * 4));
+      CUDA_CHECK(cudaMemcpy(L.affs, q.data(), q.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
   (void)NL;
   t.ready = true;
@@ -1283,6 +1608,32 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   const NetDims& d = I->d;
   const float scale = ldexpf(1.0f, I->ea);
   const size_t f0 = I->profile ? I->ev_get(st) : 0;
+  if (I->small) {  // the whole network of every leaf in one launch
+    SmallMaps maps;
+    SmallNetArgs a;
+    a.planes = planes; a.n_dev = n_dev; a.n_max = n_max;
+    a.F = d.F; a.H = d.H; a.W = d.W; a.Wp = d.W + 1; a.S = I->S; a.HW = d.HW(); a.A1 = d.A1; a.FC = d.FC;
+    a.nlayers = (int)I->layers.size(); a.ldp = ldp;
+    a.act_scale = scale; a.inv_scale = 1.0f / scale;
+    a.aff0 = reinterpret_cast<const float2*>(I->layers[0].affs);
+    for (int l = 0; l < SN_MAXL; l++) {
+      const Layer& Lr = I->layers[std::min<size_t>(l, I->layers.size() - 1)];
+      maps.hi[l] = Lr.mB_hi; maps.lo[l] = Lr.mB_lo;
+      a.affq[l] = l > 0 && l < a.nlayers ? Lr.affs : nullptr;
+    }
+    const SnapUnit& pu = s.units[1 + 2 * d.SharedLayers];
+    const SnapUnit& vu = s.units[2 + 2 * d.SharedLayers];
+    a.wp = s.d + pu.filter; a.gp = s.d + pu.gamma; a.bp = s.d + pu.beta;
+    a.wv = s.d + vu.filter; a.gv = s.d + vu.gamma; a.bv = s.d + vu.beta;
+    a.pW = s.d + s.pW; a.pB = s.d + s.pB; a.vW = s.d + s.vW; a.vB = s.d + s.vB; a.voW = s.d + s.voW; a.voB = s.d + s.voB;
+    a.policy = policy; a.value = value; a.err = err_flag;
+    const int grid = std::max(1, std::min(n_max, I->num_sms));
+    const size_t e0 = I->profile ? I->ev_get(st) : 0;
+    k_net_small<<<grid, SN_THREADS, smem_bytes_small(), st>>>(maps, a); LAUNCH_CHECK();
+    if (I->profile) { const size_t e1 = I->ev_get(st); I->conv_spans.push_back({e0, e1}); I->fwd_spans.push_back({f0, e1}); }
+    if (launches) (*launches)++;
+    return;
+  }
   {
     size_t total = (size_t)n_max * d.HW() * 64;
     k_pack_planes<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(planes, n_dev, n_max, d.F, d.H, d.W, 64, I->guard, I->S, scale,

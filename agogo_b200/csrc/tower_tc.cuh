@@ -13,7 +13,7 @@ bool tc_tower_supported(const NetDims& d);
 // operands) instead of fp16 — 2 tensor passes per MAC instead of 3; default false = fp32-faithful three fp16 passes
 void tc_tower_alloc(TcTower& t, const NetDims& d, int n_max, int act_scale_log2, bool fast);
 // 0: single-CTA kernel, 1: CTA-pair per-tap 3 x fp16, 2: CTA-pair per-tap FP8 corrections, 3: halo FP8 corrections,
-// 4: halo 3 x fp16 — which kernel runs the fused layers (bench labels)
+// 4: halo 3 x fp16, 5: the whole small net in one kernel (k_net_small) — which kernel runs the fused layers (bench labels)
 int tc_tower_kernel_kind(const TcTower& t);
 void tc_tower_free(TcTower& t);
 // split/scale/reorder the snapshot's filters and BN affines into the tensor-core operand layout

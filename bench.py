@@ -62,6 +62,9 @@ KERNELS = {
     4: ("k_conv3x3_tc2_halo<false> (CTA pair, activation halo tile + 9 row-shifted descriptor views, fp16 hi/lo 3-pass "
         "tcgen05)", 3.0,
         "fp32 semantics on fp16 tensor cores: hi/lo operand split, 3 tcgen05 passes, fp32 TMEM accumulate"),
+    5: ("k_net_small (whole 6 x 64 network of a leaf in one CTA: activations resident in shared memory, nine row-shifted "
+        "descriptor views per layer, filters streamed by TMA, fp16 hi/lo 3-pass tcgen05, heads fused)", 3.0,
+        "fp32 semantics on fp16 tensor cores: hi/lo operand split, 3 tcgen05 passes, fp32 TMEM accumulate"),
 }
 
 

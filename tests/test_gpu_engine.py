@@ -778,3 +778,32 @@ def test_wq_complete_game_engine_vs_pyref(engine_lib):
         k, c, _ = _complete_game_vs_pyref(engine_lib, 5, 20, seed, 90)
         kos += k; caps += c
     assert caps > 10
+
+
+@pytest.mark.parametrize("size,layers,n", [(9, 6, 37), (9, 1, 300), (5, 3, 5), (10, 2, 9)])
+def test_small_net_kernel_equals_layered_path(oracle, engine_lib, monkeypatch, size, layers, n):
+    """k_net_small (K = 64: the whole network of a leaf in one CTA, activations resident in shared memory) against the
+    per-layer kernels it replaces and against the oracle.  Same MMA sequence, same epilogue arithmetic, same head
+    summation order: the two device paths agree to the last bits; n > 2 x SMs exercises the persistent sample loop."""
+    A1 = size * size + 1
+    def desc():
+        return K.make_desc(K.GAME_WQ, size, size, 0, komi=7.5, sims=2, n_games=8, seed=2, max_moves=4,
+                           nn=dict(k=64, shared_layers=layers, fc=128, batch_size=2, features=18, action_space=A1))
+    planes = _wq_planes(np.random.default_rng(3), n, size)
+    eo = oracle.create(desc())
+    params = H.tame_gammas([eo], 0, 21)
+    eo.set_inferer(0, K.INF_DUAL)
+    po, vo = eo.infer(0, planes[:16])
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("AZ_TC_SMALLNET", mode)
+        e = engine_lib.create(desc())
+        e.net_set(0, params)
+        e.set_inferer(0, K.INF_DUAL)
+        outs[mode] = e.infer(0, planes)
+        e.close()
+    (p1, v1), (p0, v0) = outs["1"], outs["0"]
+    print("small vs layered: dp=%.3g dv=%.3g ; small vs oracle: dp=%.3g dv=%.3g" %
+          (np.abs(p1 - p0).max(), np.abs(v1 - v0).max(), np.abs(p1[:16] - po).max(), np.abs(v1[:16] - vo).max()))
+    assert np.abs(p1 - p0).max() <= 1e-7 and np.abs(v1 - v0).max() <= 1e-6
+    assert np.abs(p1[:16] - po).max() < 1e-4 and np.abs(v1[:16] - vo).max() < 1e-4
