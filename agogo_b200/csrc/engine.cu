@@ -56,6 +56,8 @@ struct az_engine {
   EngineDev E;  // device pointers
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                   // agent B's evaluation when both small-net towers fit the GPU side by side
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
   NetLayout L;
   float* net_params[2] = {nullptr, nullptr};  // train-form, device
@@ -212,6 +214,9 @@ void az_engine_destroy(az_engine* e) {
   if (e->h_ex_value) cudaFreeHost(e->h_ex_value);
   if (e->h_ex_valid) cudaFreeHost(e->h_ex_valid);
   if (e->h_small) cudaFreeHost(e->h_small);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -247,6 +252,9 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
     e->device = desc->device;
     CUDA_CHECK(cudaSetDevice(e->device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     GameP& P = e->P;
     P.kind = gd.kind; P.m = gd.m; P.n = gd.n; P.k = gd.k; P.cells = gd.m * gd.n;
     P.A = gd.kind == AZ_GAME_C4 ? gd.n : P.cells;
@@ -450,15 +458,16 @@ int az_agent_set_table(az_engine* e, int32_t agent, int32_t n_rows, int32_t row_
 }
 
 // forward of one agent's pending batch (count on device)
-static void run_forward(az_engine* e, int agent) {
+static void run_forward(az_engine* e, int agent, cudaStream_t st = nullptr) {
+  if (!st) st = e->stream;
   const EngineDev& E = e->E;
   if (E.inf[agent].kind != INF_DUAL) return;
   const float* in = E.nn_in + (size_t)agent * E.GS * e->P.plane;
   float* pol = E.policy + (size_t)agent * E.GS * E.Lmax;
   float* val = E.value + (size_t)agent * E.GS;
   const int* cnt = E.batch_count + agent;
-  if (e->use_tc) tc_tower_forward(e->tc[agent], e->L, e->snap[agent], e->fp32, in, cnt, E.GS, pol, E.Lmax, val, E.err, e->stream, &e->launches);
-  else forward_fp32(e->L, e->snap[agent], e->fp32, in, cnt, E.GS, pol, E.Lmax, val, e->stream, &e->launches);
+  if (e->use_tc) tc_tower_forward(e->tc[agent], e->L, e->snap[agent], e->fp32, in, cnt, E.GS, pol, E.Lmax, val, E.err, st, &e->launches);
+  else forward_fp32(e->L, e->snap[agent], e->fp32, in, cnt, E.GS, pol, E.Lmax, val, st, &e->launches);
 }
 
 int az_infer(az_engine* e, int32_t agent, const float* planes, int32_t n, float* policy, float* value) {
@@ -532,8 +541,21 @@ int az_arena_begin(az_engine* e, int32_t n_games, int32_t record) {
 
 static void eval_pending(az_engine* e) {
   launch_infer_simple(e->P, e->E, e->n_play, e->stream); e->launches++;
-  run_forward(e, 0);
-  if (!e->P.shared_tree) run_forward(e, 1);
+  // the whole-net kernel of a small tower keeps one sample pair per CTA: two agents' batches fit the SMs side by side
+  // (fork / join through events: also what the captured wave graph records); the fused head scratch is per tower
+  const bool side_by_side = !e->P.shared_tree && e->use_tc && e->E.inf[0].kind == INF_DUAL && e->E.inf[1].kind == INF_DUAL &&
+                            tc_tower_kernel_kind(e->tc[0]) == 5;
+  if (side_by_side) {
+    CUDA_CHECK(cudaEventRecord(e->ev_fork, e->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+    run_forward(e, 0);
+    run_forward(e, 1, e->stream2);
+    CUDA_CHECK(cudaEventRecord(e->ev_join, e->stream2));
+    CUDA_CHECK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+  } else {
+    run_forward(e, 0);
+    if (!e->P.shared_tree) run_forward(e, 1);
+  }
   launch_expand_backup(e->P, e->E, e->n_play, e->stream); e->launches++;
 }
 

@@ -844,15 +844,20 @@ k_conv3x3_tc2_halo(const __grid_constant__ CUtensorMap tmA16, const __grid_const
 // streams its 32 KB share in 8 KB chunks (cp.async.bulk, issued while the tensor core still works on the layer), so the
 // epilogue reads shared memory instead of stalling on L2 (ncu of the first version: 70 % of samples in long-scoreboard stalls).
 constexpr int SN_HR = 160;                       // activation rows: halo + 128 + halo, halo = Wp + 1 <= 16
-constexpr int SN_ACT_BYTES = 2 * SN_HR * 128;    // hi + lo planes
+constexpr int SN_SLOTS = 2;                      // samples a CTA carries at once, one layer phase apart (tensor core on one
+                                                 // while the epilogue warps finish the other's previous layer)
+constexpr int SN_ACT_BYTES = 2 * SN_HR * 128;    // hi + lo planes of one slot
 constexpr int SN_NST = 3;                        // filter stages (96 KB in flight)
 constexpr int SN_WST_BYTES = 2 * 128 * 64 * 2;   // filter stage: hi + lo tiles of 128 rows x 64 K
 constexpr int SN_EPI_WARPS = 8;                  // two epilogue warps per TMEM lane quadrant: 32 channels each
 constexpr int SN_THREADS = 64 + 32 * SN_EPI_WARPS;
-constexpr int SN_AFF_BYTES = SN_EPI_WARPS * 2 * 4096;  // per epilogue warp two 4 KB chunks of the layer's affine (8 channels x 32 rows x float4)
+constexpr int SN_CHUNK_CH = 4;                   // channels per staged affine chunk: 4 x 32 rows x float4 = 2 KB
+constexpr int SN_AFF_BYTES = SN_EPI_WARPS * 2 * 2048;
 constexpr int SN_SCRATCH = 16384;                // head-conv partial sums [128 rows][8 groups][3] + head vectors
 constexpr int SN_MAXL = 8;                       // init conv + up to 7 blocks
-__host__ __device__ constexpr int smem_bytes_small() { return SN_ACT_BYTES + SN_NST * SN_WST_BYTES + SN_AFF_BYTES + SN_SCRATCH + 1024 + 512; }
+__host__ __device__ constexpr int smem_bytes_small() {
+  return SN_SLOTS * SN_ACT_BYTES + SN_NST * SN_WST_BYTES + SN_AFF_BYTES + SN_SCRATCH + 1024 + 512;
+}
 
 struct SmallMaps { CUtensorMap hi[SN_MAXL], lo[SN_MAXL]; };
 struct SmallNetArgs {
@@ -867,34 +872,48 @@ struct SmallNetArgs {
 };
 __device__ __forceinline__ void bar_epi() { asm volatile("bar.sync 1, %0;" ::"n"(32 * SN_EPI_WARPS) : "memory"); }
 
+// Work items of a CTA, identical for the three roles: item w -> slot w & 1, step w >> 1 -> the slot's (step / nlayers)-th
+// sample = the CTA's sample number 2 (step / nlayers) + slot, layer step % nlayers.  Items of samples the CTA does not
+// have are skipped.
+struct SnItem { int slot, k, layer; bool exists; };
+__device__ __forceinline__ SnItem sn_item(uint32_t w, int nlayers, uint32_t my_samples) {
+  SnItem it;
+  it.slot = (int)(w & 1u);
+  const uint32_t step = w >> 1;
+  it.k = (int)(step / (uint32_t)nlayers) * 2 + it.slot;
+  it.layer = (int)(step % (uint32_t)nlayers);
+  it.exists = (uint32_t)it.k < my_samples;
+  return it;
+}
+
 __global__ void __launch_bounds__(SN_THREADS, 1)
 k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t act_hi = smem_base, act_lo = smem_base + SN_HR * 128;
-  const uint32_t w_smem = smem_base + SN_ACT_BYTES;
-  constexpr int AFF_OFF = SN_ACT_BYTES + SN_NST * SN_WST_BYTES;
+  const uint32_t w_smem = smem_base + SN_SLOTS * SN_ACT_BYTES;
+  constexpr int AFF_OFF = SN_SLOTS * SN_ACT_BYTES + SN_NST * SN_WST_BYTES;
   float* scratch = (float*)(smem_al + AFF_OFF + SN_AFF_BYTES);
   const uint32_t bars = smem_base + AFF_OFF + SN_AFF_BYTES + SN_SCRATCH;
   uint32_t* tmem_ptr_smem = (uint32_t*)(smem_al + AFF_OFF + SN_AFF_BYTES + SN_SCRATCH + 448);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto wfull = [&](int s) { return bars + 8u * s; };
   auto wempty = [&](int s) { return bars + 8u * (SN_NST + s); };
-  const uint32_t act_ready = bars + 8u * (2 * SN_NST), acc_full = bars + 8u * (2 * SN_NST + 1);
-  auto aff_bar = [&](int ew, int buf) { return bars + 8u * (2 * SN_NST + 2 + ew * 2 + buf); };
+  auto act_ready = [&](int slot) { return bars + 8u * (2 * SN_NST + slot); };
+  auto acc_full = [&](int slot) { return bars + 8u * (2 * SN_NST + 2 + slot); };
+  auto aff_bar = [&](int ew, int buf) { return bars + 8u * (2 * SN_NST + 4 + ew * 2 + buf); };
   if (threadIdx.x == 0) {
     for (int s = 0; s < SN_NST; s++) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
-    mbar_init(act_ready, 32 * SN_EPI_WARPS); mbar_init(acc_full, 1);
+    for (int sl = 0; sl < SN_SLOTS; sl++) { mbar_init(act_ready(sl), 32 * SN_EPI_WARPS); mbar_init(acc_full(sl), 1); }
     for (int i = 0; i < 2 * SN_EPI_WARPS; i++) mbar_init(aff_bar(i >> 1, i & 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(128));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  // zero the activation tile once: halo rows and the border positions stay zero for every sample and layer
-  for (int i = threadIdx.x; i < SN_ACT_BYTES / 16; i += SN_THREADS) reinterpret_cast<uint4*>(smem_al)[i] = make_uint4(0, 0, 0, 0);
+  // zero the activation tiles once: halo rows and the border positions stay zero for every sample and layer
+  for (int i = threadIdx.x; i < SN_SLOTS * SN_ACT_BYTES / 16; i += SN_THREADS) reinterpret_cast<uint4*>(smem_al)[i] = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
@@ -902,54 +921,65 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int n = min(*a.n_dev, a.n_max);
   const int halo = a.Wp + 1;
-  const uint32_t my_samples = (int)blockIdx.x < n ? (uint32_t)((n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) : 0u;
+  // effective grid: two samples per CTA (one per slot) whenever there are enough of them — the batch size is only known
+  // on the device, so the launch covers the SMs and the surplus CTAs leave at once
+  const int G = max(1, min((int)gridDim.x, (n + 1) / 2));
+  const uint32_t my_samples = (int)blockIdx.x < G && (int)blockIdx.x < n ? (uint32_t)((n - (int)blockIdx.x + G - 1) / G) : 0u;
+  const uint32_t n_items = 2u * (uint32_t)a.nlayers * ((my_samples + 1u) / 2u);
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== filter producer: streams every layer's nine K blocks, ahead of the activations =====
+      // ===== filter producer: streams every item's nine K blocks, ahead of the activations =====
       uint32_t it = 0;
-      for (uint32_t sm = 0; sm < my_samples; sm++)
-        for (int l = 0; l < a.nlayers; l++) {
-          const uint32_t bytes = l == 0 ? 2u * 64u * 64u * 2u : (uint32_t)SN_WST_BYTES;  // init conv: 64 filter rows
-          for (int tap = 0; tap < 9; tap++, it++) {
-            const int s = (int)(it % SN_NST);
-            mbar_wait(wempty(s), ((it / SN_NST) & 1u) ^ 1u);
-            const uint32_t sb = w_smem + s * SN_WST_BYTES;
-            mbar_expect_tx(wfull(s), bytes);
-            tma_load_2d(sb, &maps.hi[l], wfull(s), tap * 64, 0);
-            tma_load_2d(sb + 128 * 64 * 2, &maps.lo[l], wfull(s), tap * 64, 0);
-          }
+      for (uint32_t w = 0; w < n_items; w++) {
+        const SnItem wi = sn_item(w, a.nlayers, my_samples);
+        if (!wi.exists) continue;
+        const int l = wi.layer;
+        const uint32_t bytes = l == 0 ? 2u * 64u * 64u * 2u : (uint32_t)SN_WST_BYTES;  // init conv: 64 filter rows
+        for (int tap = 0; tap < 9; tap++, it++) {
+          const int s = (int)(it % SN_NST);
+          mbar_wait(wempty(s), ((it / SN_NST) & 1u) ^ 1u);
+          const uint32_t sb = w_smem + s * SN_WST_BYTES;
+          mbar_expect_tx(wfull(s), bytes);
+          tma_load_2d(sb, &maps.hi[l], wfull(s), tap * 64, 0);
+          tma_load_2d(sb + 128 * 64 * 2, &maps.lo[l], wfull(s), tap * 64, 0);
         }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer =====
-      uint32_t it = 0, lcount = 0;
-      for (uint32_t sm = 0; sm < my_samples; sm++)
-        for (int l = 0; l < a.nlayers; l++, lcount++) {
-          mbar_wait(act_ready, lcount & 1u);
+      // ===== MMA issuer: alternates between the two slots =====
+      uint32_t it = 0, cnt[SN_SLOTS] = {0, 0};
+      for (uint32_t w = 0; w < n_items; w++) {
+        const SnItem wi = sn_item(w, a.nlayers, my_samples);
+        if (!wi.exists) continue;
+        const int l = wi.layer, sl = wi.slot;
+        mbar_wait(act_ready(sl), cnt[sl] & 1u);
+        cnt[sl]++;
+        tc_fence_after();
+        const uint32_t idesc = l == 0 ? make_idesc(BM, 64) : make_idesc(BM, 128);
+        const uint32_t act_hi = smem_base + sl * SN_ACT_BYTES, act_lo = act_hi + SN_HR * 128;
+        const uint32_t d_tmem = tmem_base + sl * 128;
+        for (int tap = 0; tap < 9; tap++, it++) {
+          const int s = (int)(it % SN_NST);
+          mbar_wait(wfull(s), (it / SN_NST) & 1u);
           tc_fence_after();
-          const uint32_t idesc = l == 0 ? make_idesc(BM, 64) : make_idesc(BM, 128);
-          for (int tap = 0; tap < 9; tap++, it++) {
-            const int s = (int)(it % SN_NST);
-            mbar_wait(wfull(s), (it / SN_NST) & 1u);
-            tc_fence_after();
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            const uint32_t j0 = (uint32_t)(halo + dy * a.Wp + dx);
-            const uint32_t sb = w_smem + s * SN_WST_BYTES;
-            const uint64_t dAh = make_desc_sw<64>(act_hi + j0 * 128u), dAl = make_desc_sw<64>(act_lo + j0 * 128u);
-            const uint64_t dBh = make_desc_sw<64>(sb), dBl = make_desc_sw<64>(sb + 128 * 64 * 2);
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          const uint32_t j0 = (uint32_t)(halo + dy * a.Wp + dx);
+          const uint32_t sb = w_smem + s * SN_WST_BYTES;
+          const uint64_t dAh = make_desc_sw<64>(act_hi + j0 * 128u), dAl = make_desc_sw<64>(act_lo + j0 * 128u);
+          const uint64_t dBh = make_desc_sw<64>(sb), dBl = make_desc_sw<64>(sb + 128 * 64 * 2);
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-              const uint64_t adv = (uint64_t)(ks * 2);
-              umma_f16(tmem_base, dAh + adv, dBh + adv, idesc, (tap | ks) ? 1u : 0u);
-              umma_f16(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
-              umma_f16(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
-            }
-            umma_commit(wempty(s));
+          for (int ks = 0; ks < 4; ks++) {
+            const uint64_t adv = (uint64_t)(ks * 2);
+            umma_f16(d_tmem, dAh + adv, dBh + adv, idesc, (tap | ks) ? 1u : 0u);
+            umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
           }
-          umma_commit(acc_full);
+          umma_commit(wempty(s));
         }
+        umma_commit(acc_full(sl));
+      }
     }
   } else {
     // ===== epilogue warps: thread = (board position = TMEM lane, half of the channels) =====
@@ -960,84 +990,104 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
     const bool valid = r < a.S && y < a.H && x < a.W;
     const int hw = y * a.W + x;
     const uint32_t brow = (uint32_t)(halo + r);
-    uint8_t* row_hi = smem_al + (size_t)brow * 128;
-    uint8_t* row_lo = smem_al + (size_t)SN_HR * 128 + (size_t)brow * 128;
-    const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 32;
     const int epi_tid = threadIdx.x - 64;           // 0..255
     float* s_part = scratch;                        // [128 rows][8 channel groups][3]: head-conv partial sums
     float* s_ph = scratch + 128 * 8 * 3;            // [2*HW]
     float* s_vh = s_ph + 2 * a.HW;                  // [HW]
     float* s_lg = s_vh + a.HW;                      // [A1]
     float* s_hh = s_lg + a.A1;                      // [FC]
-    uint32_t lcount = 0, qq_issue = 0, qq_use = 0;  // affine chunks issued / consumed by this warp (4 per layer, 8 channels each)
     bool overflow = false;
-    const uint32_t aff_buf = smem_base + AFF_OFF + ew * 8192;
-    const uint8_t* aff_ptr = smem_al + AFF_OFF + ew * 8192;
-    const uint32_t total_chunks = my_samples * (uint32_t)a.nlayers * 4u;
-    auto aff_issue = [&]() {  // next chunk of this warp's share: layer (qq / 4) % nlayers, channels 32 half + 8 (qq % 4) ...
-      if (qq_issue >= total_chunks) return;
-      const int l = (int)((qq_issue >> 2) % (uint32_t)a.nlayers), part = (int)(qq_issue & 3u);
-      const uint32_t bytes = l == 0 ? 2048u : 4096u;  // float2 / float4 per (channel, row)
+    // ---- staged affine: chunks of 4 channels, consumed in item order; the issue cursor runs two chunks ahead
+    constexpr int CPL = 32 / SN_CHUNK_CH;           // chunks per layer for this warp
+    const uint32_t aff_buf = smem_base + AFF_OFF + ew * 4096;
+    const uint8_t* aff_ptr = smem_al + AFF_OFF + ew * 4096;
+    uint32_t qq_issue = 0, qq_use = 0, w_issue = 0;
+    int part_issue = 0;
+    while (w_issue < n_items && !sn_item(w_issue, a.nlayers, my_samples).exists) w_issue++;
+    auto aff_issue = [&]() {
+      if (w_issue >= n_items) return;
+      const int l = sn_item(w_issue, a.nlayers, my_samples).layer;
+      const uint32_t bytes = l == 0 ? 1024u : 2048u;  // float2 / float4 per (channel, row)
       if (lane == 0) {
         const uint8_t* src = l == 0 ? reinterpret_cast<const uint8_t*>(a.aff0) : reinterpret_cast<const uint8_t*>(a.affq[l]);
-        src += ((size_t)quad * 64 + half * 32 + part * 8) * 32 * (l == 0 ? 8 : 16);
+        src += ((size_t)quad * 64 + half * 32 + part_issue * SN_CHUNK_CH) * 32 * (l == 0 ? 8 : 16);
         const uint32_t bar = aff_bar(ew, (int)(qq_issue & 1u));
         mbar_expect_tx(bar, bytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(aff_buf + (qq_issue & 1u) * 4096u), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                     ::"r"(aff_buf + (qq_issue & 1u) * 2048u), "l"(src), "r"(bytes), "r"(bar) : "memory");
       }
       qq_issue++;
+      if (++part_issue == CPL) {
+        part_issue = 0;
+        w_issue++;
+        while (w_issue < n_items && !sn_item(w_issue, a.nlayers, my_samples).exists) w_issue++;
+      }
     };
     aff_issue();
     aff_issue();
-    for (uint32_t sm = 0; sm < my_samples; sm++) {
-      const int b = (int)blockIdx.x + (int)sm * (int)gridDim.x;
-      // ---- the encoder's planes -> first operand (k_pack_planes' arithmetic), channels F..63 zero
-      {
+    // the encoder's planes of the CTA's k-th sample -> the slot's first operand (k_pack_planes' arithmetic)
+    auto load_planes = [&](int k) {
+      const int sl = k & 1;
+      const int b = (int)blockIdx.x + k * G;
+      uint8_t* row_hi = smem_al + (size_t)sl * SN_ACT_BYTES + (size_t)brow * 128;
+      uint8_t* row_lo = row_hi + (size_t)SN_HR * 128;
 #pragma unroll 1
-        for (int cc = half * 4; cc < half * 4 + 4; cc++) {
-          __align__(16) __half hi[8];
-          __align__(16) __half lo[8];
+      for (int cc = half * 4; cc < half * 4 + 4; cc++) {
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const int c = cc * 8 + k;
-            const float v = (valid && c < a.F) ? a.planes[((size_t)b * a.F + c) * a.HW + hw] * a.act_scale : 0.0f;
-            const __half h = __float2half_rn(v);
-            hi[k] = h;
-            lo[k] = __float2half_rn(v - __half2float(h));
-          }
-          const uint32_t off = (uint32_t)((cc ^ (int)(brow & 7u)) << 4);
-          *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
+        for (int kk = 0; kk < 8; kk++) {
+          const int c = cc * 8 + kk;
+          const float v = (valid && c < a.F) ? a.planes[((size_t)b * a.F + c) * a.HW + hw] * a.act_scale : 0.0f;
+          const __half h = __float2half_rn(v);
+          hi[kk] = h;
+          lo[kk] = __float2half_rn(v - __half2float(h));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(act_ready);
+        const uint32_t off = (uint32_t)((cc ^ (int)(brow & 7u)) << 4);
+        *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
       }
-      for (int l = 0; l < a.nlayers; l++, lcount++) {
-        const bool last = l == a.nlayers - 1;
-        mbar_wait(acc_full, lcount & 1u);
-        tc_fence_after();
-        uint32_t ra[32], rb[32];
-        tmem_ld32(t_row, ra);
-        if (l > 0) tmem_ld32(t_row + 64, rb);
-        tmem_ld_wait();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(act_ready(sl));
+    };
+    if (my_samples > 0) load_planes(0);
+    if (my_samples > 1) load_planes(1);
+    uint32_t acnt[SN_SLOTS] = {0, 0};
+    for (uint32_t w = 0; w < n_items; w++) {
+      const SnItem wi = sn_item(w, a.nlayers, my_samples);
+      if (!wi.exists) continue;
+      const int l = wi.layer, sl = wi.slot;
+      const int b = (int)blockIdx.x + wi.k * G;
+      const bool last = l == a.nlayers - 1;
+      uint8_t* row_hi = smem_al + (size_t)sl * SN_ACT_BYTES + (size_t)brow * 128;
+      uint8_t* row_lo = row_hi + (size_t)SN_HR * 128;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + sl * 128 + half * 32;
+      mbar_wait(acc_full(sl), acnt[sl] & 1u);
+      acnt[sl]++;
+      tc_fence_after();
+      uint32_t ra[32], rb[32];
+      tmem_ld32(t_row, ra);
+      if (l > 0) tmem_ld32(t_row + 64, rb);
+      tmem_ld_wait();
 #pragma unroll
-        for (int sub = 0; sub < 4; sub++) {  // 8 channels = one affine chunk = one 16-byte operand chunk
-          __align__(16) __half hi[8];
-          __align__(16) __half lo[8];
-          const int cbase = half * 32 + sub * 8;
-          float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+      for (int sub = 0; sub < 4; sub++) {  // 8 channels = one 16-byte operand chunk = two staged affine chunks
+        __align__(16) __half hi[8];
+        __align__(16) __half lo[8];
+        const int cbase = half * 32 + sub * 8;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+        for (int hc = 0; hc < 2; hc++) {
           mbar_wait(aff_bar(ew, (int)(qq_use & 1u)), (qq_use >> 1) & 1u);
-          const uint8_t* chunk = aff_ptr + (qq_use & 1u) * 4096u;
+          const uint8_t* chunk = aff_ptr + (qq_use & 1u) * 2048u;
 #pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const int i = sub * 8 + k, ch = cbase + k;
+          for (int kk = 0; kk < 4; kk++) {
+            const int k = hc * 4 + kk, i = sub * 8 + k, ch = cbase + k;
             float v = 0.0f;
             if (l == 0) {
-              const float2 fa = reinterpret_cast<const float2*>(chunk)[k * 32 + lane];
+              const float2 fa = reinterpret_cast<const float2*>(chunk)[kk * 32 + lane];
               v = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
             } else {
-              const float4 f = reinterpret_cast<const float4*>(chunk)[k * 32 + lane];
+              const float4 f = reinterpret_cast<const float4*>(chunk)[kk * 32 + lane];
               v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
             }
             v = valid ? v * a.act_scale : 0.0f;
@@ -1053,67 +1103,68 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
               a2 = fmaf(vv, __ldg(a.wv + ch), a2);
             }
           }
-          if (last) {
-            float* o = s_part + ((size_t)r * 8 + (cbase >> 3)) * 3;
-            o[0] = a0; o[1] = a1; o[2] = a2;
-          } else {
-            const uint32_t off = (uint32_t)(((cbase >> 3) ^ (int)(brow & 7u)) << 4);
-            *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
-          }
           qq_use++;
           __syncwarp();  // chunk consumed by every lane: refill its buffer with the chunk after next
           aff_issue();
         }
-        tc_fence_before();
-        if (!last) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(act_ready);
+        if (last) {
+          float* o = s_part + ((size_t)r * 8 + (cbase >> 3)) * 3;
+          o[0] = a0; o[1] = a1; o[2] = a2;
         } else {
-          // ---- heads.  Head convs: the xor-shuffle tree of k_head_convs_nhwc over its lanes 0..7 (8 channels each)
-          bar_epi();
-          if (valid && half == 0) {
-            const float* q = s_part + (size_t)r * 24;
-            const float isd = 1.0f / sqrtf(1e-5f);
-            const float q0 = ((q[0] + q[12]) + (q[6] + q[18])) + ((q[3] + q[15]) + (q[9] + q[21]));
-            const float q1 = ((q[1] + q[13]) + (q[7] + q[19])) + ((q[4] + q[16]) + (q[10] + q[22]));
-            const float q2 = ((q[2] + q[14]) + (q[8] + q[20])) + ((q[5] + q[17]) + (q[11] + q[23]));
-            const float p0 = a.gp[hw] * (q0 * isd) + a.bp[hw];
-            const float p1 = a.gp[a.HW + hw] * (q1 * isd) + a.bp[a.HW + hw];
-            const float v0 = a.gv[hw] * (q2 * isd) + a.bv[hw];
-            s_ph[hw] = p0 > 0.0f ? p0 : 0.0f;
-            s_ph[a.HW + hw] = p1 > 0.0f ? p1 : 0.0f;
-            s_vh[hw] = v0 > 0.0f ? v0 : 0.0f;
-          }
-          bar_epi();
-          const int J2 = 2 * a.HW;
-          for (int o = epi_tid; o < a.A1 + a.FC; o += 32 * SN_EPI_WARPS) {   // k_heads_tiled: ascending-j fma chains
-            if (o < a.A1) {
-              float acc = 0.0f;
-#pragma unroll 27
-              for (int j = 0; j < J2; j++) acc = fmaf(s_ph[j], __ldg(a.pW + (size_t)j * a.A1 + o), acc);
-              s_lg[o] = expf(acc + a.pB[o]);
-            } else {
-              const int f = o - a.A1;
-              float acc = 0.0f;
-#pragma unroll 27
-              for (int j = 0; j < a.HW; j++) acc = fmaf(s_vh[j], __ldg(a.vW + (size_t)j * a.FC + f), acc);
-              const float v = acc + a.vB[f];
-              s_hh[f] = v > 0.0f ? v : 0.0f;
-            }
-          }
-          bar_epi();
-          if (epi_tid < 32) {
-            float sum = 0.0f, dot = 0.0f;
-            for (int o = lane; o < a.A1; o += 32) sum += s_lg[o];
-            for (int f = lane; f < a.FC; f += 32) dot = fmaf(s_hh[f], a.voW[f], dot);
-#pragma unroll
-            for (int off = 16; off; off >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, off); dot += __shfl_xor_sync(0xffffffffu, dot, off); }
-            for (int o = lane; o < a.A1; o += 32) a.policy[(size_t)b * a.ldp + o] = s_lg[o] / sum;
-            if (lane == 0) a.value[b] = tanhf(dot + a.voB[0]);
-          }
-          bar_epi();  // the scratch (and the activation tile) are free for the next sample
+          const uint32_t off = (uint32_t)(((cbase >> 3) ^ (int)(brow & 7u)) << 4);
+          *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
+          *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
         }
+      }
+      tc_fence_before();
+      if (!last) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(act_ready(sl));
+      } else {
+        // ---- heads.  Head convs: the xor-shuffle tree of k_head_convs_nhwc over its lanes 0..7 (8 channels each)
+        bar_epi();
+        if (valid && half == 0) {
+          const float* q = s_part + (size_t)r * 24;
+          const float isd = 1.0f / sqrtf(1e-5f);
+          const float q0 = ((q[0] + q[12]) + (q[6] + q[18])) + ((q[3] + q[15]) + (q[9] + q[21]));
+          const float q1 = ((q[1] + q[13]) + (q[7] + q[19])) + ((q[4] + q[16]) + (q[10] + q[22]));
+          const float q2 = ((q[2] + q[14]) + (q[8] + q[20])) + ((q[5] + q[17]) + (q[11] + q[23]));
+          const float p0 = a.gp[hw] * (q0 * isd) + a.bp[hw];
+          const float p1 = a.gp[a.HW + hw] * (q1 * isd) + a.bp[a.HW + hw];
+          const float v0 = a.gv[hw] * (q2 * isd) + a.bv[hw];
+          s_ph[hw] = p0 > 0.0f ? p0 : 0.0f;
+          s_ph[a.HW + hw] = p1 > 0.0f ? p1 : 0.0f;
+          s_vh[hw] = v0 > 0.0f ? v0 : 0.0f;
+        }
+        bar_epi();
+        const int J2 = 2 * a.HW;
+        for (int o = epi_tid; o < a.A1 + a.FC; o += 32 * SN_EPI_WARPS) {   // k_heads_tiled: ascending-j fma chains
+          if (o < a.A1) {
+            float acc = 0.0f;
+#pragma unroll 27
+            for (int j = 0; j < J2; j++) acc = fmaf(s_ph[j], __ldg(a.pW + (size_t)j * a.A1 + o), acc);
+            s_lg[o] = expf(acc + a.pB[o]);
+          } else {
+            const int f = o - a.A1;
+            float acc = 0.0f;
+#pragma unroll 27
+            for (int j = 0; j < a.HW; j++) acc = fmaf(s_vh[j], __ldg(a.vW + (size_t)j * a.FC + f), acc);
+            const float v = acc + a.vB[f];
+            s_hh[f] = v > 0.0f ? v : 0.0f;
+          }
+        }
+        bar_epi();
+        if (epi_tid < 32) {
+          float sum = 0.0f, dot = 0.0f;
+          for (int o = lane; o < a.A1; o += 32) sum += s_lg[o];
+          for (int f = lane; f < a.FC; f += 32) dot = fmaf(s_hh[f], a.voW[f], dot);
+#pragma unroll
+          for (int off = 16; off; off >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, off); dot += __shfl_xor_sync(0xffffffffu, dot, off); }
+          for (int o = lane; o < a.A1; o += 32) a.policy[(size_t)b * a.ldp + o] = s_lg[o] / sum;
+          if (lane == 0) a.value[b] = tanhf(dot + a.voB[0]);
+        }
+        bar_epi();  // the scratch is free for the other slot's heads
+        if ((uint32_t)(wi.k + 2) < my_samples) load_planes(wi.k + 2);  // the slot's next sample
       }
     }
     if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
@@ -1121,7 +1172,7 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
 }
 
@@ -1627,7 +1678,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
     a.wv = s.d + vu.filter; a.gv = s.d + vu.gamma; a.bv = s.d + vu.beta;
     a.pW = s.d + s.pW; a.pB = s.d + s.pB; a.vW = s.d + s.vW; a.vB = s.d + s.vB; a.voW = s.d + s.voW; a.voB = s.d + s.voB;
     a.policy = policy; a.value = value; a.err = err_flag;
-    const int grid = std::max(1, std::min(n_max, I->num_sms));
+    const int grid = std::max(1, std::min(n_max, I->num_sms));  // the kernel folds it to ceil(n / 2) CTAs from the device-side n
     const size_t e0 = I->profile ? I->ev_get(st) : 0;
     k_net_small<<<grid, SN_THREADS, smem_bytes_small(), st>>>(maps, a); LAUNCH_CHECK();
     if (I->profile) { const size_t e1 = I->ev_get(st); I->conv_spans.push_back({e0, e1}); I->fwd_spans.push_back({f0, e1}); }
