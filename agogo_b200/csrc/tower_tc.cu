@@ -886,7 +886,24 @@ __device__ __forceinline__ SnItem sn_item(uint32_t w, int nlayers, uint32_t my_s
   return it;
 }
 
-__global__ void __launch_bounds__(SN_THREADS, 1)
+// The filter stream is what the L2 has to feed: 32 KB per 768-clock K block per SM.  With 128 CTAs pipelined on two
+// samples each that is ~10 TB/s — the first pipelined version was bound by it (launch 122 us vs a 73 us MMA floor).  CTAs
+// therefore run as PAIRS (cluster of 2) on the same item sequence: rank 0 loads every stage's hi tile, rank 1 its lo tile,
+// each multicast into both CTAs' rings; a stage is refilled when both CTAs' tensor cores have consumed it (tcgen05.commit
+// multicast onto both empty barriers, count 2).  A pair whose CTAs own different sample counts pads the shorter one with
+// dummy items (zero input, nothing written).
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SN_THREADS, 1)
 k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -903,7 +920,7 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
   auto acc_full = [&](int slot) { return bars + 8u * (2 * SN_NST + 2 + slot); };
   auto aff_bar = [&](int ew, int buf) { return bars + 8u * (2 * SN_NST + 4 + ew * 2 + buf); };
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SN_NST; s++) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 1); }
+    for (int s = 0; s < SN_NST; s++) { mbar_init(wfull(s), 1); mbar_init(wempty(s), 2); }  // empty: both CTAs of the pair
     for (int sl = 0; sl < SN_SLOTS; sl++) { mbar_init(act_ready(sl), 32 * SN_EPI_WARPS); mbar_init(acc_full(sl), 1); }
     for (int i = 0; i < 2 * SN_EPI_WARPS; i++) mbar_init(aff_bar(i >> 1, i & 1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -917,14 +934,20 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const int n = min(*a.n_dev, a.n_max);
   const int halo = a.Wp + 1;
   // effective grid: two samples per CTA (one per slot) whenever there are enough of them — the batch size is only known
   // on the device, so the launch covers the SMs and the surplus CTAs leave at once
-  const int G = max(1, min((int)gridDim.x, (n + 1) / 2));
-  const uint32_t my_samples = (int)blockIdx.x < G && (int)blockIdx.x < n ? (uint32_t)((n - (int)blockIdx.x + G - 1) / G) : 0u;
+  const int G = max(2, min((int)gridDim.x, (((n + 1) / 2) + 1) & ~1));  // even: CTAs work in pairs
+  auto samples_of = [&](int x) { return x < G && x < n ? (uint32_t)((n - x + G - 1) / G) : 0u; };
+  const uint32_t real_samples = samples_of((int)blockIdx.x);
+  // both CTAs of a pair walk the same item sequence (they share the filter stream): the longer list, the shorter padded
+  const uint32_t my_samples = max(real_samples, samples_of((int)(blockIdx.x ^ 1u)));
   const uint32_t n_items = 2u * (uint32_t)a.nlayers * ((my_samples + 1u) / 2u);
 
   if (warp == 0) {
@@ -940,9 +963,9 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
           const int s = (int)(it % SN_NST);
           mbar_wait(wempty(s), ((it / SN_NST) & 1u) ^ 1u);
           const uint32_t sb = w_smem + s * SN_WST_BYTES;
-          mbar_expect_tx(wfull(s), bytes);
-          tma_load_2d(sb, &maps.hi[l], wfull(s), tap * 64, 0);
-          tma_load_2d(sb + 128 * 64 * 2, &maps.lo[l], wfull(s), tap * 64, 0);
+          mbar_expect_tx(wfull(s), bytes);  // own half + the peer's half, both land here
+          if (crank == 0) tma_load_2d_mc(sb, &maps.hi[l], wfull(s), tap * 64, 0, (uint16_t)3);
+          else tma_load_2d_mc(sb + 128 * 64 * 2, &maps.lo[l], wfull(s), tap * 64, 0, (uint16_t)3);
         }
       }
     }
@@ -976,7 +999,7 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
             umma_f16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
             umma_f16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
           }
-          umma_commit(wempty(s));
+          umma_commit_mc2(wempty(s));  // the stage is free once both CTAs of the pair have read it
         }
         umma_commit(acc_full(sl));
       }
@@ -996,7 +1019,8 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
     float* s_vh = s_ph + 2 * a.HW;                  // [HW]
     float* s_lg = s_vh + a.HW;                      // [A1]
     float* s_hh = s_lg + a.A1;                      // [FC]
-    bool overflow = false;
+    bool nanflag = false;
+    float amax = 0.0f;
     // ---- staged affine: chunks of 4 channels, consumed in item order; the issue cursor runs two chunks ahead
     constexpr int CPL = 32 / SN_CHUNK_CH;           // chunks per layer for this warp
     const uint32_t aff_buf = smem_base + AFF_OFF + ew * 4096;
@@ -1038,7 +1062,7 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
 #pragma unroll
         for (int kk = 0; kk < 8; kk++) {
           const int c = cc * 8 + kk;
-          const float v = (valid && c < a.F) ? a.planes[((size_t)b * a.F + c) * a.HW + hw] * a.act_scale : 0.0f;
+          const float v = (valid && c < a.F && (uint32_t)k < real_samples) ? a.planes[((size_t)b * a.F + c) * a.HW + hw] * a.act_scale : 0.0f;
           const __half h = __float2half_rn(v);
           hi[kk] = h;
           lo[kk] = __float2half_rn(v - __half2float(h));
@@ -1071,36 +1095,43 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
       tmem_ld_wait();
 #pragma unroll
       for (int sub = 0; sub < 4; sub++) {  // 8 channels = one 16-byte operand chunk = two staged affine chunks
-        __align__(16) __half hi[8];
-        __align__(16) __half lo[8];
+        __align__(16) __half2 hi2[4];
+        __align__(16) __half2 lo2[4];
         const int cbase = half * 32 + sub * 8;
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
 #pragma unroll
         for (int hc = 0; hc < 2; hc++) {
           mbar_wait(aff_bar(ew, (int)(qq_use & 1u)), (qq_use >> 1) & 1u);
           const uint8_t* chunk = aff_ptr + (qq_use & 1u) * 2048u;
+          float v[4];
 #pragma unroll
           for (int kk = 0; kk < 4; kk++) {
-            const int k = hc * 4 + kk, i = sub * 8 + k, ch = cbase + k;
-            float v = 0.0f;
+            const int i = sub * 8 + hc * 4 + kk;
+            // the staged affine already carries the activation scale 2^ea (exact) and is all-zero on border / padding
+            // rows, so neither a multiply nor a validity select is needed here
             if (l == 0) {
               const float2 fa = reinterpret_cast<const float2*>(chunk)[kk * 32 + lane];
-              v = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
+              v[kk] = fmaxf(fmaf(fa.x, __uint_as_float(ra[i]), fa.y), 0.0f);
             } else {
               const float4 f = reinterpret_cast<const float4*>(chunk)[kk * 32 + lane];
-              v = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
+              v[kk] = fmaxf(fmaf(f.x, __uint_as_float(ra[i]), f.y), 0.0f) + fmaxf(fmaf(f.z, __uint_as_float(rb[i]), f.w), 0.0f);
             }
-            v = valid ? v * a.act_scale : 0.0f;
-            const __half h = __float2half_rn(v);
-            const float hf = __half2float(h);
-            overflow |= valid && !(fabsf(hf) <= 65504.0f);
-            const __half lw = __float2half_rn(v - hf);
-            hi[k] = h; lo[k] = lw;
+            amax = fmaxf(amax, v[kk]);  // v >= 0; NaN / inf reach the overflow check through the fp16 conversion below
+          }
+#pragma unroll
+          for (int pr = 0; pr < 2; pr++) {
+            const __half2 h2 = __floats2half2_rn(v[2 * pr], v[2 * pr + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(v[2 * pr] - hf.x, v[2 * pr + 1] - hf.y);
+            hi2[hc * 2 + pr] = h2; lo2[hc * 2 + pr] = l2;
+            nanflag |= !(hf.x <= 65504.0f) || !(hf.y <= 65504.0f);
             if (last) {  // the 1x1 head convolutions read what the layered path would have stored: (hi + lo) / scale
-              const float vv = (hf + __half2float(lw)) * a.inv_scale;
-              a0 = fmaf(vv, __ldg(a.wp + ch), a0);
-              a1 = fmaf(vv, __ldg(a.wp + 64 + ch), a1);
-              a2 = fmaf(vv, __ldg(a.wv + ch), a2);
+              const float2 lf = __half22float2(l2);
+              const int ch = cbase + hc * 4 + 2 * pr;
+              const float vv0 = (hf.x + lf.x) * a.inv_scale, vv1 = (hf.y + lf.y) * a.inv_scale;
+              a0 = fmaf(vv0, __ldg(a.wp + ch), a0);      a0 = fmaf(vv1, __ldg(a.wp + ch + 1), a0);
+              a1 = fmaf(vv0, __ldg(a.wp + 64 + ch), a1); a1 = fmaf(vv1, __ldg(a.wp + 64 + ch + 1), a1);
+              a2 = fmaf(vv0, __ldg(a.wv + ch), a2);      a2 = fmaf(vv1, __ldg(a.wv + ch + 1), a2);
             }
           }
           qq_use++;
@@ -1112,8 +1143,8 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
           o[0] = a0; o[1] = a1; o[2] = a2;
         } else {
           const uint32_t off = (uint32_t)(((cbase >> 3) ^ (int)(brow & 7u)) << 4);
-          *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi);
-          *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo);
+          *reinterpret_cast<uint4*>(row_hi + off) = *reinterpret_cast<const uint4*>(hi2);
+          *reinterpret_cast<uint4*>(row_lo + off) = *reinterpret_cast<const uint4*>(lo2);
         }
       }
       tc_fence_before();
@@ -1154,7 +1185,7 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
           }
         }
         bar_epi();
-        if (epi_tid < 32) {
+        if (epi_tid < 32 && (uint32_t)wi.k < real_samples) {
           float sum = 0.0f, dot = 0.0f;
           for (int o = lane; o < a.A1; o += 32) sum += s_lg[o];
           for (int f = lane; f < a.FC; f += 32) dot = fmaf(s_hh[f], a.voW[f], dot);
@@ -1167,10 +1198,11 @@ k_net_small(const __grid_constant__ SmallMaps maps, SmallNetArgs a) {
         if ((uint32_t)(wi.k + 2) < my_samples) load_planes(wi.k + 2);  // the slot's next sample
       }
     }
-    if (overflow) atomicOr(a.err, ERR_ACT_OVERFLOW);
+    if (nanflag || !(amax <= 65504.0f)) atomicOr(a.err, ERR_ACT_OVERFLOW);
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still multicast into this CTA's ring or signal its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
@@ -1637,9 +1669,9 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
         const int hw = y * d.W + x;
         for (int ch = 0; ch < 64; ch++) {
           float* o = q.data() + (((size_t)(r / 32) * 64 + ch) * 32 + (r % 32)) * per;
-          for (int br = 0; br < (L.pair ? 2 : 1); br++) {
-            o[2 * br] = h[u[br]->gamma + (size_t)ch * HW + hw] * fold;
-            o[2 * br + 1] = h[u[br]->beta + (size_t)ch * HW + hw];
+          for (int br = 0; br < (L.pair ? 2 : 1); br++) {  // x 2^ea: relu(A'x + B) * s == relu(sA'x + sB) exactly for a power of two
+            o[2 * br] = ldexpf(h[u[br]->gamma + (size_t)ch * HW + hw] * fold, I->ea);
+            o[2 * br + 1] = ldexpf(h[u[br]->beta + (size_t)ch * HW + hw], I->ea);
           }
         }
       }
@@ -1678,7 +1710,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
     a.wv = s.d + vu.filter; a.gv = s.d + vu.gamma; a.bv = s.d + vu.beta;
     a.pW = s.d + s.pW; a.pB = s.d + s.pB; a.vW = s.d + s.vW; a.vB = s.d + s.vB; a.voW = s.d + s.voW; a.voB = s.d + s.voB;
     a.policy = policy; a.value = value; a.err = err_flag;
-    const int grid = std::max(1, std::min(n_max, I->num_sms));  // the kernel folds it to ceil(n / 2) CTAs from the device-side n
+    const int grid = std::max(2, std::min((n_max + 1) & ~1, I->num_sms & ~1));  // CTA pairs; the kernel folds it to ~n / 2 CTAs from the device-side n
     const size_t e0 = I->profile ? I->ev_get(st) : 0;
     k_net_small<<<grid, SN_THREADS, smem_bytes_small(), st>>>(maps, a); LAUNCH_CHECK();
     if (I->profile) { const size_t e1 = I->ev_get(st); I->conv_spans.push_back({e0, e1}); I->fwd_spans.push_back({f0, e1}); }
