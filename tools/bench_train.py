@@ -18,6 +18,7 @@ SHAPES = [
     ("C4 connect-4 (K=16, 6 blocks, batch 256)", K.GAME_C4, 6, 7, 4, dict(k=16, shared_layers=6, fc=32, batch_size=256, features=2, action_space=8)),
     ("C2 9x9 Go (K=64, 6 blocks, batch 256)", K.GAME_WQ, 9, 9, 0, dict(k=64, shared_layers=6, fc=128, batch_size=256, features=18, action_space=82)),
     ("C3/C5 19x19 Go (K=256, 20 blocks, batch 32)", K.GAME_WQ, 19, 19, 0, dict(k=256, shared_layers=20, fc=512, batch_size=32, features=18, action_space=362)),
+    ("C5 19x19 Go at DefaultConf batch (K=256, 20 blocks, batch 256)", K.GAME_WQ, 19, 19, 0, dict(k=256, shared_layers=20, fc=512, batch_size=256, features=18, action_space=362)),
 ]
 lib = K.load()
 ONLY = sys.argv[1] if len(sys.argv) > 1 else ""   # substring filter on the shape name (e.g. C3)
