@@ -219,12 +219,14 @@ def main():
         if os.environ.get("OMP_NUM_THREADS", "1") == "1":
             os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
         os.environ.setdefault("OMP_WAIT_POLICY", "passive")
-        r = cpu_reference_run(w, args.steps, warmup)
+        r = cpu_reference_run(w, args.steps, warmup, faithful=True)
         line = {"impl": "reference", "metric": "mcts_sims_per_sec", "value": r["value"], "unit": "sims/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": dict(config, step="one simulation of one game (bounded sample of the GPU arm's wave)"),
-                "cpu_baseline": {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "kind": "port",
+                "faithful_sims_per_sec": r.get("faithful_value"), "faithful_sample": r.get("faithful_sample"),
+                "cpu_baseline": {"value": r["value"], "unit": "sims/s", "cores": r["cores"], "nproc": r["nproc"], "threads": r["cores"],
+                                 "kind": "port", "useful_work_sims_per_sec": r["value"], "faithful_sims_per_sec": r.get("faithful_value"),
                                  "sample": "oracle (C++ restatement of mcts+dualnet), 1 game, %d pipeline iterations, "
                                            "1 leaf eval each at useful-work batch 1 (the reference pads every eval to "
                                            "ActionSpace=%d samples, meta.go:125-135: divide by that for its faithful rate)"
