@@ -280,7 +280,8 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant_
 }
 
 // -------------------------------------------------------------------------------------------------
-// EXPERIMENT (AZ_TC_FP8=1, not the product path; DESIGN.md §10, tools/precision_study_fp8.py): the CTA-pair layer with
+// Per-tap twin of the FP8-correction layer (AZ_TC_FP8=1: A/B against the halo kernel below, which is what AZ_FLAG_FAST_TOWER
+// runs; DESIGN.md §4 "Precision policy", tools/precision_study_fp8.py): the CTA-pair layer with
 // its two correction passes on the FP8 tensor path.  acc = hi16(x)·hi16(w)  [kind::f16]
 //                                                         + e4m3(hi·2^pa)·e4m3(w_lo·2^-pa) + e4m3(x_lo·2^q)·e4m3(w_hi·2^-q)  [kind::f8f6f4]
 // — every product carries the accumulator's scale, so the three kinds accumulate into the same fp32 TMEM tile.  FP8 MMAs
@@ -1299,7 +1300,7 @@ void tower_configure_device() {
   CUDA_CHECK(cudaFuncSetAttribute(k_conv3x3_tc2_halo<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_f8h(F8H_MAX_HROWS)));
 }
 
-// e4m3 operands (AZ_TC_FP8 experiment): [rows][cols] bytes, box {64 bytes, box_rows}, SWIZZLE_64B
+// 1-byte operands (FP8 correction passes): [rows][cols] bytes, box {64 bytes, box_rows}, SWIZZLE_64B
 CUtensorMap make_map_u8(void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   CUtensorMap m;
   cuuint64_t dims[2] = {cols, rows};
@@ -1333,7 +1334,7 @@ struct Layer {
   CUtensorMap mB_hi, mB_lo, mAff;
   CUtensorMap mB2_hi, mB2_lo;               // CTA-pair kernel: 128-row boxes (each CTA of the pair loads half of the N tile)
   float* affs = nullptr;                    // k_net_small: the layer's affine as [4][64][32] x (float2 | float4), rows = tile positions
-  // AZ_TC_FP8 experiment: e4m3(w_hi * 2^-q), e4m3(w_lo * 2^-pa), 64-byte-row boxes
+  // FP8 correction passes (AZ_FLAG_FAST_TOWER): e4m3(w_hi * 2^-q), e4m3(w_lo * 2^-pa), 64-byte-row boxes
   uint8_t *w_h8 = nullptr, *w_l8 = nullptr;
   CUtensorMap mB2_h8, mB2_l8;
 };
@@ -1341,7 +1342,7 @@ struct Impl {
   NetDims d;
   int n_max, ea, guard, S, rows_alloc, num_sms, passes = 3, mode3d = 0, tps = 1, bk = 64;
   int pair_clusters = 0;  // > 0: fused layers run on k_conv3x3_tc2 with this many co-resident CTA pairs
-  // AZ_TC_FP8=1 (experiment): correction passes on the FP8 tensor path; activations also travel as e4m3 h8 / l8
+  // correction passes on the FP8 tensor path (AZ_FLAG_FAST_TOWER); activations then also travel as e5m2 h8 / l8
   int fp8 = 0;         // 0: three fp16 passes; 1: per-tap FP8-correction kernel (A/B); 2: halo FP8-correction kernel (default)
   int pa = 0, q = 11;  // h8 = e5m2(hi16 * 2^pa), l8 = e5m2(lo * 2^q); filters (e4m3) carry the inverse factors
   int hrows = 0, halo = 0;                     // halo kernel: rows per activation stage, Wp + 1
@@ -1606,7 +1607,7 @@ void tc_tower_prepare(TcTower& t, const NetLayout& NL, const Snapshot& s, cudaSt
       for (size_t i = 0; i < (size_t)K * ci_real * 9; i++) mx = std::max(mx, std::fabs(f[i]));
     }
     int ew = 0;
-    const bool f8 = I->fp8 && L.pair && L.bn == 256;  // experiment: hi parts up at [2^13, 2^14) so that the e4m3 copies keep bits
+    const bool f8 = I->fp8 && L.pair && L.bn == 256;  // FP8 corrections: hi parts up at [2^13, 2^14) so that the e4m3 copies keep bits
     if (mx > 0 && std::isfinite(mx)) { int e2; frexpf(mx, &e2); ew = (f8 ? 14 : 7) - e2; }  // mx*2^ew in [64,128)
     const float wscale = ldexpf(1.0f, ew);
     std::vector<__half> whi((size_t)L.n_total * ktot, __float2half_rn(0.0f)), wlo((size_t)L.n_total * ktot, __float2half_rn(0.0f));
@@ -1726,7 +1727,7 @@ void tc_tower_forward(TcTower& t, const NetLayout& NL, const Snapshot& s, Fp32Sc
   int cur = 0;
   dispatch_conv(*I, I->layers[0], I->mIn_hi, I->mIn_lo, I->x_hi[0], I->x_lo[0], n_dev, err_flag, st);
   if (launches) (*launches)++;
-  if (I->fp8) {  // experiment: the init conv's output also as e4m3 h8 / l8 for the first fused layer
+  if (I->fp8) {  // the init conv's output also as e5m2 h8 / l8 for the first fused layer
     const size_t ne = (size_t)I->rows_alloc * d.K;
     k_split_fp8<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(I->x_hi[0], I->x_lo[0], ne, ldexpf(1.0f, I->pa), ldexpf(1.0f, I->q),
                                                              I->x_h8[0], I->x_l8[0]); LAUNCH_CHECK();
