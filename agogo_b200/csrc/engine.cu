@@ -59,6 +59,7 @@ struct az_engine {
   cudaStream_t stream2 = nullptr;                   // agent B's evaluation when both small-net towers fit the GPU side by side
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<void*> allocs;
+  std::vector<unsigned long long> zt64;  // host copy of the position keys (external states are hashed on the host)
   NetLayout L;
   float* net_params[2] = {nullptr, nullptr};  // train-form, device
   Snapshot snap[2];
@@ -319,6 +320,17 @@ int az_engine_create(const az_engine_desc* desc, az_engine** out) {
       int32_t* z = e->dalloc<int32_t>(zt.size());
       CUDA_CHECK(cudaMemcpy(z, zt.data(), zt.size() * 4, cudaMemcpyHostToDevice));
       E.ztable = z;
+    }
+    E.zt64 = nullptr; E.poshash = nullptr; E.pathhash = nullptr;
+    if (P.wq_complete) {  // positional superko: 64-bit position keys from their own stream of the zobrist seed
+      e->zt64.resize((size_t)P.cells * 2);
+      uint64_t s = derive_seed(gd.zobrist_seed, 0x706f736974696f6eull);
+      for (auto& v : e->zt64) v = splitmix64(&s);
+      unsigned long long* z = e->dalloc<unsigned long long>(e->zt64.size());
+      CUDA_CHECK(cudaMemcpy(z, e->zt64.data(), e->zt64.size() * 8, cudaMemcpyHostToDevice));
+      E.zt64 = z;
+      E.poshash = e->dalloc<unsigned long long>((size_t)G * (P.max_plies + 2));
+      E.pathhash = e->dalloc<unsigned long long>(GV * (P.maxDepth + 2));
     }
     for (int a = 0; a < 2; a++) { E.inf[a].kind = -1; E.inf[a].L = n.action_space; E.inf[a].dummy_value = 0; E.inf[a].table = nullptr; E.inf[a].table_values = nullptr; E.inf[a].table_rows = 0; }
     e->coins_dev = e->dalloc<int>(G);
@@ -776,6 +788,20 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   CUDA_CHECK(cudaMemcpy(E.board, b.data(), b.size(), cudaMemcpyHostToDevice));
   if (P.hist_len) CUDA_CHECK(cudaMemcpy(E.hist, ring.data(), ring.size(), cudaMemcpyHostToDevice));
+  if (E.poshash) {  // positional superko sees the boards the caller supplies (<= 8 earlier positions), then the current one
+    std::vector<unsigned long long> ph;
+    auto hash_of = [&](const int32_t* bd) {
+      unsigned long long h = 0;
+      for (int c = 0; c < P.cells; c++) if (bd[c]) h ^= e->zt64[(size_t)c * 2 + (bd[c] == AZ_BLACK ? 0 : 1)];
+      return h;
+    };
+    for (int i = 0; i < st->n_hist; i++)
+      if (st->move_number - st->n_hist + i >= 0) ph.push_back(hash_of(st->hist + (size_t)i * P.cells));
+    while ((int)ph.size() > P.max_plies) ph.erase(ph.begin());  // the row holds max_plies + 2 entries
+    gi[GI_N_POS] = (int32_t)ph.size();
+    ph.push_back(hash_of(st->board));
+    CUDA_CHECK(cudaMemcpy(E.poshash, ph.data(), ph.size() * 8, cudaMemcpyHostToDevice));
+  }
   CUDA_CHECK(cudaMemcpy(E.gi, gi, sizeof gi, cudaMemcpyHostToDevice));
   e->in_play = true; e->record = false; e->n_play = 1;
   e->ex_by_game.assign(1, {});

@@ -23,6 +23,7 @@ struct WS {
 __host__ __device__ inline size_t ws_bytes(const GameP& P, int cellsP) {
   size_t n = cellsP + (size_t)(P.hist_len ? 8 * cellsP : 0);
   n += 3 * (size_t)cellsP * 4;                 // label, libcnt, gsize
+  if (P.wq_complete) n += (size_t)cellsP * 8;  // ghash (positional superko)
   n += 10 * (size_t)((P.A + 2 + 3) & ~3) * 4;  // fa fb ia ib ic st[5]
   return (n + 15) & ~(size_t)15;
 }
@@ -33,6 +34,7 @@ __device__ inline WS make_ws(const GameP& P, int cellsP, uint8_t* base) {
   w.wq.label = (int*)base; base += cellsP * 4;
   w.wq.libcnt = (int*)base; base += cellsP * 4;
   w.wq.gsize = (int*)base; base += cellsP * 4;
+  if (P.wq_complete) { w.wq.ghash = (unsigned long long*)base; base += cellsP * 8; }  // cellsP % 16 == 0: 8-byte aligned
   int AP = (P.A + 2 + 3) & ~3;
   w.fa = (float*)base; base += AP * 4;
   w.fb = (float*)base; base += AP * 4;
@@ -216,6 +218,7 @@ __global__ void k_arena_begin(GameP P, EngineDev E, int n_games, const int* __re
       gi[GI_PASSES] = P.kind == KIND_MNK ? -1 : 0;
       gi[GI_LAST_MOVE] = MV_PASS;  // State.LastMove() of an empty history (mnk.go:84-89)
       gi[GI_KO] = -1;
+      if (E.poshash) E.poshash[(size_t)g * (P.max_plies + 2)] = 0ull;  // the empty board; GI_N_POS = 0 positions before it
     }
   }
   __syncwarp();
@@ -358,6 +361,8 @@ __global__ void k_search_begin(GameP P, EngineDev E, int n_games) {
     if (lane == 0) {
       wv[WV_STATUS] = ST_LEAF; wv[WV_TO_MOVE] = player; wv[WV_MOVE_NUMBER] = mn; wv[WV_PASSES] = passes;
       wv[WV_KO] = gi[GI_KO];
+      wv[WV_NPATH] = 0;
+      if (E.pathhash) E.pathhash[(size_t)g * E.V * (P.maxDepth + 2)] = E.poshash[(size_t)g * (P.max_plies + 2) + gi[GI_N_POS]];
     }
     // planes are written after slots are known (k_encode_roots)
   } else {
@@ -428,6 +433,10 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
     s.move_number = gi[GI_MOVE_NUMBER];
     s.passes = P.kind == KIND_WQ ? gi[GI_PASSES] : (P.kind == KIND_MNK ? -1 : 0);
     s.ko = gi[GI_KO];
+    // positional superko: the hashes of the positions this descent walks through (entry 0 = the root's)
+    unsigned long long* ph = E.pathhash ? E.pathhash + ((size_t)g * E.V + wk) * (P.maxDepth + 2) : nullptr;
+    int npath = 0;
+    if (ph && lane == 0) ph[0] = E.poshash[(size_t)g * (P.max_plies + 2) + gi[GI_N_POS]];
     int node = ti[TI_ROOT];
     int depth = 0, path_len = 0;
     int status = ST_DONE;
@@ -459,7 +468,7 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
             float* out = E.nn_in + ((size_t)agent * E.GS + slot0 + (size_t)wk * slot_stride) * P.plane;
             encode_planes(P, w.board, w.hist, E.cellsP, s.to_move, s.move_number, out, lane);
           }
-          if (lane == 0) { wv[WV_TO_MOVE] = s.to_move; wv[WV_MOVE_NUMBER] = s.move_number; wv[WV_PASSES] = s.passes; wv[WV_KO] = s.ko; }
+          if (lane == 0) { wv[WV_TO_MOVE] = s.to_move; wv[WV_MOVE_NUMBER] = s.move_number; wv[WV_PASSES] = s.passes; wv[WV_KO] = s.ko; wv[WV_NPATH] = npath; }
           status = ST_LEAF;
           is_null = false;
         }
@@ -520,8 +529,15 @@ __global__ void k_select(GameP P, EngineDev E, int n_games) {
       if (besti == 0x7fffffff) { raise(E, ERR_NO_ACTIVE_CHILD, lane); break; }
       const int next = first + besti;
       const int move = META_MOVE(E.meta[tb + next]);
+      // (positional superko is not re-tested here: the child exists because expansion found the move legal against
+      // the same history — game positions + this very path — so the reference's second Check cannot disagree)
       if (!state_check(P, w, player, move, lane, &analyzed, s.ko)) break;  // illegal: null result, no retry
       state_apply(P, w, E.cellsP, s, player, move, lane, &analyzed, nullptr, nullptr);
+      if (ph) {
+        const unsigned long long h = wq_pos_hash(P, w.board, E.zt64, lane);
+        npath++;
+        if (lane == 0) ph[npath] = h;
+      }
       node = next;
     }
     if (vl && status != ST_LEAF) {  // the call returned: undoVirtualLoss on every node it entered (search.go:254)
@@ -599,7 +615,11 @@ __global__ void k_expand_backup(GameP P, EngineDev E, int n_games) {
   const bool already = META_EXPANDED(E.meta[tb + leaf]) != 0;
 
   // legal list in index order, then Pass (search.go:285-296)
+  w.wq.zt64 = E.zt64;  // complete rules: the analysis also leaves the group hashes
   if (P.kind == KIND_WQ && !already) wq_analyze(P, w.board, w.wq, lane);
+  const unsigned long long* gh_ = E.poshash ? E.poshash + (size_t)g * (P.max_plies + 2) : nullptr;
+  const unsigned long long* ph_ = E.pathhash ? E.pathhash + ((size_t)g * E.V + wk) * (P.maxDepth + 2) : nullptr;
+  const int n_pos = gh_ ? E.gi[(size_t)g * GI_COUNT + GI_N_POS] : 0, npath = gh_ ? wv[WV_NPATH] : 0;
   int nleg = 0;
   for (int base = 0; base < (already ? 0 : P.A); base += 32) {
     int i = base + lane;
@@ -607,6 +627,11 @@ __global__ void k_expand_backup(GameP P, EngineDev E, int n_games) {
     if (i < P.A) {
       if (P.kind == KIND_WQ) { bool cap; legal = wq_check_pt(P, w.board, w.wq, i, player, &cap, wv[WV_KO]); }
       else legal = simple_check(P, w.board, i);
+      if (legal && gh_) {  // positional superko: the move may not recreate a position of the game or of this path
+        const unsigned long long h = wq_hash_after(P, w.board, w.wq, i, player, ph_[npath]);
+        for (int j = 0; j < n_pos && legal; j++) legal = gh_[j] != h;
+        for (int j = 0; j < npath && legal; j++) legal = ph_[j] != h;
+      }
     }
     unsigned m = __ballot_sync(FULL, legal);
     if (legal) {
@@ -895,6 +920,13 @@ __global__ void k_search_end(GameP P, EngineDev E, int n_games, int record) {
   } else {
     state_apply(P, w, E.cellsP, s, player, best, lane, &analyzed, &zhash, E.ztable);
     last_move = best;
+    if (E.poshash) {  // positional superko: the position just left joins the game's list, the new one follows it
+      const unsigned long long h = wq_pos_hash(P, w.board, E.zt64, lane);
+      if (lane == 0) {
+        const int np = gi[GI_N_POS] + 1;
+        if (np <= P.max_plies) { E.poshash[(size_t)g * (P.max_plies + 2) + np] = h; gi[GI_N_POS] = np; }
+      }
+    }
   }
   __syncwarp();
   for (int i = lane; i < P.cells; i += 32) gb[i] = w.board[i];

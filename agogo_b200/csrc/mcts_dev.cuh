@@ -15,10 +15,10 @@
 #include "common.cuh"
 
 enum { GI_TO_MOVE, GI_MOVE_NUMBER, GI_PASSES, GI_ACTIVE, GI_WINNER, GI_ARENA_PASS, GI_A_PLAYER, GI_CUR_AGENT,
-       GI_N_MOVES, GI_ZHASH, GI_N_EX, GI_C4_PASS, GI_N_HMOVES, GI_LAST_MOVE, GI_KO, GI_COUNT = 16 };
+       GI_N_MOVES, GI_ZHASH, GI_N_EX, GI_C4_PASS, GI_N_HMOVES, GI_LAST_MOVE, GI_KO, GI_N_POS, GI_COUNT = 16 };
 enum { TI_ROOT, TI_ALLOC, TI_PREV_VALID, TI_PREV_MN, TI_NPOL, TI_RNG_LO, TI_RNG_HI, TI_COUNT = 8 };
 enum { WV_STATUS, WV_PATHLEN, WV_TO_MOVE, WV_MOVE_NUMBER, WV_PASSES, WV_SLOT, WV_AGENT, WV_FLAGS, WV_TREE,
-       WV_PLAYER, WV_HASH, WV_KO, WV_COUNT = 16 };
+       WV_PLAYER, WV_HASH, WV_KO, WV_NPATH, WV_COUNT = 16 };
 enum { ST_IDLE = 0, ST_LEAF = 1, ST_DONE = 2 };
 enum { INF_DUAL = 0, INF_DUMMY = 1, INF_TABLE = 2 };
 enum { CNT_SEARCHES, CNT_SIMS, CNT_NULL, CNT_EVALS, CNT_SEL_CHILDREN, CNT_SEL_LEVELS, CNT_CREATED, CNT_BACKUP,
@@ -68,6 +68,12 @@ struct EngineDev {
   int32_t* ex_valid; // [G]
   // misc
   const int32_t* ztable;  // [cells][2] wq zobrist
+  // positional superko (AZ_FLAG_WQ_COMPLETE only, else null): 64-bit position keys; per game the hashes of the positions
+  // before the root (gi[GI_N_POS] of them) followed by the root position's own; per descent the positions along the path
+  // (entry d = after d in-tree moves, entry 0 = the root position, entry wv[WV_NPATH] = the leaf)
+  const unsigned long long* zt64;  // [cells][2]
+  unsigned long long* poshash;     // [G][max_plies + 2]
+  unsigned long long* pathhash;    // [G*V][maxDepth + 2]
   int32_t* err;           // error bits
   unsigned long long* counters;  // [CNT_COUNT]
   int32_t* n_active;      // [1]

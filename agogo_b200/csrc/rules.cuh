@@ -87,6 +87,10 @@ struct WqScratch {
   int* label;   // [cells] group id = smallest point index of the group, -1 for empty points
   int* libcnt;  // [cells] indexed by group id: number of DISTINCT empty neighbours of the group
   int* gsize;   // [cells] indexed by group id: stones in the group
+  // positional superko (AZ_FLAG_WQ_COMPLETE): when both are set, wq_analyze also leaves in ghash[group id] the XOR of the
+  // group's stones' 64-bit position keys, so that a candidate move's resulting position hash costs O(1) per lane
+  unsigned long long* ghash = nullptr;      // [cells]
+  const unsigned long long* zt64 = nullptr;  // [cells][2] position keys (black, white)
 };
 
 // neighbour order of wq.go:317-322: {0,+1},{+1,0},{0,-1},{-1,0} in (row, col)
@@ -107,6 +111,7 @@ __device__ inline void wq_analyze(const GameP& P, const uint8_t* b, WqScratch s,
     s.label[i] = b[i] ? i : -1;
     s.libcnt[i] = 0;
     s.gsize[i] = 0;
+    if (s.ghash) s.ghash[i] = 0ull;
   }
   __syncwarp();
   bool changed;
@@ -130,6 +135,7 @@ __device__ inline void wq_analyze(const GameP& P, const uint8_t* b, WqScratch s,
   for (int i = lane; i < cells; i += 32) {
     if (b[i]) {
       atomicAdd(&s.gsize[s.label[i]], 1);
+      if (s.ghash && s.zt64) atomicXor(&s.ghash[s.label[i]], s.zt64[i * 2 + (b[i] == C_BLACK ? 0 : 1)]);
     } else {
       int seen[4];
       int ns = 0;
@@ -188,6 +194,34 @@ __device__ inline bool wq_check_pt(const GameP& P, const uint8_t* b, WqScratch s
   // empty neighbour is a liberty; for an occupied point it is the stone's own group.
   if (b[p] == C_NONE) return empty_nbr;
   return s.libcnt[s.label[p]] > 0;
+}
+
+// Positional superko (AZ_FLAG_WQ_COMPLETE; game.go:77's TODO): 64-bit hash of the position.  Whole warp.
+__device__ inline unsigned long long wq_pos_hash(const GameP& P, const uint8_t* b, const unsigned long long* __restrict__ zt64, int lane) {
+  unsigned long long h = 0ull;
+  for (int i = lane; i < P.cells; i += 32)
+    if (b[i]) h ^= zt64[i * 2 + (b[i] == C_BLACK ? 0 : 1)];
+#pragma unroll
+  for (int off = 16; off; off >>= 1) h ^= __shfl_xor_sync(FULL, h, off);
+  return h;
+}
+// Hash of the position a LEGAL move of `player` at the empty point p leads to, from the analysis of the current board
+// (with group hashes) and the current position's hash: the stone, minus every neighbouring opponent group whose only
+// liberty is p (each once).  Per lane.
+__device__ inline unsigned long long wq_hash_after(const GameP& P, const uint8_t* b, WqScratch s, int p, int player,
+                                                   unsigned long long cur) {
+  const int size = P.m, o = opp(player);
+  unsigned long long h = cur ^ s.zt64[p * 2 + (player == C_BLACK ? 0 : 1)];
+  int seen[4];
+#pragma unroll
+  for (int d = 0; d < 4; d++) {
+    int a = wq_nbr(size, p, d);
+    seen[d] = (a >= 0 && b[a] == o && s.libcnt[s.label[a]] == 1) ? s.label[a] : -1;
+#pragma unroll
+    for (int q = 0; q < d; q++) if (seen[q] == seen[d]) seen[d] = -1;
+    if (seen[d] >= 0) h ^= s.ghash[seen[d]];
+  }
+  return h;
 }
 
 // Board.Apply (wq.go:141-171) on the board in shared memory; needs wq_analyze(b) beforehand.

@@ -89,6 +89,8 @@ class GTPEngine:
             if not (check[0] and applied[0]):
                 return False
             new = out[0].copy()
+            if any((new == b).all() for b in self.boards):  # positional superko over the whole game (the engine's search
+                return False                                 # sees the last 8 positions; the front end owns them all)
             ko = -1
             if taken[0] == 1:  # a lone stone that captured one stone and has no other liberty: simple ko
                 gone = int(np.flatnonzero((self.board != 0) & (new == 0))[0])

@@ -286,6 +286,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
     t->nextToMove = st->to_move; t->passes = st->passes; t->moveCount = st->move_number;
     t->history.assign(st->move_number, PlayerMove{None, st->last_move}); t->histPtr = st->move_number;
     for (int i = 0; i < st->n_hist; i++) {
+      if (st->move_number - st->n_hist + i < 0) continue;  // Historical(h) = the board before move h
       auto hn = std::make_shared<WQ::HistNode>();
       hn->board.assign(st->hist + (size_t)i * cells, st->hist + (size_t)(i + 1) * cells);
       hn->prev = t->hist; hn->idx = st->move_number - st->n_hist + i;

@@ -157,7 +157,9 @@ struct WQ : State {
   // AZ_FLAG_WQ_COMPLETE (OURS, not the reference's: SURVEY §8f row 4): real Go rules instead of the reference's unfinished
   // ones — occupied points and true suicide are illegal, simple ko (the point of a single stone just captured by a lone
   // stone left with that single liberty may not be retaken immediately), own single-point eyes are never filled (the
-  // "eye-ish situations" noPass expects Check to reject, search.go:543), area scoring with komi decides the winner.
+  // "eye-ish situations" noPass expects Check to reject, search.go:543), POSITIONAL SUPERKO (game.go:77's TODO: a move may
+  // not recreate the stones of any earlier position of the game — the `hist` list, compared board by board), area scoring
+  // with komi decides the winner.
   bool complete = false;
   int32_t ko = -1;
 
@@ -237,6 +239,13 @@ struct WQ : State {
     }
     if (!empty_nbr && !has_opp) return false;                 // own single-point eye (or a 1x1 board): never filled
     if (!(cap || empty_nbr || friend_safe)) return false;     // suicide
+    if (hist) {                                               // positional superko
+      std::vector<int32_t> after = board.data;
+      after[p] = m.player;
+      for (int st : caps) after[st] = None;
+      for (const HistNode* n = hist.get(); n; n = n->prev.get())
+        if (n->board == after) return false;
+    }
     if (captured) *captured = caps;
     if (new_ko && caps.size() == 1 && !has_friend && !empty_nbr) *new_ko = caps[0];
     return true;

@@ -244,8 +244,9 @@ def _wq_group(board, size, p):
     return seen, libs
 
 
-def wq_complete_check(board, size, player, move, ko=-1):
-    """-> (legal, captured points (set), ko point the move creates or -1)"""
+def wq_complete_check(board, size, player, move, ko=-1, positions=None):
+    """-> (legal, captured points (set), ko point the move creates or -1).  `positions`: the earlier positions of the game
+    (tuples of the board) — positional superko: none of them may be recreated."""
     if move < 0 or move >= size * size or board[move] != 0 or move == ko:
         return False, set(), -1
     opp = 3 - player
@@ -265,6 +266,8 @@ def wq_complete_check(board, size, player, move, ko=-1):
         return False, set(), -1  # suicide
     if all(board[a] == player for a in nbrs):
         return False, set(), -1  # own single-point eye: never filled
+    if positions is not None and tuple(trial) in positions:
+        return False, set(), -1  # positional superko
     mine, _ = _wq_group(trial, size, move)
     new_ko = next(iter(captured)) if (len(captured) == 1 and len(mine) == 1 and len(libs) == 1) else -1
     return True, captured, new_ko

@@ -745,10 +745,14 @@ def test_wq_complete_rules_vs_oracle(oracle, engine_lib):
         assert (x == y).all()
 
 
-@pytest.mark.parametrize("size,sims,plies,inferer,workers", [(5, 20, 90, "dummy", 1), (5, 24, 90, "table", 1), (9, 16, 60, "table", 1), (5, 24, 60, "table", 4)])
+@pytest.mark.parametrize("size,sims,plies,inferer,workers", [(5, 20, 90, "dummy", 1), (5, 24, 90, "table", 1), (9, 16, 60, "table", 1), (5, 24, 60, "table", 4),
+                                                            (4, 200, 60, "table", 1), (3, 150, 40, "table", 1), (4, 120, 60, "table", 4)])
 def test_parity_wq_complete_arena(oracle, engine_lib, size, sims, plies, inferer, workers):
     """Whole games under AZ_FLAG_WQ_COMPLETE with sampled play (captures, kos, eye-only endgames, two-pass endings scored
-    by area + komi): trees after every ply, moves, examples, labels and statistics bit-identical to the oracle."""
+    by area + komi): trees after every ply, moves, examples, labels and statistics bit-identical to the oracle.  The tiny
+    boards with many simulations are the positional-superko cases: the oracle rejects > 100 moves there that simple ko
+    allows, most of them deep in the tree (positions of the descent itself), where the device compares 64-bit position
+    hashes and the oracle whole boards."""
     A1 = size * size + 1
     def desc():
         d = K.make_desc(K.GAME_WQ, size, size, 0, komi=5.5, sims=sims, n_games=8, seed=17, max_moves=plies, workers=workers,
@@ -775,9 +779,17 @@ def test_wq_complete_game_engine_vs_pyref(engine_lib):
     from tests.test_oracle_rules_pyref import _complete_game_vs_pyref
     kos = caps = 0
     for seed in range(1, 6):
-        k, c, _ = _complete_game_vs_pyref(engine_lib, 5, 20, seed, 90)
+        k, c, _, _ = _complete_game_vs_pyref(engine_lib, 5, 20, seed, 90)
         kos += k; caps += c
     assert caps > 10
+
+
+def test_wq_superko_external_engine_vs_pyref(engine_lib):
+    """Positional superko on caller-owned positions (az_state's <= 8 earlier boards): the device's legal set against the
+    Python restatement, 160 positions with planted repetitions (capturing and non-capturing)."""
+    from tests.test_oracle_rules_pyref import _superko_external_vs_pyref
+    sk = sum(_superko_external_vs_pyref(engine_lib, size, seed, 40) for size, seed in ((3, 1), (5, 2), (7, 3), (9, 4)))
+    assert sk >= 100
 
 
 @pytest.mark.parametrize("size,layers,n", [(9, 6, 37), (9, 1, 300), (5, 3, 5), (10, 2, 9)])

@@ -31,6 +31,16 @@ def test_gtp_basics_capture_ko_undo(oracle):
     assert g.board[2 * 5 + 1] == 0
     _ok(g, "undo")
     assert g.board[2 * 5 + 1] == K.WHITE and g.board[2 * 5 + 2] == 0
+    # positional superko: after two passes the simple-ko bar is gone, but retaking would recreate the position before
+    # white's capture — still illegal; so is it for the engine's own search (the ko point never becomes a root child)
+    _ok(g, "undo"); _ok(g, "undo")                               # back to: white has just captured at B3
+    assert g.kos[-1] == 2 * 5 + 2
+    _ok(g, "play b pass"); _ok(g, "play w pass")
+    assert g.kos[-1] == -1 and g.handle("play b C3")[0].startswith("? illegal")
+    _, visits = g.engine.search(0, g.board, K.BLACK, K.BLACK, move_number=len(g.moves), passes=0, hist=g.boards[-8:],
+                                last_move=K.PASS, ko=-1)
+    assert visits[2 * 5 + 2] == 0 and visits[4 * 5 + 4] > 0
+    _ok(g, "play b E5")
     assert "X" in _ok(g, "showboard")
     assert _ok(g, "final_score")[0] in "BW0"
     _ok(g, "boardsize 7")

@@ -104,14 +104,16 @@ def test_wq_complete_rules_oracle_vs_pyref(oracle):
 
 def _complete_game_vs_pyref(lib, size, sims, seed, max_moves):
     """One Arena game under AZ_FLAG_WQ_COMPLETE: after every search the root's children must be exactly the legal moves
-    (+ Pass) of the Python restatement with its own ko tracking; returns how many kos and captures occurred."""
+    (+ Pass) of the Python restatement with its own ko and position-set tracking; returns how many kos, captures and
+    superko-only rejections (a point legal under simple ko but recreating an earlier position) occurred."""
     d = K.make_desc(K.GAME_WQ, size, size, 0, komi=5.5, sims=sims, n_games=1, seed=seed, max_moves=max_moves,
                     flags=K.FLAG_WQ_COMPLETE, nn=H.tiny_nn(size, size, size * size + 1, features=18))
     d.mcts.random_count, d.mcts.random_temperature = max_moves, 1.0   # sampled play: varied games with fights
     e = lib.create(d)
     e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
     e.arena_begin(1, False)
-    board, ko, kos, caps = [0] * (size * size), -1, 0, 0
+    board, ko, kos, caps, sk = [0] * (size * size), -1, 0, 0, 0
+    positions = set()
     player = 1
     n_act, ply = 1, 0
     while n_act:
@@ -121,13 +123,15 @@ def _complete_game_vs_pyref(lib, size, sims, seed, max_moves):
         agent = 0 if (ply % 2 == 0) == a_black else 1
         dump = e.tree_dump(0, agent)
         kids = {int(r[1]) for r in dump if r[0] == 1}
-        legal = {p for p in range(size * size) if R.wq_complete_check(board, size, player, p, ko)[0]} | {K.PASS}
+        legal = {p for p in range(size * size) if R.wq_complete_check(board, size, player, p, ko, positions)[0]} | {K.PASS}
         assert kids == legal, (ply, sorted(kids ^ legal), ko)
+        sk += sum(1 for p in range(size * size) if p not in legal and R.wq_complete_check(board, size, player, p, ko)[0])
         mv = int(rec["moves"][ply])
+        positions.add(tuple(board))
         if mv == K.PASS:
             ko = -1
         else:
-            ok, captured, ko = R.wq_complete_check(board, size, player, mv, ko)
+            ok, captured, ko = R.wq_complete_check(board, size, player, mv, ko, positions)
             assert ok, (ply, mv)
             board[mv] = player
             for q in captured:
@@ -144,12 +148,64 @@ def _complete_game_vs_pyref(lib, size, sims, seed, max_moves):
         sb, sw = R.wq_area_score(board, size, 1), R.wq_area_score(board, size, 2) + 5.5
         assert e.game_record(0)["winner"] == (0 if sb == sw else (1 if sb > sw else 2))
     e.close()
-    return kos, caps, ply
+    return kos, caps, sk, ply
 
 
 def test_wq_complete_games_oracle_vs_pyref(oracle):
-    kos = caps = 0
+    kos = caps = sks = 0
     for seed in range(1, 9):
-        k, c, plies = _complete_game_vs_pyref(oracle, 5, 20, seed, 90)
-        kos += k; caps += c
+        k, c, sk, plies = _complete_game_vs_pyref(oracle, 5, 20, seed, 90)
+        kos += k; caps += c; sks += sk
+    print("kos", kos, "captures", caps, "superko-only rejections", sks)
     assert caps > 20 and kos > 0, (kos, caps)   # the games really fought (captures, at least one ko shape)
+
+
+def _superko_external_vs_pyref(lib, size, seed, rounds):
+    """Positional superko on external states: random positions handed to Agent.Search together with <= 8 earlier boards,
+    some of which are exactly what a legal move (capturing or not) would recreate.  The root's children must be the
+    restatement's legal set (+ Pass).  Returns how many points superko alone rejected."""
+    cells = size * size
+    d = K.make_desc(K.GAME_WQ, size, size, 0, komi=0.5, sims=2, n_games=1, seed=seed, flags=K.FLAG_WQ_COMPLETE,
+                    nn=H.tiny_nn(size, size, cells + 1, features=2), encoder=K.ENC_TWO_PLANE)
+    e = lib.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    rng = np.random.default_rng(seed)
+    sk = 0
+    for _ in range(rounds):
+        b = rng.choice([0, 1, 2], size=cells, p=[0.3, 0.35, 0.35]).tolist()
+        for p in range(cells):  # drop dead groups: a possible Go position
+            if b[p] and not R._wq_group(b, size, p)[1]:
+                for q in R._wq_group(b, size, p)[0]:
+                    b[q] = 0
+        player = int(rng.integers(1, 3))
+        results = []
+        for p in range(cells):
+            ok, captured, _ = R.wq_complete_check(b, size, player, p)
+            if ok:
+                after = list(b); after[p] = player
+                for q in captured:
+                    after[q] = 0
+                results.append(after)
+        n_hist = int(rng.integers(0, 9))
+        window = []
+        for _ in range(n_hist):
+            if results and rng.random() < 0.6:
+                window.append(results[int(rng.integers(len(results)))])
+            else:
+                window.append(rng.choice([0, 1, 2], size=cells).tolist())
+        positions = {tuple(x) for x in window}
+        legal = {p for p in range(cells) if R.wq_complete_check(b, size, player, p, -1, positions)[0]}
+        sk += sum(1 for p in range(cells) if p not in legal and R.wq_complete_check(b, size, player, p)[0])
+        e.reset_tree(0)
+        _, visits = e.search(0, b, player, player, move_number=20 + n_hist, passes=0,
+                             hist=np.array(window, np.int32) if window else None, last_move=0, ko=-1)
+        kids = {(K.PASS if i == cells else i) for i in np.nonzero(visits)[0].tolist()}  # children are born with one visit
+        assert kids == legal | {K.PASS}, (size, seed, b, player, window, sorted(kids ^ (legal | {K.PASS})))
+    e.close()
+    return sk
+
+
+def test_wq_superko_external_oracle_vs_pyref(oracle):
+    sk = sum(_superko_external_vs_pyref(oracle, size, seed, 40) for size, seed in ((3, 1), (5, 2), (7, 3), (9, 4)))
+    print("superko-only rejections", sk)
+    assert sk >= 100
