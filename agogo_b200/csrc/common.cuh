@@ -47,7 +47,7 @@ struct GameP {
   int hist_len;       // 8 for wq18, else 0
   int max_nodes;      // per tree
   int max_plies;      // capacity of per-game move lists
-  int wq_complete;    // AZ_FLAG_WQ_COMPLETE: OUR completion of the wq rules (occupied / suicide / simple ko / eyes / area scoring)
+  int wq_complete;    // AZ_FLAG_WQ_COMPLETE: OUR completion of the wq rules (occupied / suicide / ko + positional superko / eyes / area scoring)
 };
 
 __host__ __device__ inline int opp(int p) { return p == C_BLACK ? C_WHITE : C_BLACK; }

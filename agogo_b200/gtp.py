@@ -3,7 +3,7 @@ clear_board, genmove, known_command, komi, list_commands, name, play, protocol_v
 plus final_score).  The board lives here (so `undo` works, which the reference's wq.Game cannot: UndoLastMove panics,
 wq/game.go:119); legality and captures come from the engine's rules kernels (`az_rules_apply`), moves from
 `Agent.Search` on the current position (`az_search`), under the complete-rules mode (AZ_FLAG_WQ_COMPLETE: occupied points,
-suicide, simple ko and own-eye fills are illegal; area scoring) — a Go program that cannot refuse a suicide or a ko
+suicide, simple ko, positional superko and own-eye fills are illegal; area scoring) — a Go program that cannot refuse a suicide or a ko
 recapture is not playable against another one.
 
     python -m agogo_b200.gtp --size 9 --sims 200 [--k 64 --blocks 6 --fc 128] [--checkpoint net.model]
