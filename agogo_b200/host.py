@@ -129,6 +129,103 @@ class Example:  # datatypes.go:38-42
     Value: float
 
 
+@dataclass
+class State:
+    """The game.State getters (game/state.go:128-169) the path reads from a caller-owned position — what `Agent.Search`,
+    `Agent.Infer` and the encoders take.  `hist` holds the last <= 8 boards before the current one, oldest first
+    (`Historical(MoveNumber()-len(hist)) ... Historical(MoveNumber()-1)`); `moves` the tail of the history as
+    (player, move) pairs, oldest first (lets the agent's tree be re-rooted across calls, search.go:424-500)."""
+    board: np.ndarray
+    to_move: int = K.BLACK
+    move_number: int = 0
+    passes: int = 0
+    last_move: int = K.PASS
+    hist: object = None
+    moves: object = None
+    ko: int = -1    # AZ_FLAG_WQ_COMPLETE only
+
+    def Board(self):
+        return np.asarray(self.board, np.int32).reshape(-1)
+
+    def ToMove(self):
+        return self.to_move
+
+    def MoveNumber(self):
+        return self.move_number
+
+    def Historical(self, i):  # wq: the board before move i; the reference panics on a bad index too
+        h = [] if self.hist is None else np.asarray(self.hist, np.int32).reshape(-1, self.Board().size)
+        j = i - (self.move_number - len(h))
+        if not 0 <= j < len(h):
+            raise IndexError("index out of range")
+        return h[j]
+
+
+def EncodeTwoPlayerBoard(a, prealloc=None):
+    """encoding_helper.go:10-26: black 1, white -1, everything else 0."""
+    a = np.asarray(a)
+    out = prealloc if prealloc is not None and len(prealloc) == len(a) else np.zeros(len(a), np.float32)
+    out[:] = np.where(a == K.BLACK, np.float32(1), np.where(a == K.WHITE, np.float32(-1), np.float32(0)))
+    return out
+
+
+def EncodeBoard(state):
+    """cmd/tictactoe/main.go:26-47 (the two-plane GameEncoder of the mnk / c4 commands): stones +-1 with empties at 0.001,
+    then a plane of +-1 for the side to move (zeros when nobody is)."""
+    board = EncodeTwoPlayerBoard(state.Board())
+    board[board == 0] = np.float32(0.001)
+    layer = np.zeros(len(board), np.float32)
+    if state.ToMove() == K.BLACK:
+        layer[:] = 1
+    elif state.ToMove() == K.WHITE:
+        layer[:] = -1
+    return np.concatenate([board, layer])
+
+
+def WQEncoder(state):
+    """encoding_helper.go:29-68, quirks included: of the 2 x 8 history planes only i = 1..7 are ever written (plane 7 of
+    each group and the CURRENT board never are), from Historical((MoveNumber()-1)-i) when that index is > 0; each plane
+    carries BOTH colours (+1 black / -1 white), the "white" group being the negation — so its empty points are -0.0;
+    the group of the side to move comes first and its to-move plane is filled with +-1."""
+    lookback = 8
+    board = state.Board()
+    size = len(board)
+    out = np.zeros(size * (2 * lookback + 2), np.float32)
+    if state.ToMove() == K.BLACK:
+        bs, ws, ns, player = 0, lookback * size, 2 * lookback * size, np.float32(1)
+    else:
+        bs, ws, ns, player = lookback * size, 0, (2 * lookback + 1) * size, np.float32(-1)
+    current = state.MoveNumber() - 1
+    for i in range(1, lookback):
+        h = current - i
+        if 0 < h < current:
+            past = state.Historical(h)
+            EncodeTwoPlayerBoard(past, out[bs:bs + size])                              # encodeBlack
+            out[ws:ws + size] = EncodeTwoPlayerBoard(past) * np.float32(-1)            # encodeWhite: vecf32.Scale(-1)
+        bs += size
+        ws += size
+    out[ns:ns + size] = player
+    return out
+
+
+def RotateBoard(board, m, n):
+    """encoding_helper.go:80-108 (the building block of the commands' Augmenters): a quarter turn of a square board —
+    new[i][j] = old[j][m-1-i]; four of them are the identity (encoding_helper_test.go:10-58)."""
+    if m != n:
+        raise ValueError("Cannot handle m %d, n %d. This function only takes square boards" % (m, n))
+    it = np.array(board, np.float32).reshape(m, n)  # a copy, like the reference's
+    for i in range(m // 2):
+        mi1 = m - i - 1
+        for j in range(i, mi1):
+            mj1 = m - j - 1
+            tmp = it[i][j]
+            it[i][j] = it[j][mi1]        # right to top
+            it[j][mi1] = it[mi1][mj1]    # bottom to right
+            it[mi1][mj1] = it[mj1][i]    # left to bottom
+            it[mj1][i] = tmp             # tmp is left
+    return it.reshape(-1)
+
+
 class Agent:
     """agent.go:14-121 — a view on one of the engine's two agents."""
 
@@ -155,6 +252,19 @@ class Agent:
 
     def NNOutput(self, planes):  # agent.go:83-89
         return self._az.engine.infer(self.idx, planes)
+
+    def Infer(self, g):  # agent.go:60-74: Enc(g) -> inferer.Infer; g is a host.State
+        enc = WQEncoder if self._az.conf.Encoder == K.ENC_WQ18 else EncodeBoard
+        policy, value = self._az.engine.infer(self.idx, enc(g)[None])
+        return policy[0], float(value[0])
+
+    def Search(self, g):  # agent.go:77-80: MCTS.Search(g.ToMove()) on a caller-owned position -> game.Single
+        best, _ = self._az.engine.search(self.idx, g.Board(), g.to_move, g.to_move, move_number=g.move_number, passes=g.passes,
+                                         hist=g.hist, last_move=g.last_move, moves=g.moves, ko=g.ko)
+        return best
+
+    def Close(self):  # agent.go:91-103: drops the inferer and the tree; the engine owns both until AZ.Close
+        self._az.engine.reset_tree(self.idx)
 
     def resetStats(self):
         self._az.engine.reset_stats(self.idx)

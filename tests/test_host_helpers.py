@@ -1,0 +1,96 @@
+"""Host-side mirrors of the reference's helpers around the path (agogo_b200/host.py): RotateBoard against the reference's
+own test (encoding_helper_test.go:10-58), the two GameEncoders against the planes the engine's device-side twins put into
+the Arena's examples (oracle library on CPU; bit for bit, -0.0 included), Agent.Search / Agent.Infer on a caller-owned
+game.State."""
+import numpy as np
+import pytest
+
+from agogo_b200 import _capi as K
+from agogo_b200 import host as Hh
+from tests import helpers as H
+from tests import pyref_rules as R
+
+
+def test_rotate_board_reference_case():
+    W, N, B = 2.0, 0.0, 1.0   # any three values: the function moves float32s around
+    board = [W, N, N, N, B,
+             N, W, N, B, N,    # this line is to break rotational symmetry
+             N, N, N, N, N,
+             N, N, N, N, N,
+             B, N, N, N, W]
+    r = board
+    seen = []
+    for _ in range(4):
+        r = Hh.RotateBoard(r, 5, 5)
+        seen.append(r.tolist())
+    assert seen[3] == board, "After 4 rotations the board should be the same"
+    assert seen[0] != board and seen[1] != board and seen[0] != seen[2]
+    assert seen[0] == np.rot90(np.array(board).reshape(5, 5), 1).reshape(-1).tolist()   # a quarter turn counter-clockwise
+    with pytest.raises(ValueError):
+        Hh.RotateBoard([0] * 6, 2, 3)
+    assert Hh.RotateBoard(list(range(16)), 4, 4).tolist() == np.rot90(np.arange(16).reshape(4, 4)).reshape(-1).tolist()
+
+
+def _replay_wq(moves, size):
+    """boards before every move of a wq game under the reference's rules as written (pyref_rules.wq_apply)"""
+    b, player, before = [0] * (size * size), 1, []
+    for mv in moves:
+        before.append(list(b))
+        if mv != K.PASS:
+            _, _, b, _ = R.wq_apply(b, size, player, int(mv))
+        player = 3 - player
+    return before
+
+
+def test_wq_encoder_equals_the_arena_examples(oracle):
+    size = 5
+    d = K.make_desc(K.GAME_WQ, size, size, 0, komi=0.5, sims=6, n_games=1, seed=3, max_moves=24,
+                    nn=H.tiny_nn(size, size, size * size + 1, features=18))
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    e.arena_play(1, True)
+    moves = e.game_record(0)["moves"]
+    boards, _, _ = e.examples(clear=True)
+    assert len(boards) == len(moves) >= 20
+    before = _replay_wq(moves, size)
+    for ply in range(len(moves)):
+        st = Hh.State(board=before[ply], to_move=1 + ply % 2, move_number=ply, hist=before[max(0, ply - 8):ply])
+        mine = Hh.WQEncoder(st)
+        assert (mine.view(np.uint32) == boards[ply].view(np.uint32)).all(), ply
+    assert np.signbit(boards[12][boards[12] == 0]).any()      # the negated group's empties are -0.0 and that is compared
+    with pytest.raises(IndexError):
+        Hh.State(board=before[9], move_number=9, hist=before[7:9]).Historical(3)
+    e.close()
+
+
+def test_two_plane_encoder_equals_the_arena_examples(oracle):
+    d = K.make_desc(K.GAME_MNK, 3, 3, 3, sims=8, n_games=1, seed=5, nn=H.tiny_nn(3, 3, 9, features=2), encoder=K.ENC_TWO_PLANE)
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    e.arena_play(1, True)
+    moves = e.game_record(0)["moves"]
+    boards, _, _ = e.examples(clear=True)
+    b = [0] * 9
+    for ply, mv in enumerate(moves):
+        st = Hh.State(board=list(b), to_move=1 + ply % 2, move_number=ply)
+        assert (Hh.EncodeBoard(st).view(np.uint32) == boards[ply].view(np.uint32)).all(), ply
+        b[int(mv)] = 1 + ply % 2
+    e.close()
+
+
+def test_agent_search_and_infer_on_a_state(oracle):
+    g = Hh.Game(K.GAME_MNK, 3, 3, 3)
+    conf = Hh.Config(NNConf=Hh.DualConfig(K=3, SharedLayers=1, FC=8, BatchSize=2, Width=3, Height=3, Features=2, ActionSpace=9),
+                     MCTSConf=Hh.MCTSConfig(PUCT=1.0, M=3, N=3, Sims=60, Budget=1000, RandomTemperature=1.0), Encoder=K.ENC_TWO_PLANE)
+    az = Hh.AZ(g, conf, lib=oracle, n_games=1, seed=2)
+    az.A.useDummy()
+    # X to move with two in a row: the search takes the win
+    st = Hh.State(board=[1, 1, 0, 2, 2, 0, 0, 0, 0], to_move=K.BLACK, move_number=4, last_move=4)
+    assert az.A.Search(st) == 2
+    az.A.Close()
+    az.A.SwitchToInference()
+    pol, val = az.A.Infer(st)
+    p2, v2 = az.A.NNOutput(Hh.EncodeBoard(st)[None])
+    # (the reference's own init overflows on a net this small — compare bits, NaNs included)
+    assert pol.shape == (9,) and (pol.view(np.uint32) == p2[0].view(np.uint32)).all()
+    assert np.float32(val).view(np.uint32) == v2[:1].view(np.uint32)[0]
