@@ -91,7 +91,7 @@ struct az_engine {
   int wave_graph_n = -1;
   uint64_t wave_graph_version = 0, cfg_version = 1;
   unsigned long long wave_graph_launches = 0;
-  bool graphs_enabled = true, profiling = false;
+  bool graphs_enabled = true, profiling = false, prof_region = false;
   int32_t* round_workers_dev = nullptr;  // mcts.Config workers: how many the current round starts
   int round_workers_host = -1;
   cudaEvent_t prof_start = nullptr, prof_stop = nullptr;  // region timing between az_profile(1) and az_profile(0)
@@ -1230,7 +1230,7 @@ int az_profile(az_engine* e, int32_t enable, double out[8]) {
     for (int i = 0; i < 8; i++) out[i] = 0;
     if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile_collect(e->tc[a], e->stream, &out[0], &out[1], &out[2], &out[3]);
     out[5] = e->use_tc ? (double)tc_tower_kernel_kind(e->tc[0]) : -1.0;  // which kernel runs the fused layers
-    if (e->profiling && !enable) {  // whole region on the engine's stream, device-timed
+    if ((e->profiling || e->prof_region) && !enable) {  // whole region on the engine's stream, device-timed
       CUDA_CHECK(cudaEventRecord(e->prof_stop, e->stream));
       CUDA_CHECK(cudaEventSynchronize(e->prof_stop));
       float ms = 0;
@@ -1239,8 +1239,9 @@ int az_profile(az_engine* e, int32_t enable, double out[8]) {
     }
   }
   if (enable) { CUDA_CHECK(cudaStreamSynchronize(e->stream)); CUDA_CHECK(cudaEventRecord(e->prof_start, e->stream)); }
-  if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile(e->tc[a], enable != 0);
-  e->profiling = enable != 0;  // event records inside the wave: replay the plain launch sequence instead of the graph
+  if (e->use_tc) for (int a = 0; a < 2; a++) tc_tower_profile(e->tc[a], enable == 1);
+  e->profiling = enable == 1;    // event records inside the wave: replay the plain launch sequence instead of the graph
+  e->prof_region = enable == 2;  // region timing only: the captured wave graph keeps running
   GUARD_END(e)
   return AZ_OK;
 }

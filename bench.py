@@ -260,7 +260,10 @@ def main():
         return 0
 
     peaks, peak_src = load_peaks()
-    roofline = roofline_of(main_arm, w, peaks, peak_src)
+    roofline = roofline_of(main_arm.get("roof_arm") or main_arm, w, peaks, peak_src)
+    if main_arm.get("roof_arm"):
+        roofline["region"] = ("separate region of %d steps with CUDA events around every launch (plain launches); `value` is timed "
+                              "over the captured wave graph without them" % main_arm["roof_arm"]["steps"])
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         os.environ.setdefault("OMP_WAIT_POLICY", "passive")
@@ -293,7 +296,8 @@ def main():
             "tflops_algorithmic": main_arm["tot_evals"] / main_arm["dt_max"] * fpe / 1e12,
             "e2e": main_arm["e2e"], "gpu_launches": int(main_arm["tot_launch"]), "roofline": roofline, "tree": tree,
             "cpu_baseline": cpu_baseline, "clocks": main_arm["clocks"],
-            "timing": "CUDA events on the engine's stream around exactly `steps` steps, barrier+synchronize both sides, max over ranks"}
+            "timing": "CUDA events on the engine's stream around exactly `steps` steps, barrier+synchronize both sides, max over ranks"
+                      + (" (wave graph replayed; per-launch events in a second region, see roofline.region)" if main_arm.get("roof_arm") else "")}
     if main_arm.get("train") is not None:
         line["train"] = main_arm["train"]
     if fast_arm is not None:
@@ -397,25 +401,36 @@ def selfplay_arm(ctx, flags, do_e2e, probe, do_train, steps=None):
     for _ in range(warmup):
         one_step()
 
-    def timed_region():
+    def timed_region(mode=1, n=None):
         e.counters_reset()
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        e.profile(True)                      # records the start event on the engine's stream
-        for _ in range(steps):
+        e.profile(mode)                      # records the start event on the engine's stream
+        for _ in range(n or steps):
             one_step()
         prof = e.profile(False)              # stop event + synchronise: device time of exactly `steps` steps
         barrier()
         sampler.stop_flag = True
         return prof, sampler.summary(), e.counters()
 
-    prof, clocks, cnt = timed_region()
+    # A launch-bound small net (k_net_small, kernel_kind 5) is timed the way it runs in production — the captured wave
+    # graph replayed, no events inside the wave (az_profile mode 2) — and the per-launch kernel times behind the roofline
+    # come from a second, shorter region with the events on (plain launches).  Everywhere else the events cost nothing
+    # measurable against millisecond kernels and one region serves both.
+    e.profile(True)
+    two_regions = e.profile(False)["kernel_kind"] == 5
+    prof, clocks, cnt = timed_region(2 if two_regions else 1)
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     if bad & set(clocks.get("reasons", [])) and world == 1:  # rejected: re-measure once (timing rules)
-        prof, clocks2, cnt = timed_region()
+        prof, clocks2, cnt = timed_region(2 if two_regions else 1)
         clocks2["rejected_first_run"] = True
         clocks = clocks2
+    roof_arm = None
+    if two_regions:
+        p2, _, c2 = timed_region(1, min(steps, 100))
+        roof_arm = dict(prof=p2, cnt=c2, dt=p2["region_ms"] / 1e3, workload=args.workload, steps=min(steps, 100))
+        prof = dict(prof, kernel_kind=p2["kernel_kind"])
     dt = prof["region_ms"] / 1e3
     tot = [dt, float(cnt["sims"]), float(cnt["evals"]), float(cnt["kernel_launches"])]
     dt_max = dt
@@ -426,7 +441,7 @@ def selfplay_arm(ctx, flags, do_e2e, probe, do_train, steps=None):
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         dt_max, tot = mx[0].item(), tt.tolist()
     out = dict(value=tot[1] / dt_max, dt=dt, dt_max=dt_max, tot_evals=tot[2], tot_launch=tot[3], prof=prof, clocks=clocks,
-               cnt=cnt, steps=steps, e2e=None, train=None, workload=args.workload)
+               cnt=cnt, steps=steps, e2e=None, train=None, workload=args.workload, roof_arm=roof_arm)
 
     # finish the ply in flight (untimed) and leave the arena
     if state["in_search"]:

@@ -275,7 +275,8 @@ int az_counters_reset(az_engine* e);
  * forward_ms_total, forward_calls, region_ms, kernel_kind, 0...} accumulated since the last enable=1; region_ms is the
  * device time between the enable=1 and the enable=0 call on the engine's stream; kernel_kind names the kernel that runs
  * the fused layers (0 single-CTA, 1 CTA-pair per-tap 3 x fp16, 2 per-tap FP8 corrections, 3 halo FP8 corrections,
- * 4 halo 3 x fp16; -1 fp32 tower). */
+ * 4 halo 3 x fp16, 5 k_net_small; -1 fp32 tower).  enable=2 times the region only (region_ms): no per-launch events, so
+ * the captured wave graph keeps running — what a launch-bound small-net workload should be timed with. */
 int az_profile(az_engine* e, int32_t enable, double out[8]);
 
 const char* az_build_info(void); /* "agogo_b200 <ver> sm_100a ..." or "oracle ..." */
