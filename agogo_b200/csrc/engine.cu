@@ -718,7 +718,8 @@ int az_arena_play(az_engine* e, int32_t n_games, int32_t record) {
 }
 
 int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, int32_t* best, float* child_visits) {
-  if (agent < 0 || agent > 1 || !st || !st->board || st->n_hist < 0 || st->n_hist > 8 || (st->n_hist > 0 && !st->hist)) return AZ_ERR_INVALID;
+  if (agent < 0 || agent > 1 || !st || !st->board || st->n_hist < 0 || (st->n_hist > 0 && !st->hist)) return AZ_ERR_INVALID;
+  if (st->n_hist > (e->P.wq_complete ? e->P.max_plies : 8)) return AZ_ERR_INVALID;  // complete rules: superko reads them all
   if (e->in_play) { e->err = "az_search during a running arena"; return AZ_ERR_STATE; }
   if (e->E.inf[agent].kind < 0) { e->err = "agent has no inferer"; return AZ_ERR_STATE; }
   GUARD_BEGIN
@@ -765,7 +766,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   }
   std::vector<uint8_t> ring(P.hist_len ? (size_t)8 * E.cellsP : 1, 0);
   if (P.hist_len)
-    for (int i = 0; i < st->n_hist; i++) {
+    for (int i = std::max(0, st->n_hist - 8); i < st->n_hist; i++) {  // the encoder looks back 8 boards
       int h = st->move_number - st->n_hist + i;  // Historical(h) = board before move h
       if (h < 0) continue;
       for (int c = 0; c < P.cells; c++) ring[(size_t)(h & 7) * E.cellsP + c] = (uint8_t)st->hist[(size_t)i * P.cells + c];
@@ -788,7 +789,7 @@ int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, i
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   CUDA_CHECK(cudaMemcpy(E.board, b.data(), b.size(), cudaMemcpyHostToDevice));
   if (P.hist_len) CUDA_CHECK(cudaMemcpy(E.hist, ring.data(), ring.size(), cudaMemcpyHostToDevice));
-  if (E.poshash) {  // positional superko sees the boards the caller supplies (<= 8 earlier positions), then the current one
+  if (E.poshash) {  // positional superko sees the boards the caller supplies (the earlier positions of the game), then the current one
     std::vector<unsigned long long> ph;
     auto hash_of = [&](const int32_t* bd) {
       unsigned long long h = 0;

@@ -89,8 +89,8 @@ class GTPEngine:
             if not (check[0] and applied[0]):
                 return False
             new = out[0].copy()
-            if any((new == b).all() for b in self.boards):  # positional superko over the whole game (the engine's search
-                return False                                 # sees the last 8 positions; the front end owns them all)
+            if any((new == b).all() for b in self.boards):  # positional superko over the whole game, as in the engine's
+                return False                                 # search (genmove hands it every earlier board)
             ko = -1
             if taken[0] == 1:  # a lone stone that captured one stone and has no other liberty: simple ko
                 gone = int(np.flatnonzero((self.board != 0) & (new == 0))[0])
@@ -160,7 +160,7 @@ class GTPEngine:
     def cmd_genmove(self, args):
         player = self._colour(args[0])
         n = len(self.moves)
-        hist = np.array(self.boards[-8:], np.int32) if self.boards else None
+        hist = np.array(self.boards, np.int32) if self.boards else None   # the whole game: superko reads all of it
         best, _ = self.engine.search(0, self.board, player, player, move_number=n, passes=min(self.passes, 1),
                                      hist=hist, last_move=self.moves[-1][1] if self.moves else K.PASS, ko=self.kos[-1])
         if best == K.RESIGN:

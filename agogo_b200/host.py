@@ -132,7 +132,7 @@ class Example:  # datatypes.go:38-42
 @dataclass
 class State:
     """The game.State getters (game/state.go:128-169) the path reads from a caller-owned position — what `Agent.Search`,
-    `Agent.Infer` and the encoders take.  `hist` holds the last <= 8 boards before the current one, oldest first
+    `Agent.Infer` and the encoders take.  `hist` holds the boards before the current one, oldest first (<= 8; any number under AZ_FLAG_WQ_COMPLETE)
     (`Historical(MoveNumber()-len(hist)) ... Historical(MoveNumber()-1)`); `moves` the tail of the history as
     (player, move) pairs, oldest first (lets the agent's tree be re-rooted across calls, search.go:424-500)."""
     board: np.ndarray

@@ -108,7 +108,7 @@ typedef struct az_dual_config {
  * keeps wq.Game exactly as written: occupied points "legal", no ko, the row-0 flood-fill Score).  With the flag:
  * occupied points and true suicide are illegal, simple ko AND positional superko (game.go:77's TODO: no move may recreate
  * the stones of an earlier position of the game — inside the search: of the game or of the descent; for az_search on a
- * caller-owned position: of the <= 8 earlier boards in az_state.hist), own single-point eyes are never filled (the
+ * caller-owned position: of the earlier boards in az_state.hist), own single-point eyes are never filled (the
  * "eye-ish situations" noPass expects Check to reject, search.go:543), Score = area (stones + empty regions touching one colour
  * only) and Ended adds komi to White.  Same arithmetic everywhere else; engine and oracle are compared bit for bit under
  * the flag too. */
@@ -192,7 +192,7 @@ typedef struct az_state {
   const int32_t* board; /* [m*n] colours */
   int32_t to_move, move_number, passes;
   int32_t last_move;    /* LastMove().Single; AZ_PASS for an empty history (mnk.go:84-89) */
-  int32_t n_hist;       /* 0..8 */
+  int32_t n_hist;       /* 0..8; under AZ_FLAG_WQ_COMPLETE up to the whole game (the encoder reads the last 8, superko all) */
   const int32_t* hist;  /* [n_hist][m*n], oldest first (wq18 planes; under AZ_FLAG_WQ_COMPLETE also the positions superko bars) */
   int32_t n_moves;      /* entries of `moves` (0 = history unknown: no reuse across calls) */
   const int32_t* moves; /* [n_moves][2] = (player, move), oldest first: the tail of the State's history */

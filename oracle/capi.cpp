@@ -258,7 +258,8 @@ int az_arena_play(az_engine* e, int32_t n_games, int32_t record) {
 }
 
 int az_search(az_engine* e, int32_t agent, const az_state* st, int32_t player, int32_t* best, float* child_visits) {
-  if (agent < 0 || agent > 1 || !st || !st->board) return AZ_ERR_INVALID;
+  if (agent < 0 || agent > 1 || !st || !st->board || st->n_hist < 0 || (st->n_hist > 0 && !st->hist)) return AZ_ERR_INVALID;
+  if (st->n_hist > 8 && !(e->d.game.kind == AZ_GAME_WQ && (e->d.flags & AZ_FLAG_WQ_COMPLETE))) return AZ_ERR_INVALID;
   if (e->in_play) { e->err = "az_search during a running arena"; return AZ_ERR_STATE; }
   if (!e->inferers[agent]) { e->err = "agent has no inferer"; return AZ_ERR_STATE; }
   GUARD_BEGIN

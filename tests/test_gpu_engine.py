@@ -785,7 +785,7 @@ def test_wq_complete_game_engine_vs_pyref(engine_lib):
 
 
 def test_wq_superko_external_engine_vs_pyref(engine_lib):
-    """Positional superko on caller-owned positions (az_state's <= 8 earlier boards): the device's legal set against the
+    """Positional superko on caller-owned positions (az_state's earlier boards, up to 14 here): the device's legal set against the
     Python restatement, 160 positions with planted repetitions (capturing and non-capturing)."""
     from tests.test_oracle_rules_pyref import _superko_external_vs_pyref
     sk = sum(_superko_external_vs_pyref(engine_lib, size, seed, 40) for size, seed in ((3, 1), (5, 2), (7, 3), (9, 4)))

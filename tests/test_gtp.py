@@ -37,7 +37,7 @@ def test_gtp_basics_capture_ko_undo(oracle):
     assert g.kos[-1] == 2 * 5 + 2
     _ok(g, "play b pass"); _ok(g, "play w pass")
     assert g.kos[-1] == -1 and g.handle("play b C3")[0].startswith("? illegal")
-    _, visits = g.engine.search(0, g.board, K.BLACK, K.BLACK, move_number=len(g.moves), passes=0, hist=g.boards[-8:],
+    _, visits = g.engine.search(0, g.board, K.BLACK, K.BLACK, move_number=len(g.moves), passes=0, hist=g.boards,
                                 last_move=K.PASS, ko=-1)
     assert visits[2 * 5 + 2] == 0 and visits[4 * 5 + 4] > 0
     _ok(g, "play b E5")

@@ -161,7 +161,7 @@ def test_wq_complete_games_oracle_vs_pyref(oracle):
 
 
 def _superko_external_vs_pyref(lib, size, seed, rounds):
-    """Positional superko on external states: random positions handed to Agent.Search together with <= 8 earlier boards,
+    """Positional superko on external states: random positions handed to Agent.Search together with <= 14 earlier boards,
     some of which are exactly what a legal move (capturing or not) would recreate.  The root's children must be the
     restatement's legal set (+ Pass).  Returns how many points superko alone rejected."""
     cells = size * size
@@ -186,7 +186,7 @@ def _superko_external_vs_pyref(lib, size, seed, rounds):
                 for q in captured:
                     after[q] = 0
                 results.append(after)
-        n_hist = int(rng.integers(0, 9))
+        n_hist = int(rng.integers(0, 15))   # more than the encoder's 8: superko reads every board the caller hands over
         window = []
         for _ in range(n_hist):
             if results and rng.random() < 0.6:
