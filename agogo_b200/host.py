@@ -277,7 +277,7 @@ class MetaState:
         self._az, self._state, self._game_number = az, state, game_number
 
     def Name(self):
-        return self._az.conf.Name or "UNKNOWN GAME"  # arena.go:56-58
+        return self._az.Name()
 
     def Epoch(self):
         return self._az.epoch
@@ -285,12 +285,8 @@ class MetaState:
     def GameNumber(self):
         return self._game_number
 
-    def Score(self, player):  # arena.go:181-189: the agent's wins
-        if player == self._az.A.Player:
-            return float(self._az.A.Wins)
-        if player == self._az.B.Player:
-            return float(self._az.B.Wins)
-        return 0.0
+    def Score(self, player):  # arena.go:191: float64(a.game.Score(p)) of the position the encoder is shown
+        return self._az._game_score(self._state, player)
 
     def State(self):  # game.State getters of the running game: board, to_move, move_number, passes, ended, winner
         return self._state
@@ -306,7 +302,59 @@ def shuffle_rows(Xs, Pi, V, rng):
             V[[i, j]] = V[[j, i]]
 
 
-class AZ:
+class Arena:
+    """agogo.Arena (arena.go:18-233): the two agents, the game being played and the training bookkeeping; it fulfils
+    game.MetaState (Name / Epoch / GameNumber / Score / State), which is what an OutputEncoder is handed after every move.
+    Embedded in AZ as in the reference (agogo.go:22); MakeArena's two Dualers are the engine's nets 0 and 1."""
+    engine = None
+    epoch = 0        # training epoch (arena.go:33)
+    gameNumber = 0   # which game of the evaluation arena this is (arena.go:34, agogo.go:144)
+    name = "UNKNOWN GAME"  # arena.go:56-58
+    _last_state = None
+    oldCount = 0
+
+    def Epoch(self):  # arena.go:182
+        return self.epoch
+
+    def GameNumber(self):  # arena.go:185
+        return self.gameNumber
+
+    def Name(self):  # arena.go:188
+        return self.name
+
+    def _game_score(self, st, player):
+        """game.State.Score(p) of a position: mnk 1 / -2 / 0 (mnk.go:147-155), c4 1 / -1 / 0 (c4/game.go:75-84), wq as
+        implemented by Board.Score (the Game method panics in the reference) or the area score under the complete rules"""
+        _, _, sb, sw = self.engine.rules_status(np.asarray(st["board"], np.int32)[None], passes=[max(int(st.get("passes", 0)), 0)])
+        return float(sb[0]) if player == K.BLACK else (float(sw[0]) if player == K.WHITE else 0.0)
+
+    def Score(self, p):  # arena.go:191: the running game's Score(p)
+        if self._last_state is None:
+            raise RuntimeError("no game has been played")
+        return self._game_score(self._last_state, p)
+
+    def State(self):  # arena.go:194
+        return self._last_state
+
+    def Log(self, w):  # arena.go:197-203: the arena's log lines, then both agents' trees (MCTS.Log)
+        for line in self.log:
+            w.write("%s\n" % (line,))
+        for nm, t in (("A", 0), ("B", 1)):
+            w.write("\n%s:\n\n" % nm)
+            try:
+                rows = self.engine.tree_dump(0, t)
+                w.write("%d nodes; root children (move, visits): %s\n" % (len(rows), [(int(r[1]), int(r[2])) for r in rows if r[0] == 1][:16]))
+            except K.AZError:
+                w.write("(no tree)\n")
+
+    def newB(self, seed, killedA=False):  # arena.go:205-224: B gets a freshly initialised network
+        if killedA:
+            self.oldCount = 0
+        self.engine.net_init(1, seed)
+        self.oldCount += 1
+
+
+class AZ(Arena):
     """agogo.AZ (agogo.go:21-39): New / SelfPlay / Learn / Save / Load over one engine handle.
 
     Multi-GPU: one AZ per rank (`dist` = an initialised torch.distributed module or None).
@@ -346,6 +394,8 @@ class AZ:
         self.A, self.B = Agent(self, 0), Agent(self, 1)
         self.useDummy = True
         self.epoch = 0
+        self.gameNumber = 0
+        self.name = conf.Name or "UNKNOWN GAME"
         self.log = []
 
     def _init_engine_comm(self):
@@ -476,10 +526,12 @@ class AZ:
         self.A.Player = rec["a_player"]
         self.B.Player = K.WHITE if rec["a_player"] == K.BLACK else K.BLACK
         active = 1
+        self.gameNumber = game_number
         while active:
             active = e.arena_step()
+            self._last_state = e.game_state(0)
             if enc is not None:
-                enc.Encode(MetaState(self, e.game_state(0), game_number))
+                enc.Encode(MetaState(self, self._last_state, game_number))
         e.arena_finish()
         boards, pols, vals = e.examples(clear=True)
         ex = [Example(boards[i], pols[i], float(vals[i])) for i in range(len(vals))]
@@ -538,7 +590,8 @@ class AZ:
             promoted = bool(ratio > np.float32(self.conf.UpdateThreshold))  # NaN (0/0) never promotes
             if promoted:
                 e.net_copy(0, 1)  # A.NN = B.NN (agogo.go:161)
-            e.net_init(1, derive_seed(self.seed, 200 + ep))  # newB (arena.go:205-224)
+            self.gameNumber = arenaGames                           # agogo.go:144: the loop variable after the arena games
+            self.newB(derive_seed(self.seed, 200 + ep), promoted)  # arena.go:205-224
             self.log.append(dict(a=(float(aw), float(al), float(ad)), b=(float(bw), float(bl), float(bd)), n_examples=len(ex), batches=batches, promoted=promoted,
                                  first_cost=float(costs[0]), last_cost=float(costs[-1]),
                                  phase_seconds=dict(selfplay=round(t1 - t0, 3), gather=round(t2 - t1, 3), prepare=round(t3 - t2, 3),

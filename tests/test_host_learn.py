@@ -107,6 +107,7 @@ def test_arena_play_hooks(oracle):
         def Encode(self, ms):
             st = ms.State()
             self.calls.append((ms.Name(), ms.Epoch(), ms.GameNumber(), st["move_number"], int((st["board"] != 0).sum())))
+            self.scores = (ms.Score(K.BLACK), ms.Score(K.WHITE), st["winner"])
 
         def Flush(self):
             return None
@@ -126,6 +127,15 @@ def test_arena_play_hooks(oracle):
     assert len(enc.calls) == n_moves and [c[3] for c in enc.calls] == list(range(1, n_moves + 1))
     assert all(c[0] == "Tic Tac Toe" and c[2] == 3 for c in enc.calls) and [c[4] for c in enc.calls] == list(range(1, n_moves + 1))
     assert len(aug) == 2 * len(plain) and len(plain) > 0
+    # MetaState.Score / Arena.Score = the game's Score(p) (arena.go:191): mnk's 1 / -2 / 0 (mnk.go:147-155)
+    want = {K.NONE: (0.0, 0.0), K.BLACK: (1.0, -2.0), K.WHITE: (-2.0, 1.0)}[enc.scores[2]]
+    assert enc.scores[:2] == want and (az2.Score(K.BLACK), az2.Score(K.WHITE)) == want
+    assert isinstance(az2, host.Arena) and (az2.Name(), az2.Epoch(), az2.GameNumber()) == ("Tic Tac Toe", 0, 3)
+    assert az2.State()["move_number"] == n_moves
+    import io
+    buf = io.StringIO()
+    az2.Log(buf)
+    assert "A:" in buf.getvalue() and "B:" in buf.getvalue()
     for i, x in enumerate(plain):
         assert (aug[2 * i].Board == x.Board).all() and aug[2 * i].Value == x.Value
         assert (aug[2 * i + 1].Board.reshape(2, 3, 3) == x.Board.reshape(2, 3, 3)[:, :, ::-1]).all()
