@@ -27,6 +27,23 @@ def test_gob_primitives_match_the_documented_examples():
     assert b[1:3] == bytes([0xFF, 0x81])
 
 
+def test_type_descriptor_matches_the_documented_point_example():
+    """The one complete byte dump in the encoding/gob documentation: `type Point struct { X, Y int }`, value {22, 33}.  Our
+    stream writer's type-definition layer (message framing, negated id, wireType / CommonType nesting, field deltas) must
+    reproduce the 32 bytes of the descriptor and the 8 bytes of the value; the structType field list is spelled here, the
+    rest comes from the same `_define` every checkpoint type goes through."""
+    doc_type = bytes.fromhex("1f ff 81 03 01 01 05 50 6f 69 6e 74 01 ff 82 00 01 02 01 01 58 01 04 00 01 01 59 01 04 00 00 00".replace(" ", ""))
+    doc_value = bytes.fromhex("07 ff 82 01 2c 01 42 00".replace(" ", ""))
+    e = G.Encoder()
+    fields = G.enc_uint(1) + G.enc_uint(2)                                      # structType.Field (field 1), two entries
+    for nm in ("X", "Y"):
+        fields += G.enc_uint(1) + G.enc_string(nm) + G.enc_uint(1) + G.enc_int(G.T_INT) + G.enc_uint(0)   # fieldType{Name, Id}
+    tid = e._define(("struct", "Point"), "Point", G.WT_STRUCT, fields)
+    assert tid == 65 and e.bytes() == doc_type
+    e._message(G.enc_int(tid) + G.enc_uint(1) + G.enc_int(22) + G.enc_uint(1) + G.enc_int(33) + G.enc_uint(0))
+    assert e.bytes() == doc_type + doc_value
+
+
 def test_vectorised_float_encoding_equals_scalar():
     rng = np.random.default_rng(0)
     x = np.concatenate([rng.normal(size=500).astype(np.float32), np.array([0.0, -0.0, 1.0, 2.0, -2.0, 0.5, 1e-30, 3e38, np.float32(1) / 3], np.float32)])
