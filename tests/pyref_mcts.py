@@ -226,6 +226,60 @@ class WQ:  # game/wq/wq.go + game/wq/game.go.  What the reference leaves unfinis
         return True, (0 if ws == bs else (WHITE if ws > bs else BLACK))
 
 
+class WQComplete(WQ):  # AZ_FLAG_WQ_COMPLETE (OUR completion, include/agogo_b200.h): occupied points, suicide, simple ko, own
+    # single-point eyes and POSITIONAL SUPERKO are illegal; area scoring, komi added to White in Ended.  The rules themselves
+    # are the naive statement in tests/pyref_rules.py; this class only threads the ko point and the list of earlier
+    # positions (`historical`: every board a move was played from, inside a search as well) through the states.
+    complete = True
+
+    def __init__(self, size, komi):
+        super().__init__(size, komi)
+        self.ko = -1
+
+    def clone(self):
+        c = WQComplete(self.size, self.komi)
+        c.board, c.history, c.historical = list(self.board), list(self.history), list(self.historical)
+        c.next, c.n_passes, c.ko = self.next, self.n_passes, self.ko
+        return c
+
+    def _check(self, player, move):
+        from tests.pyref_rules import wq_complete_check
+        return wq_complete_check(self.board, self.size, player, move, self.ko, {tuple(b) for b in self.historical})
+
+    def check(self, player, move):
+        if move == PASS:
+            return True
+        if move >= len(self.board):
+            return False
+        return self._check(player, move)[0]
+
+    def apply(self, player, move):
+        ns = self.clone()
+        ns.historical.append(list(self.board))
+        if move == PASS:
+            ns.n_passes, ns.ko = self.n_passes + 1, -1
+        else:
+            ok, captured, ko = self._check(player, move)
+            if ok:
+                ns.board[move] = player
+                for q in captured:
+                    ns.board[q] = 0
+            ns.n_passes, ns.ko = 0, (ko if ok else -1)
+        ns.next = opponent(player)
+        ns.history.append((player, move))
+        return ns
+
+    def score(self, p):
+        from tests.pyref_rules import wq_area_score
+        return f32(wq_area_score(self.board, self.size, p))
+
+    def ended(self):
+        if self.n_passes < 2:
+            return False, 0
+        ws, bs = f32(self.score(WHITE) + f32(self.komi)), self.score(BLACK)
+        return True, (0 if ws == bs else (WHITE if ws > bs else BLACK))
+
+
 class Node:
     __slots__ = ("move", "visits", "status", "black", "min_psa", "score", "vloss")
 
@@ -723,6 +777,8 @@ def arena_play(new_game, make_mcts, coin, record=True, encoder=None, max_moves=0
         moves.append(best)
         cur ^= 1
         if pass_count >= 2:  # arena.go:134-136: `winner` keeps the value of the last loop condition (None)
+            if getattr(g, "complete", False):  # OUR complete-rules mode: two passes end the game and it is scored
+                _, winner = g.ended()
             break
         if max_moves and len(moves) >= max_moves:  # the repository's cap for games that never end
             break

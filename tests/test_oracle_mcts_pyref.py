@@ -240,3 +240,50 @@ def test_config_options_vs_python(oracle, name, conf):
             for t, want in enumerate(pair):
                 got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
                 assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (name, g, ply, t)
+
+
+@pytest.mark.parametrize("size,sims,cap,seed", [(3, 200, 40, 51), (4, 250, 60, 52), (5, 24, 60, 53)])
+def test_arena_go_complete_rules_vs_python(oracle, size, sims, cap, seed):
+    """AZ_FLAG_WQ_COMPLETE through the whole Arena, sampled play: ko, positional superko INSIDE the trees (a descent may not
+    recreate a position of the game or of its own path — the tiny boards with many simulations are where it fires), own-eye
+    and suicide bars, area-scored two-pass endings.  The oracle (group BFS, board list walked per candidate) against
+    pyref_mcts.WQComplete (trial move + set of position tuples): every tree after every ply, moves, winners, examples."""
+    G_ = 4
+    cells = size * size
+    d = K.make_desc(K.GAME_WQ, size, size, 0, komi=0.5, sims=sims, n_games=G_, seed=seed, max_moves=cap, flags=K.FLAG_WQ_COMPLETE,
+                    nn=H.tiny_nn(size, size, cells + 1, features=18))
+    conf = dict(random_count=cap, random_min_visits=0, random_temperature=1.0)
+    d.mcts.random_count, d.mcts.random_temperature = cap, 1.0
+    e = oracle.create(d)
+    e.set_inferer(0, K.INF_DUMMY, 1); e.set_inferer(1, K.INF_DUMMY, 2)
+    run = H.play_and_collect(e, G_)
+    state = P.derive_seed(seed, 0)
+    tree_seed = P.derive_seed(seed, 1)
+    rejected = [0]
+    from tests import pyref_rules as R
+    orig = R.wq_complete_check
+
+    def counting(board, sz, player, move, ko=-1, positions=None):  # how often superko alone decides
+        res = orig(board, sz, player, move, ko, positions)
+        if not res[0] and positions and orig(board, sz, player, move, ko)[0]:
+            rejected[0] += 1
+        return res
+
+    R.wq_complete_check = counting
+    try:
+        for g in range(G_):
+            state, r = P._splitmix(state)
+            def make(agent, gm):
+                return P.MCTS(gm, 1.0, sims, None, None, size, size, evaluator=P.dummy_evaluator(cells, 1 + agent), conf=conf,
+                              tree_seed=P.derive_seed(tree_seed, 2 * g + agent))
+            moves, winner, a_player, examples, dumps = P.arena_play(lambda: P.WQComplete(size, 0.5), make, r % 2, encoder=P.encode_wq18, max_moves=cap)
+            rec = run["records"][g]
+            assert list(rec["moves"]) == moves and rec["winner"] == winner and rec["n_examples"] == len(examples), (g, rec, moves, winner)
+            for ply, pair in enumerate(dumps):
+                for t, want in enumerate(pair):
+                    got = run["dumps"][ply][g][t].astype(np.int64) & 0xFFFFFFFF
+                    assert got.shape == want.shape and (got == (want & 0xFFFFFFFF)).all(), (g, ply, t)
+    finally:
+        R.wq_complete_check = orig
+    print("superko-only rejections inside the searches:", rejected[0])
+    assert rejected[0] >= (10 if size < 5 else 1)
