@@ -94,3 +94,26 @@ def test_agent_search_and_infer_on_a_state(oracle):
     # (the reference's own init overflows on a net this small — compare bits, NaNs included)
     assert pol.shape == (9,) and (pol.view(np.uint32) == p2[0].view(np.uint32)).all()
     assert np.float32(val).view(np.uint32) == v2[:1].view(np.uint32)[0]
+
+
+def test_shuffle_batch_in_place_like_the_reference(oracle):
+    """dualnet's TestShuffleBatch (dual_test.go:160-183): after a pass the three tensors are no longer in their original
+    order.  Here additionally: az_train shuffles the caller's buffers in place (as the reference shuffles its tensors,
+    meta.go:47), all three with the SAME row permutation, and that permutation is host.shuffle_rows' for the same seed
+    (Fisher-Yates with j = r.Intn(i+1), meta.go:57-102)."""
+    nn = dict(k=3, shared_layers=1, fc=8, batch_size=4, features=2, action_space=10)
+    e = oracle.create(K.make_desc(K.GAME_MNK, 3, 3, 3, sims=2, n_games=1, seed=1, nn=nn))
+    rng = np.random.default_rng(7)
+    n = 12
+    X = rng.uniform(150, 152, (n, 18)).astype(np.float32)
+    Pi = rng.uniform(0, 1, (n, 10)).astype(np.float32)
+    V = rng.uniform(0, 1, n).astype(np.float32)
+    X0, P0, V0 = X.copy(), Pi.copy(), V.copy()
+    e.train(1, X, Pi, V, 3, 1, lr=0.0, shuffle_seed=1234)
+    assert not (X == X0).all() and not (Pi == P0).all() and not (V == V0).all()
+    Xh, Ph, Vh = X0.copy(), P0.copy(), V0.copy()
+    Hh.shuffle_rows(Xh, Ph, Vh, Hh.Rng(1234))
+    assert (X == Xh).all() and (Pi == Ph).all() and (V == Vh).all()
+    perm = [int(np.flatnonzero((X0 == row).all(axis=1))[0]) for row in X]
+    assert sorted(perm) == list(range(n)) and (Pi == P0[perm]).all() and (V == V0[perm]).all()
+    e.close()
