@@ -153,6 +153,20 @@ class State:
     def MoveNumber(self):
         return self.move_number
 
+    def SetToMove(self, p):
+        self.to_move = p
+
+    def Clone(self):
+        import copy
+        return copy.deepcopy(self)
+
+    def Eq(self, other):  # wq/game.go:123-160 / mnk.go:191-206: side to move, counters, board, then the known history
+        def arr(x, w):
+            return np.zeros((0, w), np.int32) if x is None else np.asarray(x, np.int32).reshape(-1, w)
+        return (isinstance(other, State) and self.to_move == other.to_move and self.move_number == other.move_number
+                and self.passes == other.passes and np.array_equal(self.Board(), other.Board())
+                and np.array_equal(arr(self.moves, 2), arr(other.moves, 2)))
+
     def Historical(self, i):  # wq: the board before move i; the reference panics on a bad index too
         h = [] if self.hist is None else np.asarray(self.hist, np.int32).reshape(-1, self.Board().size)
         j = i - (self.move_number - len(h))

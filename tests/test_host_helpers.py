@@ -117,3 +117,16 @@ def test_shuffle_batch_in_place_like_the_reference(oracle):
     perm = [int(np.flatnonzero((X0 == row).all(axis=1))[0]) for row in X]
     assert sorted(perm) == list(range(n)) and (Pi == P0[perm]).all() and (V == V0[perm]).all()
     e.close()
+
+
+def test_state_clone_eq_like_the_reference():
+    """game/wq's TestGameBasics (game_test.go:9-20): a clone is equal; changing the side to move of the parent makes them
+    unequal."""
+    g = Hh.State(board=np.zeros(19 * 19, np.int32))
+    g2 = g.Clone()
+    assert g.Eq(g2), "Expected clones to be equal"
+    g.SetToMove(K.WHITE)
+    assert not g.Eq(g2), "Expected clones to be unequal after the parent object has changed"
+    g2.SetToMove(K.WHITE)
+    g2.board[3] = K.BLACK
+    assert not g.Eq(g2) and g.Board()[3] == 0     # the clone owns its board
