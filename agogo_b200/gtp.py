@@ -22,7 +22,12 @@ class GTPEngine:
     known = ["boardsize", "clear_board", "final_score", "genmove", "known_command", "komi", "list_commands", "name", "play",
              "protocol_version", "quit", "showboard", "undo", "version"]
 
-    def __init__(self, lib=None, size=9, komi=7.5, sims=100, nn=None, inferer=K.INF_DUMMY, params=None, seed=1):
+    def __init__(self, lib=None, size=9, komi=7.5, sims=100, nn=None, inferer=K.INF_DUMMY, params=None, seed=1,
+                 name=None, version=None):  # gtp.New(g, name, version, known) (internal/gtp/gtp.go:47-57)
+        if name is not None:
+            self.name = name
+        if version is not None:
+            self.version = version
         self.lib = lib if lib is not None else K.load()
         self.sims, self.nn, self.inferer, self.params, self.seed = sims, nn, inferer, params, seed
         self.komi = komi
@@ -203,10 +208,10 @@ class GTPEngine:
         ident = ""
         if parts[0].isdigit():
             ident, parts = parts[0], parts[1:]
-        cmd, args = parts[0], parts[1:]
+        cmd, args = parts[0].lower(), parts[1:]   # the reference lower-cases the line (gtp.go:111-113)
         fn = getattr(self, "cmd_" + cmd, None)
         if fn is None or cmd not in self.known:
-            return "?%s unknown command\n\n" % ident, False
+            return "?%s Unknown command \"%s\"\n\n" % (ident, cmd), False   # gtp.go:103
         try:
             return "=%s %s\n\n" % (ident, fn(args)), cmd == "quit"
         except (ValueError, IndexError) as ex:

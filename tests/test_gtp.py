@@ -66,3 +66,14 @@ def test_gtp_generated_game_is_legal(oracle):
                 board[q] = 0
         assert g.board.tolist() == board and g.kos[-1] == ko, ply
         player = 3 - player
+
+
+def test_gtp_general_like_the_reference(oracle):
+    """internal/gtp's Test_General (gtp_test.go:9-31), same engine arguments (name "xx", version "1"), same four exchanges,
+    same response text."""
+    e = GTPEngine(lib=oracle, size=5, sims=4, name="xx", version="1")
+    assert e.handle("version")[0] == "= 1\n\n"
+    assert e.handle("known_command hello")[0] == "= false\n\n"
+    assert e.handle("known_command name")[0] == "= true\n\n"
+    assert e.handle("completelyUnheardOfCommand xxx")[0] == "? Unknown command \"completelyunheardofcommand\"\n\n"
+    assert e.handle("name")[0] == "= xx\n\n"
