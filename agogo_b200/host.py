@@ -223,21 +223,12 @@ def WQEncoder(state):
 
 
 def RotateBoard(board, m, n):
-    """encoding_helper.go:80-108 (the building block of the commands' Augmenters): a quarter turn of a square board —
-    new[i][j] = old[j][m-1-i]; four of them are the identity (encoding_helper_test.go:10-58)."""
+    """encoding_helper.go:80-108 (the building block of the commands' Augmenters): a quarter turn, counter-clockwise, of a
+    square board given as a flat row-major slice — new[i][j] = old[j][m-1-i]; four of them are the identity
+    (encoding_helper_test.go:10-58).  Returns a new array; non-square boards are an error, as in the reference."""
     if m != n:
         raise ValueError("Cannot handle m %d, n %d. This function only takes square boards" % (m, n))
-    it = np.array(board, np.float32).reshape(m, n)  # a copy, like the reference's
-    for i in range(m // 2):
-        mi1 = m - i - 1
-        for j in range(i, mi1):
-            mj1 = m - j - 1
-            tmp = it[i][j]
-            it[i][j] = it[j][mi1]        # right to top
-            it[j][mi1] = it[mi1][mj1]    # bottom to right
-            it[mi1][mj1] = it[mj1][i]    # left to bottom
-            it[mj1][i] = tmp             # tmp is left
-    return it.reshape(-1)
+    return np.rot90(np.asarray(board, np.float32).reshape(m, n), 1).reshape(-1).copy()
 
 
 class Agent:
